@@ -1,0 +1,7 @@
+"""fqgrep_b200 -- B200-native (sm_100a) implementation of fqgrep's read-matching hot path.
+
+The product is libfqgrep_b200.so (C ABI, include/fqgrep_b200.h); this package is the thin host-side mirror of
+the reference's Matcher / MatcherFactory API over it.  There is no CPU matching path.
+"""
+from .matcher import (FIXED, FIXED_SET, INTERLEAVED, NAMES, PAIRED, REGEX, REGEX_SET, SINGLE, FqgrepError, Matcher,  # noqa: F401
+                      MatcherFactory, MatcherOpts, context, validate_fixed_pattern, write_selected)

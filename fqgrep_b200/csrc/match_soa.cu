@@ -1,0 +1,247 @@
+// match_soa.cu -- the read-matching kernel over SoA reads resident in HBM (sm_100a).
+//
+// Computes, for every read i, what the reference computes per record on a CPU pool thread:
+//     Matcher::read_match(&record)            /root/reference/src/lib/matcher.rs:164-175
+//  =  (f(seq) || (reverse_complement && f(rc(seq)))) != invert_match
+// where f is bases_match of FixedString / FixedStringSet / Regex / RegexSet (matcher.rs:203-205, 249-251,
+// 506-508, 569-571).  f and the reverse-complement branch are both folded into one host-compiled DFA
+// (regex_compile.cc / ac_build.cc), so a read is walked exactly once, left to right.
+//
+// Shape of the kernel (B200: 148 SMs, 227 KB smem/CTA, HBM-bound byte work, no tensor cores):
+//   * persistent grid, one CTA per SM, up to 32 warps; the DFA table lives in shared memory (tiers 0/1);
+//   * a warp owns a batch of 32 consecutive reads.  Their bytes are contiguous in HBM, so ONE bulk async copy
+//     (cp.async.bulk global->shared, the TMA engine, completion on an mbarrier) brings the 16 B-aligned span
+//     into the warp's private smem slot -- fully coalesced DRAM traffic, no register staging;
+//   * double-buffered per warp: the copy of batch k+1 is in flight while the 32 lanes walk batch k, one read
+//     per lane, out of shared memory (aligned 32-bit LDS + funnel shift, 4 bases per load);
+//   * epilogue: ballot -> one mask word per batch (optionally OR-ed with the mate's mask: the pair rule of
+//     src/main.rs:749-755), popcount accumulated per warp and added to the global count once.
+#include "device_common.cuh"
+#include "kernels.hpp"
+
+namespace fqg {
+namespace {
+
+// Shared memory is addressed through explicit 32-bit shared-window addresses + ld.shared so the hot loop is
+// LDS (not generic LD) whatever the optimiser can or cannot prove about pointer provenance.
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// State encodings (see kernels.hpp): tiers 0/1 keep the state as the BYTE offset of its table row, so one
+// 3-input add forms the LDS address; tier 2 keeps the row's entry index into the L2-resident table.
+template <int TIER>
+struct DfaView {
+    uint32_t tab;          // smem address of the table (tiers 0,1)
+    const uint32_t* t32;   // global (tier 2)
+    uint32_t cls;          // smem address of the byte->class LUT (tiers 1,2); tier 1 stores class*2
+    // `b2` is the input byte times two (tier 0) or the plain byte (tiers 1,2)
+    __device__ __forceinline__ uint32_t step(uint32_t st, uint32_t b) const {
+        if (TIER == 0) return lds_u16(tab + st + b);
+        if (TIER == 1) return lds_u16(tab + st + lds_u8(cls + b));
+        return __ldg(t32 + st + lds_u8(cls + b));
+    }
+    // byte k (0..3) of word w in the form step() wants
+    __device__ __forceinline__ uint32_t pick(uint32_t w, int k) const {
+        if (TIER == 0) return k == 0 ? (w << 1) & 0x1FEu : (w >> (8 * k - 1)) & 0x1FEu;
+        return k == 3 ? w >> 24 : (w >> (8 * k)) & 0xFFu;
+    }
+};
+
+// walk `len` bytes starting at shared address p (any alignment)
+template <int TIER>
+__device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st) {
+    const uint32_t sh = (p & 3u) * 8u;
+    uint32_t wp = p & ~3u;
+    uint32_t w0 = lds_u32_volatile(wp);
+    const uint32_t nw = len >> 2;
+#pragma unroll 2
+    for (uint32_t k = 0; k < nw; k++) {
+        wp += 4;
+        const uint32_t w1 = lds_u32_volatile(wp);
+        const uint32_t w = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+        st = d.step(st, d.pick(w, 0));
+        st = d.step(st, d.pick(w, 1));
+        st = d.step(st, d.pick(w, 2));
+        st = d.step(st, d.pick(w, 3));
+    }
+    const uint32_t rem = len & 3u;
+    if (rem) {
+        const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh);
+        st = d.step(st, d.pick(w, 0));
+        if (rem > 1) st = d.step(st, d.pick(w, 1));
+        if (rem > 2) st = d.step(st, d.pick(w, 2));
+    }
+    return st;
+}
+
+// fallback for a batch whose span does not fit the smem slot (very long reads): straight from global memory
+template <int TIER>
+__device__ __noinline__ uint32_t walk_global(const DfaView<TIER>& d, const uint8_t* p, uint32_t len, uint32_t st) {
+    for (uint32_t i = 0; i < len; i++) st = d.step(st, d.pick(__ldg(p + i), 0));
+    return st;
+}
+
+struct BatchDesc {
+    uint32_t s, e;        // this lane's read [s,e) as offsets into bases
+    uintptr_t src;        // 16 B-aligned global address the warp's copy starts at (warp-uniform)
+    uint32_t off;         // this lane's first byte relative to src
+    uint32_t bytes;       // bytes to copy (multiple of 16); 0 = nothing to copy (warp-uniform)
+    bool fits;            // warp-uniform: span fits the slot
+};
+
+template <int TIER, int STAGES>
+__global__ void __launch_bounds__(1024, 1)
+match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    // ---- smem carve-up: [table][class LUT 256][mbarriers][slots]
+    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem);
+    uint8_t* s_cls = smem + table_smem_bytes;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cls + 256);
+    uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_bar + 32 * STAGES);
+    s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
+
+    if (TIER <= 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(dfa.table);
+        uint4* dst = reinterpret_cast<uint4*>(s_tab);
+        for (uint32_t i = threadIdx.x; i < dfa.table_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (TIER >= 1)
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
+    if (lane == 0)
+        for (int s = 0; s < STAGES; s++) mbar_init(smem_addr(&s_bar[warp * STAGES + s]), 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    DfaView<TIER> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls)};
+    uint8_t* my_slots = s_slots + (size_t)warp * STAGES * slot_bytes;
+    const uint32_t n_batches = (b.n_reads + 31u) >> 5;
+    const uint32_t stride = gridDim.x * nwarps;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
+
+    auto load_desc = [&](uint32_t batch) -> BatchDesc {
+        BatchDesc d;
+        const uint32_t r = batch * 32u + lane;
+        const bool valid = batch < n_batches && r < b.n_reads;
+        d.s = valid ? __ldg(b.start + r) : 0u;
+        d.e = valid ? __ldg(b.end + r) : 0u;
+        if (d.e < d.s) d.e = d.s;
+        const uint32_t lo = __reduce_min_sync(kFullMask, valid ? d.s : 0xFFFFFFFFu);
+        const uint32_t hi = __reduce_max_sync(kFullMask, valid ? d.e : 0u);
+        if (hi > lo) {
+            const uintptr_t a_lo = (base + lo) & ~uintptr_t(15), a_hi = (base + hi + 15) & ~uintptr_t(15);
+            d.src = a_lo;
+            d.off = (uint32_t)(base + d.s - a_lo);
+            d.fits = (a_hi - a_lo) <= (uintptr_t)(slot_bytes - 16u);
+            d.bytes = d.fits ? (uint32_t)(a_hi - a_lo) : 0u;
+        } else {
+            d.src = base; d.off = 0; d.bytes = 0; d.fits = true;
+        }
+        return d;
+    };
+    auto issue = [&](const BatchDesc& d, uint32_t stage) {
+        if (d.fits && d.bytes && lane == 0) {
+            const uint32_t bar = smem_addr(&s_bar[warp * STAGES + stage]);
+            mbar_arrive_expect_tx(bar, d.bytes);
+            bulk_copy_g2s(smem_addr(my_slots + (size_t)stage * slot_bytes), reinterpret_cast<const void*>(d.src), d.bytes, bar);
+        }
+    };
+
+    uint32_t batch = blockIdx.x * nwarps + warp;
+    uint32_t phase_bits = 0, stage = 0;
+    unsigned long long local_count = 0;
+
+    BatchDesc cur = load_desc(batch);
+    issue(cur, 0);
+    BatchDesc nxt = load_desc(batch + stride);
+
+    for (; batch < n_batches; batch += stride) {
+        BatchDesc nn;
+        if (STAGES == 2) {
+            issue(nxt, stage ^ 1u);                 // descriptors were fetched one iteration ago
+            nn = load_desc(batch + 2u * stride);    // consumed next iteration
+        }
+        uint32_t st = dfa.start;
+        const uint32_t len = cur.e - cur.s;
+        if (cur.fits) {
+            if (cur.bytes) {
+                mbar_wait(smem_addr(&s_bar[warp * STAGES + stage]), (phase_bits >> stage) & 1u);
+                phase_bits ^= 1u << stage;
+            }
+            if (len) st = walk_shared<TIER>(view, smem_addr(my_slots) + stage * slot_bytes + cur.off, len, st);
+        } else if (len) {
+            st = walk_global<TIER>(view, b.bases + cur.s, len, st);
+        }
+        const uint32_t r = batch * 32u + lane;
+        const bool sel = (r < b.n_reads) && ((st >= dfa.accept_from) != (b.invert != 0));
+        uint32_t m = __ballot_sync(kFullMask, sel);
+        if (lane == 0) {
+            if (b.or_mask) m |= __ldg(b.or_mask + batch);
+            b.mask_out[batch] = m;
+            local_count += __popc(m);
+        }
+        __syncwarp();   // every lane is done reading the slot before it is refilled
+        if (STAGES == 2) {
+            cur = nxt; nxt = nn; stage ^= 1u;
+        } else {
+            cur = nxt;
+            issue(cur, 0);
+            nxt = load_desc(batch + 2u * stride);
+        }
+    }
+    if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
+}
+
+template <int TIER, int STAGES>
+cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
+    const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
+    uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
+    slot = (slot + 127u) & ~127u;
+    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : 0u;
+    const uint32_t fixed = table_smem + 256u + 32u * STAGES * 8u + 128u;
+    const uint32_t budget = 227u * 1024u;
+    if (fixed + STAGES * slot > budget) {
+        // slot too large for even one warp: shrink it; oversized batches take the global-memory path
+        slot = ((budget - fixed) / STAGES) & ~127u;
+    }
+    uint32_t warps = (budget - fixed) / (STAGES * slot);
+    if (warps > 32u) warps = 32u;
+    if (warps < 1u) warps = 1u;
+    const uint32_t smem = fixed + warps * STAGES * slot;
+    auto kern = match_soa_kernel<TIER, STAGES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t n_batches = (b.n_reads + 31u) / 32u;
+    uint32_t grid = (n_batches + warps - 1u) / warps;
+    if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, warps * 32u, smem, stream>>>(b, dfa, slot, table_smem);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
+    switch (dfa.tier) {
+        case 0: return launch_t<0, 2>(dfa, b, sm_count, stream);
+        case 1: return launch_t<1, 2>(dfa, b, sm_count, stream);
+        default: return launch_t<2, 2>(dfa, b, sm_count, stream);
+    }
+}
+
+}  // namespace fqg

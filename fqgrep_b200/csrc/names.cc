@@ -1,0 +1,35 @@
+// names.cc -- read-name set -> open-addressing table probed on the device.
+// Replaces AHashSet<Vec<u8>> (/root/reference/src/lib/matcher.rs:604, :632; filled at src/main.rs:258-271).
+// Membership is exact: the 64-bit hash only picks the slot, the kernel then compares length and bytes.
+#include "automata.hpp"
+#include "names_hash.h"
+
+#include <unordered_set>
+
+namespace fqg {
+
+uint64_t name_hash(const uint8_t* p, size_t n) { return fqg_name_hash(p, (uint32_t)n); }
+
+void build_name_table(const std::vector<std::string>& names, NameTable* out) {
+    std::unordered_set<std::string> uniq(names.begin(), names.end());
+    uint32_t slots = 16;
+    while (slots < uniq.size() * 2 + 2) slots <<= 1;
+    out->n_slots = slots;
+    out->slots.assign(slots, 0);
+    out->slot_off.assign(slots, 0);
+    out->pool.clear();
+    out->max_len = 0;
+    for (auto& s : uniq) {
+        uint64_t h = fqg_name_hash((const uint8_t*)s.data(), (uint32_t)s.size());
+        uint32_t i = (uint32_t)(h >> 32) & (slots - 1);
+        while (out->slots[i]) i = (i + 1) & (slots - 1);
+        // slot word: high 40 bits of the hash (never all-zero thanks to the |1<<63), low 24 bits = length
+        out->slots[i] = fqg_slot_word(h, (uint32_t)s.size());
+        out->slot_off[i] = (uint32_t)out->pool.size();
+        out->pool.insert(out->pool.end(), s.begin(), s.end());
+        if (s.size() > out->max_len) out->max_len = (uint32_t)s.size();
+    }
+    out->pool.resize(out->pool.size() + 8, 0);
+}
+
+}  // namespace fqg

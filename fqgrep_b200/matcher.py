@@ -1,0 +1,188 @@
+"""Host-side mirror of the reference's matcher API over the C ABI.
+
+Names follow /root/reference/src/lib/matcher.rs: MatcherOpts (:20-28), the Matcher trait's
+`opts / bases_match / read_match` (:150-193), MatcherFactory::new_matcher / new_query_name_matcher
+(:645-685), validate_fixed_pattern (:128-147).  The batch-level calls (`match_bases`, `grep_fastq`)
+are the seam the GPU needs: one call per batch instead of one virtual call per record
+(src/lib/seq_io.rs:314-326).  Everything executes on the device; there is no host matching path.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+
+FIXED, FIXED_SET, REGEX, REGEX_SET, NAMES = 0, 1, 2, 3, 4
+SINGLE, INTERLEAVED, PAIRED = 0, 1, 2
+INVERT_MATCH, REVERSE_COMPLEMENT = 1, 2
+
+
+class FqgrepError(Exception):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+        self.message = message
+
+    @property
+    def exit_code(self):
+        """What the reference binary would exit with (src/main.rs:295-311)."""
+        return {-2: 2, -4: 101, -5: 101}.get(self.code, 2)
+
+
+def _check(rc):
+    if rc != 0:
+        raise FqgrepError(rc, _ffi.last_error())
+
+
+@dataclass(frozen=True)
+class MatcherOpts:
+    invert_match: bool = False
+    reverse_complement: bool = False
+
+    def bits(self):
+        return (INVERT_MATCH if self.invert_match else 0) | (REVERSE_COMPLEMENT if self.reverse_complement else 0)
+
+
+def validate_fixed_pattern(pattern, protein=False):
+    """Raises FqgrepError with the reference's message when the pattern is not a valid fixed pattern."""
+    _check(_ffi.lib().fqg_validate_fixed_pattern(pattern.encode("utf-8"), int(protein)))
+
+
+def _b(x):
+    return x.encode("utf-8") if isinstance(x, str) else bytes(x)
+
+
+_contexts = {}
+
+
+def context(device=0):
+    """One device context per (process, GPU).  Raises when no CUDA device is usable."""
+    h = _contexts.get(device)
+    if h is None:
+        p = C.c_void_p()
+        _check(_ffi.lib().fqg_ctx_create(device, C.byref(p)))
+        h = _contexts[device] = p
+    return h
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Matcher:
+    """A compiled pattern set (`Box<dyn Matcher + Sync + Send>` in the reference)."""
+
+    def __init__(self, kind, patterns, opts=MatcherOpts()):
+        pats = [_b(p) for p in patterns]
+        blob = b"".join(pats)
+        offs = np.zeros(len(pats) + 1, dtype=np.uint64)
+        if pats:
+            offs[1:] = np.cumsum([len(p) for p in pats])
+        h = C.c_void_p()
+        _check(_ffi.lib().fqg_matcher_new(kind, blob, _ptr(offs), len(pats), opts.bits(), C.byref(h)))
+        self._h = h
+        self.kind = kind
+        self._opts = opts
+        self._pats = pats
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _ffi.lib().fqg_matcher_free(h)
+            self._h = None
+
+    def opts(self):
+        return self._opts
+
+    # -- introspection of the compiled automaton (CPU-side tests of the compilers)
+    def dfa_info(self):
+        info = _ffi.DfaInfo()
+        _check(_ffi.lib().fqg_matcher_dfa_info(self._h, C.byref(info)))
+        return info
+
+    def dfa_export(self):
+        info = self.dfa_info()
+        cls = np.zeros(256, dtype=np.uint8)
+        nxt = np.zeros(info.n_states * info.n_classes, dtype=np.uint32)
+        _check(_ffi.lib().fqg_matcher_dfa_export(self._h, _ptr(cls), _ptr(nxt)))
+        return cls, nxt.reshape(info.n_states, info.n_classes), info.start, info.accept_from
+
+    # -- batch seam
+    def match_bases(self, bases, offsets, device=0):
+        """read_match for every read of an SoA batch in host memory -> (bool array, n_selected)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.size - 1
+        mask = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+        cnt = C.c_uint64(0)
+        _check(_ffi.lib().fqg_match_bases_host(context(device), self._h, _ptr(bases), _ptr(offsets), n, _ptr(mask), C.byref(cnt)))
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return bits, cnt.value
+
+    def grep_fastq(self, r1, r2=None, mode=SINGLE, device=0, want_mask=True):
+        """Parse + match raw FASTQ bytes (host memory).  Returns dict(count, units, records, mask, result)."""
+        a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)
+        b = None if r2 is None else (r2 if isinstance(r2, np.ndarray) else np.frombuffer(bytes(r2), dtype=np.uint8))
+        words = a.size // 8 // 32 + 2
+        mask = np.zeros(words, dtype=np.uint32) if want_mask else None
+        res = _ffi.Result()
+        _check(_ffi.lib().fqg_grep_fastq_host(context(device), self._h, mode, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size,
+                                              _ptr(mask), words if want_mask else 0, C.byref(res)))
+        out = {"count": res.n_selected, "units": res.n_units, "records": res.n_records, "result": res}
+        if want_mask:
+            out["mask_words"] = mask
+            out["mask"] = np.unpackbits(mask.view(np.uint8), bitorder="little")[:res.n_units].astype(bool)
+        return out
+
+    # -- per-record convenience with the reference's names (1-record batches; tests and KATs only)
+    def bases_match(self, bases, device=0):
+        """Matcher::bases_match: pattern found != invert_match (matcher.rs:204,250,507,570); no reverse complement."""
+        if self._opts.reverse_complement:
+            fwd = Matcher(self.kind, self._pats, MatcherOpts(self._opts.invert_match, False))
+            return fwd.bases_match(bases, device)
+        b = np.frombuffer(_b(bases), dtype=np.uint8)
+        bits, _ = self.match_bases(b, np.array([0, b.size], dtype=np.uint64), device)
+        return bool(bits[0])
+
+    def read_match(self, seq, head=b"", device=0):
+        """Matcher::read_match (matcher.rs:164-175; QueryNameMatcher override :631-638)."""
+        if self.kind == NAMES:
+            s = _b(seq)
+            rec = b"@" + _b(head) + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n"
+            return bool(self.grep_fastq(rec)["mask"][0])
+        b = np.frombuffer(_b(seq), dtype=np.uint8)
+        bits, _ = self.match_bases(b, np.array([0, b.size], dtype=np.uint64), device)
+        return bool(bits[0])
+
+
+def write_selected(mask_words, r1, r2=None, mode=SINGLE, split=False):
+    """Selected records in input order, seq_io write_to form (src/main.rs:641-657, 682-727)."""
+    a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)
+    b = None if r2 is None else (r2 if isinstance(r2, np.ndarray) else np.frombuffer(bytes(r2), dtype=np.uint8))
+    cap = a.size + (0 if b is None else b.size) + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    out2 = np.zeros(cap, dtype=np.uint8) if split else None
+    n1, n2 = C.c_size_t(0), C.c_size_t(0)
+    mw = np.ascontiguousarray(mask_words, dtype=np.uint32)
+    _check(_ffi.lib().fqg_write_selected(mode, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size, _ptr(mw), _ptr(out), C.byref(n1),
+                                         _ptr(out2), C.byref(n2)))
+    if split:
+        return out[:n1.value].tobytes(), out2[:n2.value].tobytes()
+    return out[:n1.value].tobytes()
+
+
+class MatcherFactory:
+    """MatcherFactory of the reference (matcher.rs:641-686); the bitmask variants are out of scope."""
+
+    @staticmethod
+    def new_matcher(pattern, fixed_strings, regexp, bitencs=None, match_opts=MatcherOpts()):
+        if bitencs is not None:
+            raise FqgrepError(-1, "--iupac bit-mask matchers are not part of the B200 hot path yet")
+        if pattern is not None:
+            return Matcher(FIXED if fixed_strings else REGEX, [pattern], match_opts)
+        return Matcher(FIXED_SET if fixed_strings else REGEX_SET, list(regexp), match_opts)
+
+    @staticmethod
+    def new_query_name_matcher(query_names, match_opts=MatcherOpts()):
+        return Matcher(NAMES, sorted(_b(n) for n in query_names), match_opts)

@@ -1,0 +1,224 @@
+"""CPU tests of the product's host compilers (regex -> DFA, Aho-Corasick -> DFA) through the C ABI:
+the exported tables are walked by a test-side simulator and compared with the oracle, the reference's
+golden vectors, and Python's `re` as a third, independent implementation.  No compute call needs a GPU."""
+import random
+import re
+
+import numpy as np
+import pytest
+
+import fqgrep_b200 as F
+from oracle import oracle as O
+from tests import synth
+from tests.dfa_sim import run_dfa, run_dfa_soa
+
+
+def opts(inv, rc):
+    return F.MatcherOpts(invert_match=inv, reverse_complement=rc)
+
+
+def test_library_exports_every_declared_symbol():
+    import os
+    from fqgrep_b200 import _ffi
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "fqgrep_b200.h")).read()
+    declared = set(re.findall(r"\b(fqg_[a-z_0-9]+)\s*\(", hdr))
+    L = _ffi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_ffi.SYMBOLS)
+    assert b"sm_100a" in L.fqg_version()
+
+
+def test_kat_fixed(kat):
+    for rc, pat, seq, exp in kat["fixed_string"]["cases"]:
+        for inv in (False, True):
+            m = F.MatcherFactory.new_matcher(pat, True, [], None, opts(inv, rc))
+            assert run_dfa(m, [seq])[0] == (exp != inv)
+    for pat, seq, fwd, rcv in kat["rc_special"]["cases"]:
+        assert run_dfa(F.Matcher(F.FIXED, [pat], opts(False, False)), [seq])[0] == fwd
+        assert run_dfa(F.Matcher(F.FIXED, [pat], opts(False, True)), [seq])[0] == rcv
+
+
+def test_kat_fixed_set(kat):
+    for rc, pats, seq, exp in kat["fixed_string_set"]["cases"]:
+        for inv in (False, True):
+            m = F.MatcherFactory.new_matcher(None, True, pats, None, opts(inv, rc))
+            assert run_dfa(m, [seq])[0] == (exp != inv)
+
+
+def test_kat_regex(kat):
+    for rc, pat, seq, exp in kat["regex"]["cases"]:
+        for inv in (False, True):
+            m = F.MatcherFactory.new_matcher(pat, False, [], None, opts(inv, rc))
+            assert run_dfa(m, [seq])[0] == (exp != inv), (rc, pat, seq, inv)
+
+
+def test_kat_regex_set(kat):
+    for rc, pats, seq, exp in kat["regex_set"]["cases"]:
+        for inv in (False, True):
+            m = F.MatcherFactory.new_matcher(None, False, pats, None, opts(inv, rc))
+            assert run_dfa(m, [seq])[0] == (exp != inv), (rc, pats, seq, inv)
+
+
+def test_kat_validate_fixed(kat):
+    v = kat["validate_fixed"]
+    for p, prot in v["ok"]:
+        F.validate_fixed_pattern(p, prot)
+    for p, prot, msg in v["err"]:
+        with pytest.raises(F.FqgrepError) as e:
+            F.validate_fixed_pattern(p, prot)
+        assert e.value.message == msg and e.value.exit_code == 2
+    for p, prot, sub in v["err_contains"]:
+        with pytest.raises(F.FqgrepError) as e:
+            F.validate_fixed_pattern(p, prot)
+        assert sub in e.value.message
+
+
+def test_invalid_regex_message():
+    with pytest.raises(F.FqgrepError) as e:
+        F.MatcherFactory.new_matcher("*", False, [])
+    assert e.value.message.startswith("Invalid regular expression: '*'") and e.value.exit_code == 2
+    for bad in ["(", "a)", "[a", "a{2", "a{3,2}", r"\1", "(?=a)", "(?<!a)b", r"\p{Greek}", r"\q", "a{", "(?P<1>a)", "(?z)"]:
+        with pytest.raises(F.FqgrepError):
+            F.Matcher(F.REGEX, [bad])
+        with pytest.raises(O.OracleError):
+            O.Matcher(O.REGEX, [bad])
+
+
+BASELINE_REGEXES = ["GACGAGATTA", "GACGTGATTA", "AC[GT]{3}TT(A|G)CA"]
+
+SYNTAX_CASES = [
+    r"A.A", r"^A", r"T$", r"^ACGT$", r"^$", r"", r"A|", r"(|A)C", r"A*", r"A+C", r"AC?G", r"A{3}", r"A{2,}", r"A{1,3}C", r"(AC){2}G",
+    r"[ACG]T", r"[^A]C", r"[A-C]G", r"[^A-C]", r"[[:alpha:]]N", r"[[:^upper:]]", r"\dA", r"\w+", r"\W", r"\s", r"\S{4}", r"A\b", r"\bA", r"\BA",
+    r"(?i)acgt", r"(?i:a)C", r"a(?i)c", r"(?x) A C  # comment", r"(?s).", r".", r"\x41C", r"\x{41}C", r"\u0041", r"A\.C", r"\.", r"\\",
+    r"[A&&[^C]]", r"[A-G&&[^C-F]]", r"[A-Z--[C-X]]", r"[AC~~CG]", r"[\]A]", r"[]A]", r"[A\-C]", r"[-A]", r"[A-]", r"(?P<n>AC)G", r"(?<n>AC)G", r"(?:AC)+G",
+    r"A*?C", r"A+?C", r"A??C", r"A{2,3}?C", r"(A|C|G)(A|T)", r"(A*)*C", r"(A|AA)+$", r"^(A|C)*$", r"\AAC", r"AC\z", r"(?m)^A", r"(?m)A$",
+    r"\b{start}A", r"A\b{end}", r"\<A", r"A\>", r"\b{start-half}A", r"A\b{end-half}", r"[\d\s]", r"[^\d]", r"[\w&&[^_]]", r"(?-u:\xFF)", r"(?-u)[^A]",
+    r"é", r"[é]", r"[^é]", r"[α-ω]", r"\u{1F600}", r"(?i)k", r"(?i)s", r"(?i)[k]", r"}", r"]", r"a{,3}" if False else r"A{0}C", r"(){3}", r"^*A",
+]
+
+
+def _haystacks(rng, n=400):
+    alph = ["ACGT", "ACGTN", "ACGTacgt", "AC", "ACGT_ 09\n\t", "ACGTkKsS"]
+    hs = ["", "A", "C", "AC", "ACGT", "AAAA", "N"]
+    for _ in range(n):
+        a = rng.choice(alph)
+        hs.append("".join(rng.choice(a) for _ in range(rng.randint(0, 24))))
+    return hs
+
+
+def test_regex_dfa_vs_oracle_syntax_surface():
+    rng = random.Random(1)
+    hs = _haystacks(rng) + ["é", "aé", "\u212a", "\u017f", "αβγ", "😀", "A\u00e9C"]
+    hb = [h.encode("utf-8") for h in hs] + [b"\xff", b"A\xffC", b"\xc3", b"\xe2\x84"]
+    for pat in SYNTAX_CASES:
+        for rc in (False, True):
+            m = F.Matcher(F.REGEX, [pat], opts(False, rc))
+            o = O.Matcher(O.REGEX, [pat], False, rc)
+            got = run_dfa(m, hb)
+            exp = [o.read_match(h) for h in hb]
+            bad = [h for h, g, e in zip(hb, got, exp) if g != e]
+            assert not bad, (pat, rc, bad[:5])
+
+
+# patterns whose meaning is the same in Python `re` (bytes) and regex-syntax on ASCII haystacks
+PY_SAFE = [r"A.A", r"^A", r"^ACGT", r"A*C", r"A+C", r"AC?G", r"A{3}", r"A{2,}", r"A{1,3}C", r"(AC){2}G", r"[ACG]T", r"[^A]C", r"[A-C]G",
+           r"\dA", r"\w+", r"\W", r"\s", r"A\b", r"\bA", r"\BA", r"(?i)acgt", r"(A|C|G)(A|T)", r"(A*)*C", r"AC[GT]{3}TT(A|G)CA", r"G.{3,5}C",
+           r"(?:AC)+G", r"A|C{2}|GT", r"[^ACGT]", r"\AAC", r"T.....G", r"C+.T", r"A.+G"]
+
+
+def test_regex_vs_python_re():
+    rng = random.Random(2)
+    hs = [h.encode() for h in _haystacks(rng, 600)]
+    for pat in PY_SAFE:
+        pr = re.compile(pat.encode())
+        m = F.Matcher(F.REGEX, [pat])
+        o = O.Matcher(O.REGEX, [pat])
+        got = run_dfa(m, hs)
+        for h, g in zip(hs, got):
+            e = pr.search(h) is not None
+            assert g == e, (pat, h)
+            assert o.read_match(h) == e, ("oracle", pat, h)
+    # `$` differs from Python before a trailing newline: regex crate's $ is end-of-haystack only
+    assert run_dfa(F.Matcher(F.REGEX, ["A$"]), [b"A\n"])[0] is False or not run_dfa(F.Matcher(F.REGEX, ["A$"]), [b"A\n"])[0]
+    assert not O.Matcher(O.REGEX, ["A$"]).read_match(b"A\n")
+
+
+def test_random_regex_differential():
+    rng = random.Random(3)
+    atoms = ["A", "C", "G", "T", "N", ".", "[AC]", "[^G]", "[ACGT]", "(A|T)", "(CG|GC)", "^", "$", r"\b"]
+    quants = ["", "", "", "*", "+", "?", "{2}", "{1,2}", "{0,1}"]
+    hs = [h.encode() for h in _haystacks(rng, 300)]
+    for _ in range(150):
+        k = rng.randint(1, 5)
+        pat = "".join(rng.choice(atoms) + rng.choice(quants) for _ in range(k))
+        if rng.random() < 0.3:
+            pat = pat + "|" + "".join(rng.choice(atoms[:9]) for _ in range(rng.randint(1, 4)))
+        for rc, inv in ((False, False), (True, False), (True, True)):
+            try:
+                o = O.Matcher(O.REGEX_SET, [pat], inv, rc)
+            except O.OracleError:
+                with pytest.raises(F.FqgrepError):
+                    F.Matcher(F.REGEX_SET, [pat], opts(inv, rc))
+                continue
+            m = F.Matcher(F.REGEX_SET, [pat], opts(inv, rc))
+            got = run_dfa(m, hs)
+            for h, g in zip(hs, got):
+                assert g == o.read_match(h), (pat, rc, inv, h)
+
+
+def test_literal_sets_vs_oracle():
+    rng = random.Random(4)
+    hs = [h.encode() for h in _haystacks(rng, 500)]
+    for _ in range(60):
+        pats = ["".join(rng.choice("ACGTN") for _ in range(rng.randint(0 if rng.random() < 0.05 else 1, 7))) for _ in range(rng.randint(1, 6))]
+        for rc, inv in ((False, False), (True, False), (False, True), (True, True)):
+            m = F.Matcher(F.FIXED_SET, pats, opts(inv, rc))
+            o = O.Matcher(O.FIXED_SET, pats, inv, rc)
+            got = run_dfa(m, hs)
+            for h, g in zip(hs, got):
+                assert g == o.read_match(h), (pats, rc, inv, h)
+            # the reference's own property: FixedString == Regex on literal patterns (matcher.rs:1391-1486)
+            if all(pats):
+                r = F.Matcher(F.REGEX_SET, pats, opts(inv, rc))
+                assert run_dfa(r, hs) == got
+
+
+@pytest.mark.parametrize("name,kind,pats,inv,rc", [
+    ("cfg1_literal_regex", F.REGEX, ["GACGAGATTA"], False, False),
+    ("cfg1_fixed", F.FIXED, ["GACGAGATTA"], False, False),
+    ("cfg2_two_regex_rc", F.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], False, True),
+    ("cfg4_class_regex_invert", F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, False),
+])
+def test_baseline_configs_on_synthetic_reads(name, kind, pats, inv, rc):
+    n = 20000
+    mat = synth.bases(n, seed=1)
+    lit = ["GACGAGATTA", "GACGTGATTA", "ACGTGTTACA"]
+    planted = synth.plant(mat, lit, rate=0.01)
+    assert 100 < planted.size < 300
+    bases, offs = synth.soa(mat)
+    m = F.Matcher(kind, pats, opts(inv, rc))
+    got = run_dfa_soa(m, bases, offs)
+    cnt, flags = O.Matcher(kind, pats, inv, rc).match_soa(bases, offs, threads=4)
+    assert (got == (flags != 0)).all()
+    assert 0 < cnt < n
+
+
+def test_large_literal_set_aho_corasick():
+    rng = np.random.default_rng(7)
+    pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(10000)]
+    m = F.Matcher(F.FIXED_SET, pats, opts(False, True))
+    info = m.dfa_info()
+    assert info.tier == 2 and info.n_states > 100000
+    n = 3000
+    mat = synth.bases(n, seed=5)
+    synth.plant(mat, pats[:50], rate=0.05)
+    bases, offs = synth.soa(mat)
+    got = run_dfa_soa(m, bases, offs)
+    cnt, flags = O.Matcher(O.FIXED_SET, pats[:50], False, True).match_soa(bases, offs, threads=4)
+    # every read the 50-pattern oracle selects must be selected by the 10k set; spot-check the rest exactly
+    assert (got[flags != 0]).all()
+    full = O.Matcher(O.FIXED_SET, pats, False, True)
+    idx = rng.integers(0, n, 200)
+    for i in idx:
+        assert got[i] == full.read_match(bytes(mat[i]))

@@ -1,0 +1,158 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the reference's
+golden vectors.  Bit-exact (integer / byte work): the bar is equality of every selection bit and of --count."""
+import random
+
+import numpy as np
+import pytest
+
+import fqgrep_b200 as F
+from oracle import oracle as O
+from tests import synth
+from tests.fq_util import soa
+
+pytestmark = pytest.mark.gpu
+
+
+def opts(inv, rc):
+    return F.MatcherOpts(invert_match=inv, reverse_complement=rc)
+
+
+def check(kind, pats, inv, rc, bases, offs):
+    m = F.Matcher(kind, pats, opts(inv, rc))
+    bits, cnt = m.match_bases(bases, offs)
+    ocnt, flags = O.Matcher(kind, pats, inv, rc).match_soa(bases, offs, threads=8)
+    bad = np.nonzero(bits != (flags != 0))[0]
+    assert bad.size == 0, (kind, pats[:3], inv, rc, bad[:10])
+    assert cnt == ocnt
+    return cnt
+
+
+def test_kat_all_matchers_on_gpu(kat):
+    for rc, pat, seq, exp in kat["fixed_string"]["cases"]:
+        for inv in (False, True):
+            assert F.MatcherFactory.new_matcher(pat, True, [], None, opts(inv, rc)).read_match(seq) == (exp != inv)
+    for rc, pats, seq, exp in kat["fixed_string_set"]["cases"]:
+        for inv in (False, True):
+            assert F.MatcherFactory.new_matcher(None, True, pats, None, opts(inv, rc)).read_match(seq) == (exp != inv)
+    for rc, pat, seq, exp in kat["regex"]["cases"]:
+        for inv in (False, True):
+            assert F.MatcherFactory.new_matcher(pat, False, [], None, opts(inv, rc)).read_match(seq) == (exp != inv)
+    for rc, pats, seq, exp in kat["regex_set"]["cases"]:
+        for inv in (False, True):
+            assert F.MatcherFactory.new_matcher(None, False, pats, None, opts(inv, rc)).read_match(seq) == (exp != inv)
+    for pat, seq, fwd, rcv in kat["rc_special"]["cases"]:
+        assert F.Matcher(F.FIXED, [pat], opts(False, False)).read_match(seq) == fwd
+        assert F.Matcher(F.FIXED, [pat], opts(False, True)).read_match(seq) == rcv
+
+
+@pytest.mark.parametrize("kind,pats,inv,rc", [
+    (F.REGEX, ["GACGAGATTA"], False, False),
+    (F.FIXED, ["GACGAGATTA"], False, False),
+    (F.FIXED, ["GACGAGATTA"], True, True),
+    (F.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], False, True),
+    (F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, False),
+    (F.REGEX_SET, ["^ACG", "TTT$", "G.{3,5}C{2}A"], False, True),
+])
+def test_baseline_configs_200k_reads(kind, pats, inv, rc):
+    n = 200_000
+    mat = synth.bases(n, seed=1)
+    synth.plant(mat, ["GACGAGATTA", "GACGTGATTA", "ACGTGTTACA"], rate=0.01)
+    bases, offs = synth.soa(mat)
+    cnt = check(kind, pats, inv, rc, bases, offs)
+    assert 0 < cnt < n
+
+
+def test_tail_batches_and_tiny_inputs():
+    mat = synth.bases(1000, seed=3)
+    synth.plant(mat, ["GACGAGATTA"], rate=0.05)
+    for n in (1, 2, 31, 32, 33, 63, 64, 65, 999):
+        bases, offs = synth.soa(mat[:n])
+        check(F.FIXED, ["GACGAGATTA"], False, True, bases, offs)
+        check(F.FIXED, ["GACGAGATTA"], True, False, bases, offs)
+
+
+def test_ragged_empty_and_unaligned_reads():
+    rng = random.Random(5)
+    seqs = []
+    for i in range(5000):
+        L = rng.choice([0, 0, 1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 33, 64, 100, 149, 150, 151, 255, 300])
+        seqs.append("".join(rng.choice("ACGTN") for _ in range(L)))
+    bases, offs = soa(seqs)
+    for kind, pats in ((F.FIXED_SET, ["ACG", "TTN", "GG"]), (F.REGEX_SET, ["^$", "^A.*T$", "N{2}"]), (F.REGEX, [""]), (F.FIXED, [""])):
+        for inv, rc in ((False, False), (True, True)):
+            check(kind, pats, inv, rc, bases, offs)
+
+
+def test_long_reads_take_the_global_memory_path():
+    rng = np.random.default_rng(11)
+    lens = [20000, 150, 150, 70000, 1, 0, 9000] + [150] * 100 + [30000]
+    seqs = [bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)]) for L in lens]
+    seqs[3] = seqs[3][:-10] + b"GACGAGATTA"
+    bases, offs = soa(seqs)
+    cnt = check(F.FIXED, ["GACGAGATTA"], False, False, bases, offs)
+    assert cnt >= 1
+
+
+def test_all_three_table_tiers():
+    mat = synth.bases(50_000, seed=9)
+    rng = np.random.default_rng(3)
+    small = ["ACGTAC", "TTTTT"]
+    medium = ["".join("ACGT"[i] for i in rng.integers(0, 4, 12)) for _ in range(200)]
+    large = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(10_000)]
+    synth.plant(mat, small + medium[:20] + large[:200], rate=0.05)
+    bases, offs = synth.soa(mat)
+    tiers = []
+    for pats in (small, medium, large):
+        m = F.Matcher(F.FIXED_SET, pats, opts(False, True))
+        tiers.append(m.dfa_info().tier)
+        cnt = check(F.FIXED_SET, pats, False, True, bases, offs)
+        assert cnt > 0
+    assert tiers == [0, 1, 2]
+
+
+def test_protein_alphabet(kat):
+    e = kat["e2e_protein"]
+    bases, offs = soa(e["reads"])
+    for fixed, pats, exp in e["cases"]:
+        m = F.Matcher(F.FIXED_SET if fixed else F.REGEX_SET, pats)
+        bits, cnt = m.match_bases(bases, offs)
+        assert [r for r, b in zip(e["reads"], bits) if b] == exp
+
+
+def test_device_resident_entry_with_pair_or_mask():
+    """fqg_match_bases_device with torch-owned HBM buffers, mate OR-mask and device-side count (main.rs:749-755)."""
+    import ctypes as C
+    import torch
+    from fqgrep_b200 import _ffi
+    n = 100_003
+    m1, m2 = synth.bases(n, seed=1), synth.bases(n, seed=2)
+    synth.plant(m1, ["GACGAGATTA"], rate=0.01, seed=5)
+    synth.plant(m2, ["GACGTGATTA"], rate=0.01, seed=6)
+    pats = ["GACGAGATTA", "GACGTGATTA"]
+    m = F.Matcher(F.REGEX_SET, pats, opts(False, True))
+    o = O.Matcher(O.REGEX_SET, pats, False, True)
+    dev = torch.device("cuda:0")
+    words = (n + 31) // 32
+    outs = []
+    mask1 = torch.zeros(words, dtype=torch.int32, device=dev)
+    mask2 = torch.zeros(words, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx = F.context(0)
+    for mat, mask, orm in ((m1, mask1, None), (m2, mask2, mask1)):
+        b, offs = synth.soa(mat)
+        tb = torch.zeros(b.size + 64, dtype=torch.uint8, device=dev)
+        tb[: b.size] = torch.from_numpy(b).to(dev)
+        to = torch.from_numpy(offs.astype(np.int64)).to(dev).to(torch.int32)
+        count.zero_()
+        torch.cuda.synchronize()
+        rc = _ffi.lib().fqg_match_bases_device(ctx, m._h, tb.data_ptr(), to.data_ptr(), to.data_ptr() + 4, n, mask.data_ptr(),
+                                               orm.data_ptr() if orm is not None else None, count.data_ptr(), 150,
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, _ffi.last_error()
+        torch.cuda.synchronize()
+        outs.append((tb, to))
+    f1 = o.match_soa(*synth.soa(m1), threads=8)[1] != 0
+    f2 = o.match_soa(*synth.soa(m2), threads=8)[1] != 0
+    got = np.unpackbits(mask2.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert (got == (f1 | f2)).all()
+    assert int(count.item()) == int((f1 | f2).sum())
