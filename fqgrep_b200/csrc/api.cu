@@ -295,7 +295,7 @@ int fqg_match_bases_device(fqg_ctx* c, const fqg_matcher* m, const uint8_t* d_ba
     if (rc) return rc;
     SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
                (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len};
-    CU_TRY(launch_match_soa(dd, b, c->sm_count, stream ? (cudaStream_t)stream : c->stream));
+    CU_TRY(launch_match_soa(dd, b, c->sm_count, (cudaStream_t)stream));
     g_launches++;
     return FQG_OK;
 }
@@ -348,7 +348,7 @@ int fqg_synth_reads_device(fqg_ctx* c, uint8_t* d_out, uint64_t n_reads, uint64_
                            void* stream) {
     if (!c || !d_out || read_len == 0) return fail(FQG_E_INVALID_ARG, "bad argument");
     CU_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     SynthParams p{};
     p.out = d_out; p.n_reads = n_reads; p.first = first_index; p.read_len = read_len; p.fastq = fastq ? 1u : 0u;
     p.seed = seed; p.plant_seed = plant_seed; p.n_plant = n_plant;

@@ -1,0 +1,465 @@
+// match_fastq.cu -- fused FASTQ parse + match kernel (sm_100a): raw FASTQ bytes in HBM are read ONCE.
+//
+// Replaces, in one pass, three stages of the reference:
+//   * the reader thread's record splitting (seq_io 0.3.4 fastq::Reader / RecordSet [third party], driven from
+//     /root/reference/src/lib/seq_io.rs:60-80, 149-198, 271-281): newline scan, 4-line record structure,
+//     '@' / '+' / equal-length validation, CR stripping;
+//   * the worker-pool loop calling Matcher::read_match per record (src/lib/seq_io.rs:314-326 ->
+//     src/main.rs:635-640 -> src/lib/matcher.rs:164-175), incl. QueryNameMatcher::read_match (:631-638);
+//   * the per-record `found` flag (src/main.rs:558-575, 635-657), emitted as one bit per record.
+//
+// Shape: the byte stream is cut into 16 KB tiles.  A CTA takes the next tile id from an atomic counter
+// (in-order acquisition), pulls tile + 2 KB of overlap into shared memory with one bulk async copy (TMA),
+// builds a newline bitmap with SIMD-within-register byte compares, and obtains the number of newlines
+// before its tile by a decoupled look-back over per-tile aggregates (single pass, no second read of HBM).
+// With the global line number known, every record that STARTS in the tile is handled by one thread:
+// the four line ends come from the bitmap, the sequence line is walked through the DFA straight out of
+// shared memory, and the selection bit is OR-ed into the global record bitmask.  Records that do not end
+// inside tile+overlap (reads longer than ~1 kb) fall back to a global-memory walk.
+#include "dfa_device.cuh"
+#include "kernels.hpp"
+#include "names_hash.h"
+
+namespace fqg {
+namespace {
+
+constexpr uint32_t kTile = 16384;
+constexpr uint32_t kOverlap = 2048;
+constexpr uint32_t kLoad = kTile + kOverlap;
+constexpr uint32_t kGroups = kLoad / 32;          // one bitmap word per 32 bytes
+constexpr uint32_t kListCap = kTile / 8;          // record starts per tile we can index (records >= 8 B on average)
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+enum : uint32_t { kErrInvalidStart = 1, kErrInvalidSep = 2, kErrUnequal = 3, kErrUnexpectedEnd = 4, kErrDensity = 5, kErrMaskOverflow = 6 };
+
+__device__ __forceinline__ void report(const FastqArgs& a, uint64_t pos, uint32_t code) {
+    atomicMin(a.err, (unsigned long long)((pos << 4) | code));
+}
+
+__device__ __forceinline__ uint4 lds_v4_volatile(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// 4 bytes -> 4 bits: bit i set iff byte i == '\n'.  Exact per-byte zero test (no borrow false positives).
+__device__ __forceinline__ uint32_t newline_nibble(uint32_t w) {
+    const uint32_t x = w ^ 0x0A0A0A0Au;
+    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where the byte is zero
+    return (z * 0x00204081u) >> 28;
+}
+
+struct NamesProbe {
+    NamesView nv;
+    // exact membership of id bytes [p, p+len) (shared memory) in the name set
+    __device__ bool contains_shared(uint32_t p, uint32_t len) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull ^ len;
+        for (uint32_t i = 0; i < len; i++) h = (h ^ lds_u8_volatile(p + i)) * 0x100000001B3ull;
+        h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+        const uint64_t want = fqg_slot_word(h, len);
+        uint32_t i = (uint32_t)(h >> 32) & nv.mask;
+        for (;;) {
+            const uint64_t s = __ldg(nv.slots + i);
+            if (s == 0) return false;
+            if (s == want) {
+                const uint8_t* q = nv.pool + __ldg(nv.slot_off + i);
+                uint32_t k = 0;
+                while (k < len && __ldg(q + k) == lds_u8_volatile(p + k)) k++;
+                if (k == len) return true;
+            }
+            i = (i + 1) & nv.mask;
+        }
+    }
+    __device__ bool contains_global(const uint8_t* p, uint32_t len) const {
+        uint64_t h = fqg_name_hash(p, len);
+        const uint64_t want = fqg_slot_word(h, len);
+        uint32_t i = (uint32_t)(h >> 32) & nv.mask;
+        for (;;) {
+            const uint64_t s = __ldg(nv.slots + i);
+            if (s == 0) return false;
+            if (s == want) {
+                const uint8_t* q = nv.pool + __ldg(nv.slot_off + i);
+                uint32_t k = 0;
+                while (k < len && __ldg(q + k) == p[k]) k++;
+                if (k == len) return true;
+            }
+            i = (i + 1) & nv.mask;
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t id_hash32_shared(uint32_t p, uint32_t len) {
+    uint32_t h = 0x811C9DC5u ^ len;
+    for (uint32_t i = 0; i < len; i++) h = (h ^ lds_u8_volatile(p + i)) * 0x01000193u;
+    return h ^ (h >> 15);
+}
+__device__ __forceinline__ uint32_t id_hash32_global(const uint8_t* p, uint32_t len) {
+    uint32_t h = 0x811C9DC5u ^ len;
+    for (uint32_t i = 0; i < len; i++) h = (h ^ p[i]) * 0x01000193u;
+    return h ^ (h >> 15);
+}
+
+// TIER 0..2: DFA tiers (see kernels.hpp); TIER 3: read-name lookup.
+template <int TIER>
+struct RecordEval {
+    DfaView<(TIER < 3 ? TIER : 0)> view;
+    NamesProbe names;
+    uint32_t start, accept_from;
+    bool invert;
+
+    // record fully in shared memory: s = '@' position, p0..p3 = the four line ends (shared-window addresses)
+    __device__ __forceinline__ bool eval_shared(uint32_t tile, uint32_t s, uint32_t p0, uint32_t p1, uint32_t seq_len, uint32_t* idh, bool want_idh) const {
+        uint32_t head_end = p0;
+        if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
+        uint32_t id_len = 0;
+        if (TIER == 3 || want_idh) {
+            while (s + 1 + id_len < head_end && lds_u8_volatile(tile + s + 1 + id_len) != ' ') id_len++;
+            if (want_idh) *idh = id_hash32_shared(tile + s + 1, id_len);
+        }
+        bool found;
+        if (TIER == 3) found = names.contains_shared(tile + s + 1, id_len);
+        else found = walk_shared(view, tile + p0 + 1, seq_len, start) >= accept_from;
+        return found != invert;
+    }
+    __device__ __noinline__ bool eval_global(const uint8_t* head, uint32_t head_len, const uint8_t* seq, uint32_t seq_len, uint32_t* idh, bool want_idh) const {
+        uint32_t id_len = 0;
+        if (TIER == 3 || want_idh) {
+            while (id_len < head_len && head[id_len] != ' ') id_len++;
+            if (want_idh) *idh = id_hash32_global(head, id_len);
+        }
+        bool found;
+        if (TIER == 3) found = names.contains_global(head, id_len);
+        else found = walk_global(view, seq, seq_len, start) >= accept_from;
+        return found != invert;
+    }
+};
+
+template <int TIER, int THREADS>
+__global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t kWarps = THREADS / 32;
+    constexpr uint32_t kGpt = (kGroups + THREADS - 1) / THREADS;   // contiguous groups per thread in the prefix pass
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    // ---- smem carve-up
+    uint8_t* s_tab = smem;
+    uint8_t* s_cls = smem + table_smem_bytes;
+    uint8_t* s_tile = s_cls + 256;                                          // kLoad + 32
+    uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);  // kGroups + 2
+    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);  // kGroups + 2
+    uint16_t* s_list = s_pre + kGroups + 2;                                  // kListCap
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_list + kListCap);       // warp sums [kWarps], tile id, flags
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 48);
+    unsigned long long* s_prefix = reinterpret_cast<unsigned long long*>(s_bar + 1);
+
+    if (TIER <= 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(dfa.table);
+        uint4* dst = reinterpret_cast<uint4*>(s_tab);
+        for (uint32_t i = tid; i < dfa.table_bytes / 16; i += THREADS) dst[i] = __ldg(src + i);
+    }
+    if (TIER == 1 || TIER == 2)
+        for (uint32_t i = tid; i < 256; i += THREADS) s_cls[i] = __ldg(dfa.byte_class + i);
+    if (tid == 0) mbar_init(smem_addr(s_bar), 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    RecordEval<TIER> ev;
+    ev.view.tab = smem_addr(s_tab);
+    ev.view.t32 = reinterpret_cast<const uint32_t*>(dfa.table);
+    ev.view.cls = smem_addr(s_cls);
+    ev.names.nv = a.names;
+    ev.start = dfa.start;
+    ev.accept_from = dfa.accept_from;
+    ev.invert = a.invert != 0;
+    const bool want_idh = a.id_hash != nullptr;
+
+    const uint32_t tile_sa = smem_addr(s_tile), bar = smem_addr(s_bar);
+    const unsigned long long lines_in = *a.lines_in;
+    uint32_t phase = 0;
+    unsigned long long local_count = 0;
+
+    for (;;) {
+        if (tid == 0) s_misc[40] = atomicAdd(a.tile_counter, 1u);
+        __syncthreads();
+        const uint32_t t = s_misc[40];
+        if (t >= a.tile_count) break;
+        const uint64_t T0 = (uint64_t)(a.tile_first + t) * kTile;
+        const uint64_t remaining = a.nbytes - T0;
+        const uint32_t avail = remaining < kLoad ? (uint32_t)remaining : kLoad;      // bytes of the stream in smem
+        const uint32_t region = remaining < kTile ? (uint32_t)remaining : kTile;    // bytes this tile owns
+        if (tid == 0) {
+            const uint32_t bytes = (avail + 15u) & ~15u;
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_copy_g2s(tile_sa, a.buf + T0, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        // ---- newline bitmap: one word per 32 bytes
+        for (uint32_t g = tid; g < kGroups + 2; g += THREADS) {
+            uint32_t bits = 0;
+            if (g * 32u < avail) {
+                const uint4 lo = lds_v4_volatile(tile_sa + g * 32u), hi = lds_v4_volatile(tile_sa + g * 32u + 16u);
+                bits = newline_nibble(lo.x) | (newline_nibble(lo.y) << 4) | (newline_nibble(lo.z) << 8) | (newline_nibble(lo.w) << 12) |
+                       (newline_nibble(hi.x) << 16) | (newline_nibble(hi.y) << 20) | (newline_nibble(hi.z) << 24) | (newline_nibble(hi.w) << 28);
+                if (g * 32u + 32u > avail) bits &= (1u << (avail - g * 32u)) - 1u;
+            }
+            s_bitmap[g] = bits;
+        }
+        __syncthreads();
+
+        // ---- exclusive prefix of newline counts per group (block scan; thread i owns groups [i*kGpt, (i+1)*kGpt))
+        uint32_t cnt[kGpt], mine = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kGpt; k++) {
+            const uint32_t g = tid * kGpt + k;
+            cnt[k] = g < kGroups ? __popc(s_bitmap[g]) : 0u;
+            mine += cnt[k];
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (uint32_t)d) incl += v;
+        }
+        if (lane == 31) s_misc[warp] = incl;
+        __syncthreads();
+        uint32_t warp_base = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kWarps; w++) if (w < warp) warp_base += s_misc[w];
+        uint32_t run = warp_base + incl - mine;
+#pragma unroll
+        for (uint32_t k = 0; k < kGpt; k++) {
+            const uint32_t g = tid * kGpt + k;
+            if (g <= kGroups) s_pre[g] = (uint16_t)run;
+            run += cnt[k];
+        }
+        __syncthreads();
+        const uint32_t agg = (region & 31u) == 0 ? s_pre[region >> 5] : s_pre[region >> 5] + __popc(s_bitmap[region >> 5]);   // newlines in [0, region)
+
+        // ---- decoupled look-back: newlines before this tile (within the launch)
+        if (warp == 0) {
+            unsigned long long excl = 0;
+            if (t > 0) {
+                if (lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
+                int32_t look = (int32_t)t - 1;
+                for (;;) {
+                    const int32_t idx = look - (int32_t)lane;
+                    unsigned long long st = (2ull << 62);   // tiles before the launch: prefix 0
+                    if (idx >= 0) {
+                        do { st = *reinterpret_cast<volatile unsigned long long*>(a.tile_state + idx); } while ((st >> 62) == 0);
+                    }
+                    const uint32_t has_prefix = __ballot_sync(kFullMask, (st >> 62) == 2);
+                    const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
+                    unsigned long long v = lane <= first ? (st & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+                    excl += v;
+                    if (has_prefix) break;
+                    look -= 32;
+                }
+            }
+            if (lane == 0) {
+                atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
+                *s_prefix = excl;
+                if (t == a.tile_count - 1) *a.lines_out = lines_in + excl + agg;
+            }
+        }
+        __syncthreads();
+        const unsigned long long Lt = lines_in + *s_prefix;    // global index of this tile's first newline
+
+        // ---- record starts in this tile -> s_list
+        const bool first_global = (a.tile_first + t) == 0;
+        const uint32_t extra = first_global ? 1u : 0u;
+        const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
+        const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
+        uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
+        if (T0 + region == a.nbytes && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
+        if (first_global && tid == 0) s_list[0] = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kGpt; k++) {
+            const uint32_t g = tid * kGpt + k;
+            if (g < kGroups && g * 32u < region) {
+                uint32_t bits = s_bitmap[g];
+                if (g * 32u + 32u > region) bits &= (1u << (region - g * 32u)) - 1u;
+                uint32_t j = s_pre[g];
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    if (j >= j0 && ((j - j0) & 3u) == 0) {
+                        const uint32_t k2 = ((j - j0) >> 2) + extra;
+                        if (k2 < kListCap) s_list[k2] = (uint16_t)(g * 32u + b + 1u);
+                    }
+                    j++;
+                }
+            }
+        }
+        if (n_list > kListCap) {
+            if (tid == 0) report(a, T0, kErrDensity);
+            n_list = kListCap;
+        }
+        __syncthreads();
+
+        // ---- one thread per record
+        const uint32_t n_groups_avail = (avail + 31u) >> 5;
+        auto next_nl = [&](uint32_t p) -> uint32_t {
+            uint32_t g = p >> 5;
+            if (g >= n_groups_avail) return kNone;
+            uint32_t w = s_bitmap[g] & (0xFFFFFFFFu << (p & 31u));
+            while (!w) {
+                if (++g >= n_groups_avail) return kNone;
+                w = s_bitmap[g];
+            }
+            return g * 32u + (uint32_t)__ffs(w) - 1u;
+        };
+        for (uint32_t k0 = warp * 32u; k0 < n_list; k0 += THREADS) {
+            const uint32_t k = k0 + lane;
+            const bool valid = k < n_list;
+            bool sel = false;
+            uint32_t idh = 0;
+            if (valid) {
+                const uint32_t s = s_list[k];
+                const uint32_t p0 = next_nl(s);
+                const uint32_t p1 = p0 == kNone ? kNone : next_nl(p0 + 1u);
+                const uint32_t p2 = p1 == kNone ? kNone : next_nl(p1 + 1u);
+                const uint32_t p3 = p2 == kNone ? kNone : next_nl(p2 + 1u);
+                if (p3 != kNone) {
+                    const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
+                    const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
+                    const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
+                    if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
+                    else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
+                    else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
+                    sel = ev.eval_shared(tile_sa, s, p0, p1, seq_len, &idh, want_idh);
+                } else {
+                    // record runs past tile+overlap (or the stream is truncated): walk it in global memory
+                    const uint8_t* base = a.buf;
+                    const uint64_t gs = T0 + s;
+                    uint64_t q[4];
+                    uint64_t p = gs;
+                    int found = 0;
+                    for (; found < 4 && p < a.nbytes; p++)
+                        if (base[p] == '\n') q[found++] = p;
+                    if (found < 4) report(a, gs, kErrUnexpectedEnd);
+                    else {
+                        const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
+                        const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
+                        const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
+                        const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
+                        if (base[gs] != '@') report(a, gs, kErrInvalidStart);
+                        else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
+                        else if (seq_len != qual_len) report(a, gs, kErrUnequal);
+                        sel = ev.eval_global(base + gs + 1, (uint32_t)(q[0] - gs - 1 - cr0), base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
+                    }
+                }
+            }
+            const unsigned long long R_w = R_base + k0;      // record number of lane 0
+            if (valid) {
+                if (R_base + k >= a.mask_bits) { report(a, T0, kErrMaskOverflow); sel = false; }
+                else if (want_idh) a.id_hash[R_base + k] = idh;
+            }
+            const uint32_t m = __ballot_sync(kFullMask, sel);
+            if (lane == 0 && m) {
+                const uint32_t sh = (uint32_t)(R_w & 31ull);
+                atomicOr(a.mask + (R_w >> 5), m << sh);
+                if (sh && (m >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, m >> (32u - sh));
+                local_count += __popc(m);
+            }
+        }
+        __syncthreads();   // tile, bitmap and list are free for the next iteration
+    }
+    if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
+}
+
+// pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747)
+__global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t n_words, const uint32_t* h1, const uint32_t* h2,
+                                     uint64_t n_records, unsigned long long* count, unsigned long long* id_mismatch) {
+    unsigned long long c = 0, bad = ~0ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = m1[i] | m2[i];
+        out[i] = m;
+        c += __popc(m);
+    }
+    if (h1 && h2)
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_records; i += (uint64_t)gridDim.x * blockDim.x)
+            if (h1[i] != h2[i] && i < bad) bad = i;
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFullMask, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+    if (bad != ~0ull) atomicMin(id_mismatch, bad);
+}
+
+// interleaved mates (records 2k, 2k+1 of one stream): unit k = bit 2k | bit 2k+1
+__global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uint64_t n_out_words, const uint32_t* h, uint64_t n_pairs,
+                                           unsigned long long* count, unsigned long long* id_mismatch) {
+    unsigned long long c = 0, bad = ~0ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_out_words; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = (uint64_t)m[2 * i] | ((uint64_t)m[2 * i + 1] << 32);
+        x = (x | (x >> 1)) & 0x5555555555555555ull;
+        x = (x | (x >> 1)) & 0x3333333333333333ull;
+        x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+        x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+        x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+        x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+        out[i] = (uint32_t)x;
+        c += __popcll(x);
+    }
+    if (h)
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x)
+            if (h[2 * i] != h[2 * i + 1] && i < bad) bad = i;
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFullMask, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+    if (bad != ~0ull) atomicMin(id_mismatch, bad);
+}
+
+template <int TIER>
+cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
+    constexpr int THREADS = 128;
+    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : 0u;
+    const uint32_t smem = table_smem + 256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u + kListCap * 2u + 48u * 4u + 8u + 8u + 128u;
+    auto kern = match_fastq_kernel<TIER, THREADS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)(sm_count * per_sm);
+    if (grid > a.tile_count) grid = a.tile_count;
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, THREADS, smem, stream>>>(a, dfa, table_smem);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+uint32_t fastq_tile_bytes() { return kTile; }
+uint32_t fastq_overlap_bytes() { return kOverlap; }
+
+cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs& a, int sm_count, cudaStream_t stream) {
+    if (names) return launch_fastq_t<3>(dfa, a, sm_count, stream);
+    switch (dfa.tier) {
+        case 0: return launch_fastq_t<0>(dfa, a, sm_count, stream);
+        case 1: return launch_fastq_t<1>(dfa, a, sm_count, stream);
+        default: return launch_fastq_t<2>(dfa, a, sm_count, stream);
+    }
+}
+
+cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t n_words, const uint32_t* h1, const uint32_t* h2,
+                                 uint64_t n_records, unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream) {
+    if (n_words == 0) return cudaSuccess;
+    combine_pairs_kernel<<<148 * 4, 256, 0, stream>>>(m1, m2, out, n_words, h1, h2, n_records, count, id_mismatch);
+    return cudaGetLastError();
+}
+cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t n_out_words, const uint32_t* h, uint64_t n_pairs,
+                                       unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream) {
+    if (n_out_words == 0) return cudaSuccess;
+    combine_interleaved_kernel<<<148 * 4, 256, 0, stream>>>(m, out, n_out_words, h, n_pairs, count, id_mismatch);
+    return cudaGetLastError();
+}
+
+}  // namespace fqg
