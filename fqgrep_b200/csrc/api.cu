@@ -66,6 +66,7 @@ struct fqg_ctx {
     void* h_pinned = nullptr;
     size_t h_cap = 0;
     cudaEvent_t ev[6] = {nullptr};
+    cudaEvent_t chunk_ev[8] = {nullptr};
     FastqDeviceState fq;
 };
 
@@ -142,6 +143,250 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
         out->n_states = m->dfa.n_states;
     }
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Raw-FASTQ pipeline shared by the host and the device entry points.
+//   host source  : chunked cudaMemcpyAsync on the copy stream into one device buffer; after each chunk the fused
+//                  kernel is launched (compute stream, event-ordered) over the tiles that are now complete, so copy
+//                  and compute overlap (the reference overlaps its reader thread and worker pool the same way,
+//                  src/lib/seq_io.rs:287-368).
+//   device source: one launch per stream.
+enum { S_BUF = 0, S_STATE = 1, S_COUNTERS = 2, S_MASK = 3, S_IDH = 4 };
+struct StreamPlan {
+    const uint8_t* src = nullptr;   // as given (host or device)
+    size_t n = 0;                   // bytes with trailing newlines stripped
+    const uint8_t* d = nullptr;     // device bytes
+    uint32_t tiles = 0;
+    unsigned long long* state = nullptr;
+    uint32_t* counters = nullptr;
+    uint32_t* mask = nullptr;
+    uint32_t* idh = nullptr;
+    uint64_t mask_bits = 0, idh_cap = 0, mask_words = 0;
+    size_t copied = 0;
+    uint32_t tiles_done = 0, launches = 0;
+};
+constexpr size_t kCopyChunk = 64ull << 20;
+constexpr uint32_t kMaxLaunches = 1u << 16;
+
+int fq_ensure(fqg_ctx* c, int stream_idx, int what, size_t bytes, void** out) {
+    int slot = stream_idx * 5 + what;
+    FastqDeviceState& f = c->fq;
+    if (f.cap[slot] < bytes) {
+        if (f.scratch[slot]) cudaFree(f.scratch[slot]);
+        f.scratch[slot] = nullptr;
+        f.cap[slot] = 0;
+        size_t want = bytes + bytes / 16 + 4096;
+        CU_TRY(cudaMalloc(&f.scratch[slot], want));
+        f.cap[slot] = want;
+    }
+    *out = f.scratch[slot];
+    return 0;
+}
+
+const char* fastq_err_name(unsigned code) {
+    switch (code) {
+        case 1: return "expected '@' at record start (InvalidStart)";
+        case 2: return "expected '+' separator line (InvalidSep)";
+        case 3: return "sequence and quality lengths differ (UnequalLengths)";
+        case 4: return "truncated record (UnexpectedEnd)";
+        case 5: return "records shorter than 8 bytes on average are not supported on the device path";
+        case 6: return "record bitmask capacity exceeded (records shorter than 8 bytes, or 16 bytes with pair id check)";
+    }
+    return "unknown";
+}
+
+int grep_fastq(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, bool on_device,
+               uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res, cudaStream_t user_stream) {
+    std::memset(res, 0, sizeof *res);
+    if (mode != FQG_SINGLE && mode != FQG_INTERLEAVED && mode != FQG_PAIRED) return fail(FQG_E_INVALID_ARG, "unknown mode");
+    if ((n1 && !r1) || (mode == FQG_PAIRED && n2 && !r2)) return fail(FQG_E_INVALID_ARG, "NULL input");
+    CU_TRY(cudaSetDevice(c->device));
+    DeviceDfa dd;
+    int rc = get_device_dfa(c, m, &dd);
+    if (rc) return rc;
+    const bool names = m->kind == FQG_NAMES;
+    NamesView nv;
+    if (names) {
+        std::lock_guard<std::mutex> lock(const_cast<fqg_matcher*>(m)->mu);
+        const DeviceTables& t = const_cast<fqg_matcher*>(m)->dev[c->device];
+        nv.slots = t.slots; nv.slot_off = t.slot_off; nv.pool = t.pool; nv.mask = m->names.n_slots - 1;
+    }
+    const int n_streams = mode == FQG_PAIRED ? 2 : 1;
+    const bool check_ids = mode != FQG_SINGLE;
+    cudaStream_t cs = on_device ? user_stream : c->stream;       // compute stream
+    cudaStream_t xs = c->copy_stream;                            // H2D stream (host sources)
+    const uint32_t kTile = fastq_tile_bytes(), kLoad = kTile + fastq_overlap_bytes();
+
+    StreamPlan sp[2];
+    sp[0].src = r1; sp[0].n = n1;
+    sp[1].src = r2; sp[1].n = n2;
+    for (int i = 0; i < n_streams; i++) {
+        StreamPlan& s = sp[i];
+        // strip trailing newline bytes (seq_io tolerates a missing final newline and trailing blank lines)
+        uint8_t tail[4096];
+        size_t n = s.n;
+        while (n) {
+            size_t k = n < sizeof tail ? n : sizeof tail;
+            if (on_device) CU_TRY(cudaMemcpy(tail, s.src + n - k, k, cudaMemcpyDeviceToHost));
+            else std::memcpy(tail, s.src + n - k, k);
+            size_t j = k;
+            while (j && (tail[j - 1] == '\n' || tail[j - 1] == '\r')) j--;
+            n -= k - j;
+            if (j) break;
+        }
+        s.n = n;
+        const uint64_t stream_len = n ? n + 1 : 0;
+        if (stream_len / kTile >= 0xFFFFFFF0ull) return fail(FQG_E_TOO_LARGE, "input stream too large");
+        s.tiles = (uint32_t)((stream_len + kTile - 1) / kTile);
+        s.mask_bits = n / 8 + 64;
+        s.mask_words = (s.mask_bits + 31) / 32 + 2;
+        s.idh_cap = check_ids ? n / 16 + 64 : 0;
+        void* p;
+        if (!on_device) {
+            if ((rc = fq_ensure(c, i, S_BUF, n + 64, &p))) return rc;
+            s.d = (const uint8_t*)p;
+        } else s.d = s.src;
+        if ((rc = fq_ensure(c, i, S_STATE, (size_t)s.tiles * 8 + 8, &p))) return rc;
+        s.state = (unsigned long long*)p;
+        if ((rc = fq_ensure(c, i, S_COUNTERS, kMaxLaunches * 4, &p))) return rc;
+        s.counters = (uint32_t*)p;
+        if ((rc = fq_ensure(c, i, S_MASK, s.mask_words * 4, &p))) return rc;
+        s.mask = (uint32_t*)p;
+        if (check_ids) {
+            if ((rc = fq_ensure(c, i, S_IDH, s.idh_cap * 4 + 16, &p))) return rc;
+            s.idh = (uint32_t*)p;
+        }
+    }
+    // control block: [0] err, [1] count, [2] id mismatch, [3] lines r1, [4] lines r2
+    void* p;
+    if ((rc = ensure_dev(c, 4, 64, &p))) return rc;
+    unsigned long long* ctl = (unsigned long long*)p;
+    void* d_units;
+    const uint64_t max_units_words = sp[0].mask_words;
+    if ((rc = ensure_dev(c, 5, max_units_words * 4 + 16, &d_units))) return rc;
+
+    const unsigned long long ctl_init[5] = {~0ull, 0ull, ~0ull, 0ull, 0ull};
+    CU_TRY(cudaEventRecord(c->ev[0], cs));
+    CU_TRY(cudaMemcpyAsync(ctl, ctl_init, sizeof ctl_init, cudaMemcpyHostToDevice, cs));
+    for (int i = 0; i < n_streams; i++) {
+        CU_TRY(cudaMemsetAsync(sp[i].state, 0, (size_t)sp[i].tiles * 8 + 8, cs));
+        CU_TRY(cudaMemsetAsync(sp[i].counters, 0, kMaxLaunches * 4, cs));
+        CU_TRY(cudaMemsetAsync(sp[i].mask, 0, sp[i].mask_words * 4, cs));
+    }
+
+    auto launch = [&](int i, uint32_t tile_end) -> int {
+        StreamPlan& s = sp[i];
+        if (tile_end <= s.tiles_done) return 0;
+        if (s.launches >= kMaxLaunches) return fail(FQG_E_TOO_LARGE, "too many launches for one stream");
+        FastqArgs a{};
+        a.buf = s.d; a.nbytes = s.n; a.virtual_final_nl = 1;
+        a.tile_first = s.tiles_done; a.tile_count = tile_end - s.tiles_done;
+        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.lines_out = ctl + 3 + i;
+        a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
+        a.count = mode == FQG_SINGLE ? ctl + 1 : nullptr;
+        a.err = ctl + 0;
+        a.invert = (m->opts & FQG_INVERT_MATCH) ? 1u : 0u;
+        a.names = nv;
+        CU_TRY(launch_match_fastq(dd, names, a, c->sm_count, cs));
+        g_launches++;
+        s.launches++;
+        s.tiles_done = tile_end;
+        return 0;
+    };
+
+    uint64_t h2d_bytes = 0;
+    if (on_device) {
+        for (int i = 0; i < n_streams; i++) if ((rc = launch(i, sp[i].tiles))) return rc;
+    } else {
+        // interleave the streams chunk by chunk so mates progress together
+        CU_TRY(cudaEventRecord(c->ev[1], xs));
+        bool more = true;
+        int ev_slot = 0;
+        while (more) {
+            more = false;
+            for (int i = 0; i < n_streams; i++) {
+                StreamPlan& s = sp[i];
+                if (s.copied >= s.n) continue;
+                size_t k = s.n - s.copied < kCopyChunk ? s.n - s.copied : kCopyChunk;
+                CU_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(s.d) + s.copied, s.src + s.copied, k, cudaMemcpyHostToDevice, xs));
+                s.copied += k;
+                h2d_bytes += k;
+                cudaEvent_t e = c->chunk_ev[ev_slot++ % 8];
+                CU_TRY(cudaEventRecord(e, xs));
+                CU_TRY(cudaStreamWaitEvent(cs, e, 0));
+                uint32_t ready = s.copied >= s.n ? s.tiles : (s.copied >= kLoad ? (uint32_t)((s.copied - kLoad) / kTile + 1) : 0u);
+                if ((rc = launch(i, ready))) return rc;
+                if (s.copied < s.n) more = true;
+            }
+        }
+        CU_TRY(cudaEventRecord(c->ev[2], xs));
+        for (int i = 0; i < n_streams; i++) if ((rc = launch(i, sp[i].tiles))) return rc;   // empty streams / leftovers
+    }
+
+    // ---- mates -> units (src/main.rs:749-755), id agreement (:741-747)
+    const uint32_t* unit_mask_dev = sp[0].mask;
+    if (mode == FQG_PAIRED) {
+        const uint64_t w = sp[0].mask_words < sp[1].mask_words ? sp[0].mask_words : sp[1].mask_words;
+        const uint64_t nrec = sp[0].idh_cap < sp[1].idh_cap ? sp[0].idh_cap : sp[1].idh_cap;
+        CU_TRY(launch_combine_pairs(sp[0].mask, sp[1].mask, (uint32_t*)d_units, w, sp[0].idh, sp[1].idh, nrec, ctl + 3, ctl + 4, ctl + 1, ctl + 2, cs));
+        g_launches++;
+        unit_mask_dev = (const uint32_t*)d_units;
+    } else if (mode == FQG_INTERLEAVED) {
+        CU_TRY(launch_combine_interleaved(sp[0].mask, (uint32_t*)d_units, sp[0].mask_words / 2, sp[0].idh, sp[0].idh_cap, ctl + 3, ctl + 1, ctl + 2, cs));
+        g_launches++;
+        unit_mask_dev = (const uint32_t*)d_units;
+    }
+    CU_TRY(cudaEventRecord(c->ev[3], cs));
+
+    unsigned long long h_ctl[5];
+    CU_TRY(cudaMemcpyAsync(h_ctl, ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, cs));
+    CU_TRY(cudaStreamSynchronize(cs));
+    uint64_t d2h_bytes = sizeof h_ctl;
+
+    if (h_ctl[0] != ~0ull) {
+        unsigned code = (unsigned)(h_ctl[0] & 15);
+        return fail(code >= 5 ? FQG_E_TOO_LARGE : FQG_E_FASTQ, std::string("FASTQ parse error at byte ") + std::to_string(h_ctl[0] >> 4) + ": " + fastq_err_name(code));
+    }
+    uint64_t lines[2] = {sp[0].n ? h_ctl[3] : 0, sp[1].n ? h_ctl[4] : 0};
+    for (int i = 0; i < n_streams; i++)
+        if (lines[i] % 4) return fail(FQG_E_FASTQ, "FASTQ parse error: truncated final record (UnexpectedEnd)");
+    const uint64_t rec1 = lines[0] / 4, rec2 = lines[1] / 4;
+    uint64_t units = rec1;
+    if (mode == FQG_PAIRED) {
+        if (rec1 != rec2) return fail(FQG_E_PAIR_MISMATCH, "FASTQ files out of sync: R1 has " + std::to_string(rec1) + " records, R2 has " + std::to_string(rec2));
+    } else if (mode == FQG_INTERLEAVED) {
+        if (rec1 % 2) return fail(FQG_E_FASTQ, "FASTQ file does not have an even number of records.");
+        units = rec1 / 2;
+    }
+    if (check_ids && h_ctl[2] != ~0ull) return fail(FQG_E_PAIR_MISMATCH, "Mismatching read pair! (pair " + std::to_string(h_ctl[2]) + ")");
+    res->n_records = rec1 + (mode == FQG_PAIRED ? rec2 : 0);
+    res->n_units = units;
+    res->n_selected = h_ctl[1];
+    if (unit_mask_out) {
+        const uint64_t need = (units + 31) / 32;
+        if (need > unit_mask_words) return fail(FQG_E_INVALID_ARG, "unit_mask_out too small: need " + std::to_string(need) + " words");
+        if (need) {
+            CU_TRY(cudaMemcpyAsync(unit_mask_out, unit_mask_dev, need * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
+            CU_TRY(cudaEventRecord(c->ev[4], cs));
+            CU_TRY(cudaStreamSynchronize(cs));
+            if (!on_device) d2h_bytes += need * 4;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
+            res->d2h_ms = ms;
+        }
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]);
+    res->kernel_ms = ms;
+    if (!on_device && h2d_bytes) {
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+        res->h2d_ms = ms;
+    }
+    res->h2d_bytes = h2d_bytes;
+    res->d2h_bytes = d2h_bytes;
+    return FQG_OK;
 }
 
 }  // namespace
@@ -256,6 +501,7 @@ int fqg_ctx_create(int device, fqg_ctx** out) {
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CU_TRY(cudaEventCreate(&ev));
+    for (auto& ev : c->chunk_ev) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     *out = c.release();
     return FQG_OK;
 }
@@ -268,6 +514,7 @@ void fqg_ctx_destroy(fqg_ctx* c) {
     for (auto& b : c->d_buf) cudaFree(b);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->chunk_ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -373,13 +620,13 @@ int fqg_synth_reads_device(fqg_ctx* c, uint8_t* d_out, uint64_t n_reads, uint64_
 int fqg_grep_fastq_device(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* d_r1, size_t n1, const uint8_t* d_r2, size_t n2,
                           uint32_t* d_unit_mask_out, size_t unit_mask_words, fqg_result* res, void* stream) {
     if (!c || !m || !res) return fail(FQG_E_INVALID_ARG, "NULL argument");
-    return fail(FQG_E_INVALID_ARG, "fqg_grep_fastq_device: not implemented in this build");
+    return grep_fastq(c, m, mode, d_r1, n1, d_r2, n2, true, d_unit_mask_out, unit_mask_words, res, (cudaStream_t)stream);
 }
 
 int fqg_grep_fastq_host(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2,
                         uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res) {
     if (!c || !m || !res) return fail(FQG_E_INVALID_ARG, "NULL argument");
-    return fail(FQG_E_INVALID_ARG, "fqg_grep_fastq_host: not implemented in this build");
+    return grep_fastq(c, m, mode, r1, n1, r2, n2, false, unit_mask_out, unit_mask_words, res, c->stream);
 }
 
 int fqg_write_selected(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* unit_mask, uint8_t* out,

@@ -8,8 +8,8 @@ namespace fqg {
 
 // Device-side scratch owned by a context for the raw-FASTQ path (filled in by fastq path code).
 struct FastqDeviceState {
-    void* scratch[8] = {nullptr};
-    size_t cap[8] = {0};
+    void* scratch[10] = {nullptr};
+    size_t cap[10] = {0};
 };
 void fastq_state_free(FastqDeviceState* s);
 

@@ -40,6 +40,39 @@ struct SoaBatch {
 // K3/K2/K1: per-read DFA walk over SoA reads (bases + start/end), bitmask + count epilogue (K5 fused).
 cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream);
 
+// ---- fused raw-FASTQ parse + match (match_fastq.cu)
+struct NamesView {
+    const uint64_t* slots = nullptr;
+    const uint32_t* slot_off = nullptr;
+    const uint8_t* pool = nullptr;
+    uint32_t mask = 0;     // n_slots - 1
+};
+struct FastqArgs {
+    const uint8_t* buf;            // device, readable 16 bytes past nbytes
+    uint64_t nbytes;               // stream bytes, trailing newlines stripped
+    uint32_t virtual_final_nl;     // 1: treat offset nbytes as a newline
+    uint32_t tile_first, tile_count;   // this launch handles global tiles [tile_first, tile_first + tile_count)
+    uint32_t* tile_counter;        // zeroed, one per launch
+    unsigned long long* tile_state;    // zeroed, one per global tile of the stream (look-back state)
+    unsigned long long* lines_out;     // total newline count, written by the stream's last tile
+    uint32_t* mask;                // zeroed record bitmask, bit = global record number
+    uint64_t mask_bits;
+    uint32_t* id_hash;             // optional, one per record (pair id check)
+    uint64_t id_hash_cap;
+    unsigned long long* count;     // optional
+    unsigned long long* err;       // min over (position << 4 | code), initialised to ~0
+    uint32_t invert;
+    NamesView names;
+};
+uint32_t fastq_tile_bytes();
+uint32_t fastq_overlap_bytes();
+cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
+                                 uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
+                                 unsigned long long* id_mismatch, cudaStream_t stream);
+cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const uint32_t* h, uint64_t idh_cap,
+                                       const unsigned long long* lines, unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream);
+
 // Synthetic benchmark input generator; see synth.cu.
 struct SynthParams {
     uint8_t* out;

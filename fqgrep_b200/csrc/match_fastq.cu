@@ -179,36 +179,42 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
     const bool want_idh = a.id_hash != nullptr;
 
     const uint32_t tile_sa = smem_addr(s_tile), bar = smem_addr(s_bar);
-    const unsigned long long lines_in = *a.lines_in;
+    // the stream always ends with a newline: a real one, or a virtual one at offset nbytes (missing final '\n')
+    const uint64_t stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
     for (;;) {
         if (tid == 0) s_misc[40] = atomicAdd(a.tile_counter, 1u);
         __syncthreads();
-        const uint32_t t = s_misc[40];
-        if (t >= a.tile_count) break;
-        const uint64_t T0 = (uint64_t)(a.tile_first + t) * kTile;
-        const uint64_t remaining = a.nbytes - T0;
-        const uint32_t avail = remaining < kLoad ? (uint32_t)remaining : kLoad;      // bytes of the stream in smem
-        const uint32_t region = remaining < kTile ? (uint32_t)remaining : kTile;    // bytes this tile owns
-        if (tid == 0) {
-            const uint32_t bytes = (avail + 15u) & ~15u;
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_copy_g2s(tile_sa, a.buf + T0, bytes, bar);
+        if (s_misc[40] >= a.tile_count) break;
+        const uint32_t t = a.tile_first + s_misc[40];                               // global tile id
+        const uint64_t T0 = (uint64_t)t * kTile;
+        const uint64_t remaining = stream_len - T0;
+        const uint32_t avail = remaining < kLoad ? (uint32_t)remaining : kLoad;      // stream positions visible in smem
+        const uint32_t region = remaining < kTile ? (uint32_t)remaining : kTile;    // stream positions this tile owns
+        const uint64_t real_left = a.nbytes > T0 ? a.nbytes - T0 : 0;
+        const uint32_t real_avail = real_left < kLoad ? (uint32_t)real_left : kLoad;  // real bytes among them
+        if (real_avail) {
+            if (tid == 0) {
+                const uint32_t bytes = (real_avail + 15u) & ~15u;
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_copy_g2s(tile_sa, a.buf + T0, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
         }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
 
         // ---- newline bitmap: one word per 32 bytes
         for (uint32_t g = tid; g < kGroups + 2; g += THREADS) {
             uint32_t bits = 0;
-            if (g * 32u < avail) {
+            if (g * 32u < real_avail) {
                 const uint4 lo = lds_v4_volatile(tile_sa + g * 32u), hi = lds_v4_volatile(tile_sa + g * 32u + 16u);
                 bits = newline_nibble(lo.x) | (newline_nibble(lo.y) << 4) | (newline_nibble(lo.z) << 8) | (newline_nibble(lo.w) << 12) |
                        (newline_nibble(hi.x) << 16) | (newline_nibble(hi.y) << 20) | (newline_nibble(hi.z) << 24) | (newline_nibble(hi.w) << 28);
-                if (g * 32u + 32u > avail) bits &= (1u << (avail - g * 32u)) - 1u;
+                if (g * 32u + 32u > real_avail) bits &= (1u << (real_avail - g * 32u)) - 1u;
             }
+            if (real_avail < avail && (real_avail >> 5) == g) bits |= 1u << (real_avail & 31u);   // the virtual final newline
             s_bitmap[g] = bits;
         }
         __syncthreads();
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
                 int32_t look = (int32_t)t - 1;
                 for (;;) {
                     const int32_t idx = look - (int32_t)lane;
-                    unsigned long long st = (2ull << 62);   // tiles before the launch: prefix 0
+                    unsigned long long st = (2ull << 62);   // before the stream: prefix 0
                     if (idx >= 0) {
                         do { st = *reinterpret_cast<volatile unsigned long long*>(a.tile_state + idx); } while ((st >> 62) == 0);
                     }
@@ -267,19 +273,19 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
             if (lane == 0) {
                 atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
                 *s_prefix = excl;
-                if (t == a.tile_count - 1) *a.lines_out = lines_in + excl + agg;
+                if (T0 + region == stream_len) *a.lines_out = excl + agg;
             }
         }
         __syncthreads();
-        const unsigned long long Lt = lines_in + *s_prefix;    // global index of this tile's first newline
+        const unsigned long long Lt = *s_prefix;    // global index of this tile's first newline
 
         // ---- record starts in this tile -> s_list
-        const bool first_global = (a.tile_first + t) == 0;
+        const bool first_global = t == 0;
         const uint32_t extra = first_global ? 1u : 0u;
         const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
         const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
         uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
-        if (T0 + region == a.nbytes && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
+        if (T0 + region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
         if (first_global && tid == 0) s_list[0] = 0;
 #pragma unroll
         for (uint32_t k = 0; k < kGpt; k++) {
@@ -343,8 +349,8 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
                     uint64_t q[4];
                     uint64_t p = gs;
                     int found = 0;
-                    for (; found < 4 && p < a.nbytes; p++)
-                        if (base[p] == '\n') q[found++] = p;
+                    for (; found < 4 && p < stream_len; p++)
+                        if (p == a.nbytes || base[p] == '\n') q[found++] = p;
                     if (found < 4) report(a, gs, kErrUnexpectedEnd);
                     else {
                         const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
             }
             const unsigned long long R_w = R_base + k0;      // record number of lane 0
             if (valid) {
-                if (R_base + k >= a.mask_bits) { report(a, T0, kErrMaskOverflow); sel = false; }
+                if (R_base + k >= a.mask_bits || (want_idh && R_base + k >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
                 else if (want_idh) a.id_hash[R_base + k] = idh;
             }
             const uint32_t m = __ballot_sync(kFullMask, sel);
@@ -376,26 +382,37 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
 
-// pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747)
-__global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t n_words, const uint32_t* h1, const uint32_t* h2,
-                                     uint64_t n_records, unsigned long long* count, unsigned long long* id_mismatch) {
+// pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747).
+// Record counts are still on the device (written by the streams' last tiles), so they are read here.
+__global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
+                                     uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
+                                     unsigned long long* id_mismatch) {
+    const uint64_t r1 = *lines1 >> 2, r2 = *lines2 >> 2;
+    uint64_t n_records = r1 < r2 ? r1 : r2;
+    uint64_t n_words = (n_records + 31) >> 5;
+    if (n_words > cap_words) n_words = cap_words;
     unsigned long long c = 0, bad = ~0ull;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t m = m1[i] | m2[i];
         out[i] = m;
         c += __popc(m);
     }
-    if (h1 && h2)
+    if (h1 && h2) {
+        if (n_records > idh_cap) n_records = idh_cap;
         for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_records; i += (uint64_t)gridDim.x * blockDim.x)
             if (h1[i] != h2[i] && i < bad) bad = i;
+    }
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFullMask, c, d);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
     if (bad != ~0ull) atomicMin(id_mismatch, bad);
 }
 
 // interleaved mates (records 2k, 2k+1 of one stream): unit k = bit 2k | bit 2k+1
-__global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uint64_t n_out_words, const uint32_t* h, uint64_t n_pairs,
-                                           unsigned long long* count, unsigned long long* id_mismatch) {
+__global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const uint32_t* h, uint64_t idh_cap,
+                                           const unsigned long long* lines, unsigned long long* count, unsigned long long* id_mismatch) {
+    uint64_t n_pairs = *lines >> 3;
+    uint64_t n_out_words = (n_pairs + 31) >> 5;
+    if (n_out_words > cap_out_words) n_out_words = cap_out_words;
     unsigned long long c = 0, bad = ~0ull;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_out_words; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t x = (uint64_t)m[2 * i] | ((uint64_t)m[2 * i + 1] << 32);
@@ -408,9 +425,11 @@ __global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uin
         out[i] = (uint32_t)x;
         c += __popcll(x);
     }
-    if (h)
+    if (h) {
+        if (2 * n_pairs > idh_cap) n_pairs = idh_cap / 2;
         for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x)
             if (h[2 * i] != h[2 * i + 1] && i < bad) bad = i;
+    }
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFullMask, c, d);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
     if (bad != ~0ull) atomicMin(id_mismatch, bad);
@@ -449,16 +468,15 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs
     }
 }
 
-cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t n_words, const uint32_t* h1, const uint32_t* h2,
-                                 uint64_t n_records, unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream) {
-    if (n_words == 0) return cudaSuccess;
-    combine_pairs_kernel<<<148 * 4, 256, 0, stream>>>(m1, m2, out, n_words, h1, h2, n_records, count, id_mismatch);
+cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
+                                 uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
+                                 unsigned long long* id_mismatch, cudaStream_t stream) {
+    combine_pairs_kernel<<<148 * 4, 256, 0, stream>>>(m1, m2, out, cap_words, h1, h2, idh_cap, lines1, lines2, count, id_mismatch);
     return cudaGetLastError();
 }
-cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t n_out_words, const uint32_t* h, uint64_t n_pairs,
-                                       unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream) {
-    if (n_out_words == 0) return cudaSuccess;
-    combine_interleaved_kernel<<<148 * 4, 256, 0, stream>>>(m, out, n_out_words, h, n_pairs, count, id_mismatch);
+cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const uint32_t* h, uint64_t idh_cap,
+                                       const unsigned long long* lines, unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream) {
+    combine_interleaved_kernel<<<148 * 4, 256, 0, stream>>>(m, out, cap_out_words, h, idh_cap, lines, count, id_mismatch);
     return cudaGetLastError();
 }
 

@@ -222,3 +222,24 @@ def test_large_literal_set_aho_corasick():
     idx = rng.integers(0, n, 200)
     for i in idx:
         assert got[i] == full.read_match(bytes(mat[i]))
+
+
+def test_write_selected_is_host_glue_and_matches_oracle_output():
+    """Ordered write-back (main.rs:641-657, 682-727) driven by a given mask: no device needed."""
+    from tests.fq_util import fastq
+    seqs = ["ACGT", "TTTT", "ACAC", "GGGG", "AC"]
+    r1 = fastq(seqs, crlf=True, plus_name=True, final_newline=False)
+    r2 = fastq([s[::-1] for s in seqs])
+    o = O.Matcher(O.FIXED, ["AC"])
+    e = o.grep(r1, want_output=True)
+    mask = np.packbits(e["flags"].astype(bool), bitorder="little")
+    mask = np.frombuffer(mask.tobytes() + b"\0" * 8, dtype=np.uint32)
+    assert F.write_selected(mask, r1) == e["out"] == fastq(["ACGT", "ACAC", "AC"])
+    e2 = o.grep(r1, r2, mode=O.PAIRED, want_output=True, split=True)
+    mask2 = np.frombuffer(np.packbits(e2["flags"].astype(bool), bitorder="little").tobytes() + b"\0" * 8, dtype=np.uint32)
+    a, b = F.write_selected(mask2, r1, r2, mode=F.PAIRED, split=True)
+    assert a == e2["out"] and b == e2["out2"]
+    e3 = o.grep(r1, r2, mode=O.PAIRED, want_output=True)
+    assert F.write_selected(mask2, r1, r2, mode=F.PAIRED) == e3["out"]
+    with pytest.raises(F.FqgrepError):
+        F.write_selected(mask, b"@a\nACGT\n+\nXX\n")

@@ -1,0 +1,236 @@
+"""GPU parity of the fused FASTQ parse+match path (fqg_grep_fastq_host / _device) against the oracle and the
+reference's end-to-end golden vectors (src/main.rs tests): counts, selection masks, ordered output bytes."""
+import random
+
+import numpy as np
+import pytest
+
+import fqgrep_b200 as F
+from oracle import oracle as O
+from tests import synth
+from tests.fq_util import fastq, seqs_of
+
+pytestmark = pytest.mark.gpu
+
+
+def opts(inv=False, rc=False):
+    return F.MatcherOpts(invert_match=inv, reverse_complement=rc)
+
+
+def both(kind, pats, inv, rc, r1, r2=None, mode=F.SINGLE, check_output=True):
+    m = F.Matcher(kind, pats, opts(inv, rc))
+    o = O.Matcher(kind, pats, inv, rc)
+    g = m.grep_fastq(r1, r2, mode=mode)
+    e = o.grep(r1, r2, mode=mode, want_output=check_output, threads=4)
+    assert g["units"] == e["units"]
+    assert g["count"] == e["count"], (kind, pats, inv, rc, mode)
+    assert (g["mask"] == (e["flags"] != 0)).all()
+    if check_output:
+        assert F.write_selected(g["mask_words"], r1, r2, mode=mode) == e["out"]
+    return g
+
+
+def test_kat_e2e_counts(kat):
+    e = kat["e2e_counts"]
+    for paired, pats, exp in e["cases"]:
+        m = F.MatcherFactory.new_matcher(None, False, pats)
+        total = 0
+        if paired:
+            for i in range(0, 4, 2):
+                total += m.grep_fastq(fastq(e["files"][i]), fastq(e["files"][i + 1]), mode=F.PAIRED)["count"]
+        else:
+            for f in e["files"]:
+                total += m.grep_fastq(fastq(f))["count"]
+        assert total == exp, (paired, pats)
+
+
+def test_kat_e2e_order_and_split(kat):
+    e = kat["e2e_order"]
+    for paired, pats, exp in e["cases"]:
+        m = F.MatcherFactory.new_matcher(None, False, pats)
+        if paired:
+            r1, r2 = fastq(e["files"][0]), fastq(e["files"][1])
+            out = F.write_selected(m.grep_fastq(r1, r2, mode=F.PAIRED)["mask_words"], r1, r2, mode=F.PAIRED)
+        else:
+            out = b"".join(F.write_selected(m.grep_fastq(fastq(f))["mask_words"], fastq(f)) for f in e["files"])
+        assert seqs_of(out) == exp, (paired, pats)
+    s = kat["e2e_split_output"]
+    r1, r2 = fastq(s["r1"]), fastq(s["r2"])
+    g = F.Matcher(F.REGEX_SET, [s["pattern"]]).grep_fastq(r1, r2, mode=F.PAIRED)
+    assert g["count"] == s["count"]
+    o1, o2 = F.write_selected(g["mask_words"], r1, r2, mode=F.PAIRED, split=True)
+    assert seqs_of(o1) == s["out_r1"] and seqs_of(o2) == s["out_r2"]
+
+
+def test_kat_rc_invert_paired(kat):
+    e = kat["e2e_rc_invert_paired"]
+    for paired, inv, rc, exp in e["cases"]:
+        m = F.Matcher(F.REGEX_SET, [e["pattern"]], opts(inv, rc))
+        if paired:
+            got = m.grep_fastq(fastq(e["files"][0]), fastq(e["files"][1]), mode=F.PAIRED)["count"]
+        else:
+            got = sum(m.grep_fastq(fastq(f))["count"] for f in e["files"])
+        assert got == exp, (paired, inv, rc)
+
+
+def test_kat_names(kat):
+    for inv, names, rid, exp in kat["query_name"]["cases"]:
+        m = F.MatcherFactory.new_query_name_matcher(names, opts(inv))
+        assert m.read_match("ACGT", head=rid + " description") == exp
+    hc = kat["query_name"]["header_case"]
+    assert F.MatcherFactory.new_query_name_matcher(hc["names"]).read_match("ACGT", head=hc["header"]) == hc["expect"]
+    e = kat["e2e_names"]
+    for inv, names, exp in e["single"]["cases"]:
+        assert F.Matcher(F.NAMES, names, opts(inv)).grep_fastq(fastq(["ACGT"] * e["single"]["n_reads"]))["count"] == exp
+    n = e["paired"]["n_reads_per_file"]
+    for inv, names, exp in e["paired"]["cases"]:
+        assert F.Matcher(F.NAMES, names, opts(inv)).grep_fastq(fastq(["ACGT"] * n), fastq(["TTTT"] * n), mode=F.PAIRED)["count"] == exp
+    for inv, names, exp in e["empty"]["cases"]:
+        assert F.Matcher(F.NAMES, names, opts(inv)).grep_fastq(fastq(["ACGT"] * e["empty"]["n_reads"]))["count"] == exp
+
+
+def test_kat_exit_codes(kat):
+    e = kat["e2e_exit"]
+    for c in e["cases"]:
+        try:
+            if c["fixed"]:
+                F.validate_fixed_pattern(c["pattern"])
+            m = F.MatcherFactory.new_matcher(c["pattern"], c["fixed"], [])
+            code = 0 if sum(m.grep_fastq(fastq(f))["count"] for f in e["files"]) else 1
+        except F.FqgrepError as ex:
+            code = ex.exit_code
+        assert code == c["exit"], c
+
+
+def test_kat_protein(kat):
+    e = kat["e2e_protein"]
+    r = fastq(e["reads"])
+    for fixed, pats, exp in e["cases"]:
+        m = F.MatcherFactory.new_matcher(None, fixed, pats)
+        assert seqs_of(F.write_selected(m.grep_fastq(r)["mask_words"], r)) == exp
+
+
+@pytest.mark.parametrize("kind,pats,inv,rc", [
+    (F.REGEX, ["GACGAGATTA"], False, False),
+    (F.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], False, True),
+    (F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, False),
+    (F.FIXED_SET, ["GACGAGATTA", "TTTTTTTT", "ACGTAC"], True, True),
+])
+def test_synthetic_fastq_single_paired_interleaved(kind, pats, inv, rc):
+    n = 120_000     # ~38 MB per mate: thousands of tiles, several look-back windows
+    m1, m2 = synth.bases(n, seed=1), synth.bases(n, seed=2)
+    synth.plant(m1, ["GACGAGATTA", "GACGTGATTA", "ACGTGTTACA"], rate=0.01, seed=99)
+    synth.plant(m2, ["GACGAGATTA", "GACGTGATTA", "ACGTGTTACA"], rate=0.01, seed=98)
+    f1, f2 = synth.fastq(m1), synth.fastq(m2)
+    g = both(kind, pats, inv, rc, f1, check_output=False)
+    assert 0 < g["count"] < n
+    both(kind, pats, inv, rc, f1, f2, mode=F.PAIRED, check_output=False)
+    # interleave the two mates record by record
+    il = np.stack([f1.reshape(n, 317), f2.reshape(n, 317)], axis=1).reshape(-1)
+    both(kind, pats, inv, rc, il, mode=F.INTERLEAVED, check_output=False)
+
+
+def test_output_bytes_match_oracle_on_medium_file():
+    n = 30_000
+    m1 = synth.bases(n, seed=4)
+    synth.plant(m1, ["GACGAGATTA"], rate=0.02)
+    f1 = synth.fastq(m1)
+    both(F.FIXED, ["GACGAGATTA"], False, True, f1)
+
+
+def test_names_one_million_ids_scaled_down():
+    n = 200_000
+    f1 = synth.fastq(synth.bases(n, seed=1))
+    rng = np.random.default_rng(5)
+    chosen = rng.choice(n, 20_000, replace=False)
+    names = ["r%010d" % i for i in chosen] + ["r%010d" % (n + i) for i in range(2_000)]
+    for inv in (False, True):
+        g = both(F.NAMES, names, inv, False, f1, check_output=False)
+        assert g["count"] == (n - 20_000 if inv else 20_000)
+    f2 = synth.fastq(synth.bases(n, seed=2))
+    both(F.NAMES, names, False, False, f1, f2, mode=F.PAIRED, check_output=False)
+
+
+def test_format_edge_cases():
+    seqs = ["ACGT", "", "TTACGG", "N", "ACGTACGTAC" * 30]
+    for crlf in (False, True):
+        for plus_name in (False, True):
+            for final_nl in (False, True):
+                data = fastq(seqs, crlf=crlf, plus_name=plus_name, final_newline=final_nl)
+                for pats in (["ACG"], ["T$"], ["^$"], ["^A", "C$"]):
+                    both(F.REGEX_SET, pats, False, True, data)
+                both(F.NAMES, ["@0", "@3"], False, False, data)
+    both(F.REGEX, ["A"], False, False, fastq(seqs) + b"\n\n\r\n")       # trailing blank lines
+    assert F.Matcher(F.REGEX, ["A"]).grep_fastq(b"")["count"] == 0
+    # ids end at the first space only (a tab belongs to the id)
+    both(F.NAMES, ["a\tb"], False, False, fastq(["ACGT"], heads=["a\tb c"]))
+    both(F.NAMES, ["a"], False, False, fastq(["ACGT"], heads=["a b"]))
+
+
+def test_ragged_and_long_records_cross_tiles():
+    rng = random.Random(9)
+    seqs = []
+    for i in range(3000):
+        L = rng.choice([0, 1, 5, 50, 150, 151, 300, 1000, 2500, 6000]) if i % 7 else rng.choice([20000, 40000])
+        seqs.append("".join(rng.choice("ACGT") for _ in range(L)))
+    seqs[10] = seqs[10] + "GACGAGATTA"
+    data = fastq(seqs)
+    for kind, pats, inv, rc in ((F.FIXED, ["GACGAGATTA"], False, True), (F.REGEX_SET, ["^ACG", "TT$"], True, False)):
+        both(kind, pats, inv, rc, data)
+    both(F.NAMES, ["@5", "@2999", "@0"], False, False, data)
+
+
+def test_tiny_records_like_reference_fixtures():
+    seqs = ["AAAA", "TTTT", "GGGG", "CCCC"] * 5000      # 16-byte records, 1000+ records per tile
+    data = fastq(seqs, heads=["%d" % (i % 10) for i in range(len(seqs))])
+    both(F.REGEX_SET, ["^A", "GG"], False, False, data)
+    both(F.REGEX_SET, ["^A", "GG"], False, False, data, data, mode=F.PAIRED)
+
+
+def test_malformed_fastq_is_an_error_like_the_reference_panic():
+    m = F.Matcher(F.FIXED, ["AC"])
+    good = fastq(["ACGT"] * 100)
+    for bad in (b"ACGT\n" + good, good + b"@a\nACGT\n-\nXXXX\n", good + b"@a\nACGT\n+\nXXX\n", good + b"@a\nACGT\n+\n", good + b"@a\nACGT\n"):
+        with pytest.raises(F.FqgrepError) as e:
+            m.grep_fastq(bad)
+        assert e.value.exit_code == 101
+        with pytest.raises(O.OracleError):
+            O.Matcher(O.FIXED, ["AC"]).grep(bad)
+    with pytest.raises(F.FqgrepError):
+        m.grep_fastq(fastq(["ACGT"] * 3), mode=F.INTERLEAVED)
+    with pytest.raises(F.FqgrepError) as e:
+        m.grep_fastq(fastq(["ACGT"] * 3), fastq(["ACGT"] * 2), mode=F.PAIRED)
+    assert e.value.exit_code == 101
+    with pytest.raises(F.FqgrepError) as e:     # mismatching ids: assert_eq! panic in the reference (main.rs:741-747)
+        m.grep_fastq(fastq(["ACGT"], heads=["a 1"]), fastq(["ACGT"], heads=["b 1"]), mode=F.PAIRED)
+    assert e.value.exit_code == 101
+    assert m.grep_fastq(fastq(["ACGT"], heads=["a 1"]), fastq(["GGGG"], heads=["a 2"]), mode=F.PAIRED)["count"] == 1
+
+
+def test_device_resident_fastq_entry():
+    import ctypes as C
+    import torch
+    from fqgrep_b200 import _ffi
+    n = 150_000
+    m1, m2 = synth.bases(n, seed=1), synth.bases(n, seed=2)
+    synth.plant(m1, ["GACGAGATTA"], rate=0.01, seed=99)
+    f1, f2 = synth.fastq(m1), synth.fastq(m2)
+    pats = ["GACGAGATTA", "GACGTGATTA"]
+    m = F.Matcher(F.REGEX_SET, pats, opts(False, True))
+    dev = torch.device("cuda:0")
+    bufs = []
+    for f in (f1, f2):
+        t = torch.zeros(f.size + 64, dtype=torch.uint8, device=dev)
+        t[: f.size] = torch.from_numpy(f).to(dev)
+        bufs.append(t)
+    words = n // 32 + 2
+    mask = torch.zeros(words, dtype=torch.int32, device=dev)
+    res = _ffi.Result()
+    torch.cuda.synchronize()
+    rc = _ffi.lib().fqg_grep_fastq_device(F.context(0), m._h, F.PAIRED, bufs[0].data_ptr(), f1.size, bufs[1].data_ptr(), f2.size, mask.data_ptr(), words,
+                                          C.byref(res), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, _ffi.last_error()
+    e = O.Matcher(O.REGEX_SET, pats, False, True).grep(f1, f2, mode=O.PAIRED, threads=8)
+    assert res.n_selected == e["count"] and res.n_units == n
+    got = np.unpackbits(mask.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert (got == (e["flags"] != 0)).all()
