@@ -6,11 +6,12 @@
 namespace fqg {
 
 // Device-resident automaton in the layout the kernels index directly.
-//   tier 0: uint16 table[n_states][264], indexed by raw byte, staged in shared memory; an entry is the BYTE offset
-//           of the next state's row (state * 528).  Row stride 528 B skews consecutive states by 4 banks, so the
-//           hot (state, base) pairs of a warp land in different banks.
+//   tier 0: uint16 table[n_states][256 + pad] in shared memory.  Entries 0..255 of a row are FOUR-base transitions
+//           indexed by the packed 2-bit codes of four consecutive bases; entries 256.. are one-byte transitions by
+//           byte class (used for words that are not pure ACGT and for the <4-byte tail).  An entry is the BYTE
+//           offset of the next state's row; the 528 B row stride skews consecutive states by 4 banks.
 //   tier 1: uint16 table[n_states][n_classes] in smem, entries = byte offset of the next row (state * n_classes * 2);
-//           the 256 B byte->class LUT holds class*2.
+//           the 256 B byte->class LUT holds class*2 (tiers 0 and 1).
 //   tier 2: uint32 table[n_states][n_classes] read through L2, entries = entry index of the next row
 //           (state * n_classes); the LUT holds the plain class.
 struct DeviceDfa {
@@ -23,7 +24,6 @@ struct DeviceDfa {
     uint32_t accept_from = 0;        // premultiplied
     uint32_t n_states = 0;
 };
-constexpr uint32_t kTier0Row = 264;
 
 struct SoaBatch {
     const uint8_t* bases;

@@ -148,21 +148,21 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
 
     // ---- smem carve-up
     uint8_t* s_tab = smem;
-    uint8_t* s_cls = smem + table_smem_bytes;
-    uint8_t* s_tile = s_cls + 256;                                          // kLoad + 32
-    uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);  // kGroups + 2
-    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);  // kGroups + 2
-    uint16_t* s_list = s_pre + kGroups + 2;                                  // kListCap
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_list + kListCap);       // warp sums [kWarps], tile id, flags
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 48);
+    uint8_t* s_cls = smem + table_smem_bytes;                                // 256 B
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cls + 256);              // 8-byte aligned: table_smem_bytes is a multiple of 128
     unsigned long long* s_prefix = reinterpret_cast<unsigned long long*>(s_bar + 1);
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2);               // warp sums [kWarps], [40] = tile id
+    uint8_t* s_tile = s_cls + 512;                                           // kLoad + 32, 128-byte aligned for the bulk copy
+    uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);   // kGroups + 2
+    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
+    uint16_t* s_list = s_pre + kGroups + 2;                                   // kListCap
 
     if (TIER <= 1) {
         const uint4* src = reinterpret_cast<const uint4*>(dfa.table);
         uint4* dst = reinterpret_cast<uint4*>(s_tab);
         for (uint32_t i = tid; i < dfa.table_bytes / 16; i += THREADS) dst[i] = __ldg(src + i);
     }
-    if (TIER == 1 || TIER == 2)
+    if (TIER <= 2)
         for (uint32_t i = tid; i < 256; i += THREADS) s_cls[i] = __ldg(dfa.byte_class + i);
     if (tid == 0) mbar_init(smem_addr(s_bar), 1);
     mbar_fence_init();
@@ -439,7 +439,7 @@ template <int TIER>
 cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
     constexpr int THREADS = 128;
     const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : 0u;
-    const uint32_t smem = table_smem + 256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u + kListCap * 2u + 48u * 4u + 8u + 8u + 128u;
+    const uint32_t smem = table_smem + 512u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u + kListCap * 2u + 128u;
     auto kern = match_fastq_kernel<TIER, THREADS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

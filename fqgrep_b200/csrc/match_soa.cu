@@ -48,8 +48,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
         uint4* dst = reinterpret_cast<uint4*>(s_tab);
         for (uint32_t i = threadIdx.x; i < dfa.table_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    if (TIER >= 1)
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
     if (lane == 0)
         for (int s = 0; s < STAGES; s++) mbar_init(smem_addr(&s_bar[warp * STAGES + s]), 1);
     mbar_fence_init();

@@ -232,11 +232,13 @@ def test_write_selected_is_host_glue_and_matches_oracle_output():
     r2 = fastq([s[::-1] for s in seqs])
     o = O.Matcher(O.FIXED, ["AC"])
     e = o.grep(r1, want_output=True)
-    mask = np.packbits(e["flags"].astype(bool), bitorder="little")
-    mask = np.frombuffer(mask.tobytes() + b"\0" * 8, dtype=np.uint32)
-    assert F.write_selected(mask, r1) == e["out"] == fastq(["ACGT", "ACAC", "AC"])
+    def words(flags):
+        b = np.packbits(flags.astype(bool), bitorder="little").tobytes()
+        return np.frombuffer(b + b"\0" * (8 - len(b) % 4), dtype=np.uint32)
+    mask = words(e["flags"])
+    assert F.write_selected(mask, r1) == e["out"] == fastq(["ACGT", "ACAC", "AC"], heads=["@0", "@2", "@4"])
     e2 = o.grep(r1, r2, mode=O.PAIRED, want_output=True, split=True)
-    mask2 = np.frombuffer(np.packbits(e2["flags"].astype(bool), bitorder="little").tobytes() + b"\0" * 8, dtype=np.uint32)
+    mask2 = words(e2["flags"])
     a, b = F.write_selected(mask2, r1, r2, mode=F.PAIRED, split=True)
     assert a == e2["out"] and b == e2["out2"]
     e3 = o.grep(r1, r2, mode=O.PAIRED, want_output=True)
