@@ -98,13 +98,14 @@ void build_tables(fqg_matcher* m) {
         for (uint64_t s = 0; s < n; s++) {
             for (uint32_t p = 0; p < 256; p++) {
                 uint64_t t = s;
-                for (int k = 0; k < 4; k++) t = d.next[t * nc + d.byte_class[(uint8_t)kLetter[(p >> (2 * k)) & 3]]];
+                // index = c3 | c2<<2 | c1<<4 | c0<<6, c0 = first base in stream order (see step4_acgt)
+                for (int k = 0; k < 4; k++) t = d.next[t * nc + d.byte_class[(uint8_t)kLetter[(p >> (6 - 2 * k)) & 3]]];
                 m->t16[s * row0 + p] = (uint16_t)(t * row0 * 2);
             }
             for (uint64_t c = 0; c < nc; c++) m->t16[s * row0 + 256 + c] = (uint16_t)(d.next[s * nc + c] * row0 * 2);
         }
         for (int b = 0; b < 256; b++) m->lut[b] = (uint8_t)(d.byte_class[b] * 2);
-    } else if (n * nc * 2 <= 65535 && nc <= 127) {
+    } else if (n * nc * 2 <= 60 * 1024 && nc <= 127) {
         m->tier = 1;
         m->row = (uint32_t)nc * 2;
         m->t16.assign(((n * nc + 7) / 8) * 8, 0);
@@ -648,6 +649,17 @@ int fqg_grep_fastq_host(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_
                         uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res) {
     if (!c || !m || !res) return fail(FQG_E_INVALID_ARG, "NULL argument");
     return grep_fastq(c, m, mode, r1, n1, r2, n2, false, unit_mask_out, unit_mask_words, res, c->stream);
+}
+
+int fqg_fastq_split(const uint8_t* buf, size_t n, uint32_t parts, uint64_t* cuts) {
+    if (!cuts || parts == 0 || (n && !buf)) return fail(FQG_E_INVALID_ARG, "bad argument");
+    cuts[0] = 0;
+    for (uint32_t k = 1; k < parts; k++) {
+        size_t c = find_record_start(buf, n, (size_t)((unsigned __int128)n * k / parts));
+        cuts[k] = c < cuts[k - 1] ? cuts[k - 1] : c;
+    }
+    cuts[parts] = n;
+    return FQG_OK;
 }
 
 int fqg_write_selected(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* unit_mask, uint8_t* out,

@@ -12,8 +12,8 @@ __device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
-    uint16_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    uint32_t v;   // zero-extended straight into a 32-bit register: no 16-bit register shuffling in the hot loop
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
@@ -23,7 +23,10 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
 }
 
 // State encodings (see kernels.hpp).
-//   tier 0: a state is the BYTE offset of its row in the shared-memory table.  A row holds 256 four-base
+//   tiers 0 and 1 keep a state as the 16-bit SHARED-MEMORY ADDRESS of its table row (entries are relocated by the
+//   table's base address while the table is staged, see stage_table), so the dependent chain per lookup is a
+//   single add + LDS.
+//   tier 0: a row holds 256 four-base  A row holds 256 four-base
 //           transitions indexed by the packed 2-bit codes of four consecutive bases (A=0 C=1 T=2 G=3, from
 //           (byte>>1)&3), then the one-byte transitions indexed by byte class.  Four bases cost ONE table
 //           lookup on the state-dependency chain; a word holding anything but ACGT (N, lowercase, protein,
@@ -38,40 +41,73 @@ struct DfaView {
     uint32_t cls;          // smem address of the byte -> class LUT (tier 0,1: class*2; tier 2: class)
 
     __device__ __forceinline__ uint32_t step1(uint32_t st, uint32_t byte) const {
-        if (TIER == 0) return lds_u16(tab + st + 512u + lds_u8(cls + byte));
-        if (TIER == 1) return lds_u16(tab + st + lds_u8(cls + byte));
+        if (TIER == 0) return lds_u16(st + 512u + lds_u8(cls + byte));
+        if (TIER == 1) return lds_u16(st + lds_u8(cls + byte));
         return __ldg(t32 + st + lds_u8(cls + byte));
     }
-    // four stream-ordered bytes in one little-endian word
-    __device__ __forceinline__ uint32_t step4(uint32_t st, uint32_t w) const {
-        if (TIER == 0) {
-            const uint32_t x = (w >> 1) & 0x03030303u;                       // 2-bit code per byte
-            const uint32_t t = (x >> 1) & ~x & 0x01010101u;                  // bytes whose code is 2 ('T')
-            const uint32_t letters = x * 2u + 0x41414141u + t * 0x0Fu;       // the ACGT word those codes stand for
-            if (letters == w) return lds_u16(tab + st + (((x * 0x01041040u) >> 24) << 1));
-        }
-        st = step1(st, w & 0xFFu);
-        st = step1(st, (w >> 8) & 0xFFu);
-        st = step1(st, (w >> 16) & 0xFFu);
-        return step1(st, w >> 24);
+    // Four stream-ordered bytes in one little-endian word, tier 0 only: ONE lookup, taken unconditionally.
+    // `bad` accumulates, exactly, whether any byte was not one of ACGT; the caller then re-walks the read with
+    // step1 (rare: reads with N / lowercase / protein), so no per-word branch sits in the hot loop.
+    //   code  x = (byte >> 1) & 3           A=0 C=1 T=2 G=3
+    //   byte & ~6 is 0x41 for A,C,G and 0x50 for T  =>  ((byte & ~6) ^ 0x41) must equal 0x11 * [code == 2]
+    //   index = c3 | c2<<2 | c1<<4 | c0<<6 (times two, byte offset) = (x * 0x40100401) >> 23; bit 0 is provably clear
+    __device__ __forceinline__ uint32_t step4_acgt(uint32_t st, uint32_t w, uint32_t& bad) const {
+        const uint32_t x = (w >> 1) & 0x03030303u;
+        const uint32_t t = (x >> 1) & ~x & 0x01010101u;
+        bad |= ((w & 0xF9F9F9F9u) ^ 0x41414141u) ^ (t * 0x11u);
+        return lds_u16(st + ((x * 0x40100401u) >> 23));
     }
 };
 
+// Copies a tier-0/1 table into shared memory, turning row offsets into absolute shared addresses.
+// The table sits at the start of dynamic shared memory and is < 62 KB, so addresses fit 16 bits.
+__device__ __forceinline__ void stage_table(const void* gtable, uint32_t table_bytes, void* s_tab, uint32_t tid, uint32_t nthreads) {
+    const uint4* src = reinterpret_cast<const uint4*>(gtable);
+    uint4* dst = reinterpret_cast<uint4*>(s_tab);
+    const uint32_t base = smem_addr(s_tab);
+    if (tid == 0 && base + table_bytes > 0xFFFFu) __trap();   // cannot happen with the tier limits in api.cu
+    const uint32_t add = base | (base << 16);
+    for (uint32_t i = tid; i < table_bytes / 16; i += nthreads) {
+        uint4 v = __ldg(src + i);
+        v.x += add; v.y += add; v.z += add; v.w += add;    // two u16 lanes per word; sums stay below 2^16
+        dst[i] = v;
+    }
+}
+
+// walk `len` bytes starting at shared address p (any alignment), one byte per lookup
+template <int TIER>
+__device__ __noinline__ uint32_t walk_shared_bytes(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st) {
+    for (uint32_t i = 0; i < len; i++) {
+        uint32_t b;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(p + i));
+        st = d.step1(st, b);
+    }
+    return st;
+}
+
 // walk `len` bytes starting at shared address p (any alignment)
 template <int TIER>
-__device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st) {
+__device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st0) {
     const uint32_t sh = (p & 3u) * 8u;
     uint32_t wp = p & ~3u;
     uint32_t w0 = lds_u32_volatile(wp);
     const uint32_t nw = len >> 2;
-#pragma unroll 2
+    uint32_t st = st0, bad = 0;
+#pragma unroll 4
     for (uint32_t k = 0; k < nw; k++) {
         wp += 4;
         const uint32_t w1 = lds_u32_volatile(wp);
         const uint32_t w = __funnelshift_r(w0, w1, sh);
         w0 = w1;
-        st = d.step4(st, w);
+        if (TIER == 0) st = d.step4_acgt(st, w, bad);
+        else {
+            st = d.step1(st, w & 0xFFu);
+            st = d.step1(st, (w >> 8) & 0xFFu);
+            st = d.step1(st, (w >> 16) & 0xFFu);
+            st = d.step1(st, w >> 24);
+        }
     }
+    if (TIER == 0 && bad) return walk_shared_bytes(d, p, len, st0);
     const uint32_t rem = len & 3u;
     if (rem) {
         const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh);

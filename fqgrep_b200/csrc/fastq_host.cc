@@ -56,6 +56,32 @@ int next_host_record(const uint8_t* buf, size_t n, size_t* pos, HostRecord* r, s
     return 1;
 }
 
+// Shard cutting for multi-GPU runs: the first record start at or after `pos`.  A FASTQ quality line may begin with
+// '@', so a candidate line must start with '@' AND be followed two lines later by a '+' line (a sequence line never
+// starts with '+'), with equal sequence/quality lengths.  Returns n when no record starts after pos.
+size_t find_record_start(const uint8_t* buf, size_t n, size_t pos) {
+    if (pos == 0) return 0;
+    if (pos >= n) return n;
+    const uint8_t* e = buf + n;
+    const uint8_t* p = buf + pos;
+    if (p[-1] != '\n') { p = eol(p, e); if (p >= e) return n; p++; }
+    for (int guard = 0; guard < 64 && p < e; guard++) {
+        if (*p == '@') {
+            const uint8_t* l1 = eol(p, e);
+            const uint8_t* l2 = l1 < e ? eol(l1 + 1, e) : e;
+            if (l2 < e && l2 + 1 < e && l2[1] == '+') {
+                const uint8_t* l3 = eol(l2 + 1, e);
+                const uint8_t* l4 = l3 < e ? eol(l3 + 1, e) : e;
+                if (l3 < e && strip_cr(l1 + 1, (size_t)(l2 - l1 - 1)) == strip_cr(l3 + 1, (size_t)(l4 - l3 - 1))) return (size_t)(p - buf);
+            }
+        }
+        p = eol(p, e);
+        if (p >= e) return n;
+        p++;
+    }
+    return n;
+}
+
 namespace {
 inline uint8_t* emit(uint8_t* o, const HostRecord& r) {
     *o++ = '@';

@@ -21,6 +21,8 @@ struct HostRecord {
 // Returns 1 (record), 0 (clean end of input), <0 = FQG_E_FASTQ with *err set.
 int next_host_record(const uint8_t* buf, size_t n, size_t* pos, HostRecord* rec, std::string* err);
 
+size_t find_record_start(const uint8_t* buf, size_t n, size_t pos);
+
 // Ordered write-back of selected units (src/main.rs:641-657, 682-727).
 int write_selected_host(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* unit_mask, uint8_t* out,
                         size_t* out_len, uint8_t* out2, size_t* out2_len, std::string* err);

@@ -157,11 +157,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
     uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
     uint16_t* s_list = s_pre + kGroups + 2;                                   // kListCap
 
-    if (TIER <= 1) {
-        const uint4* src = reinterpret_cast<const uint4*>(dfa.table);
-        uint4* dst = reinterpret_cast<uint4*>(s_tab);
-        for (uint32_t i = tid; i < dfa.table_bytes / 16; i += THREADS) dst[i] = __ldg(src + i);
-    }
+    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, tid, THREADS);
     if (TIER <= 2)
         for (uint32_t i = tid; i < 256; i += THREADS) s_cls[i] = __ldg(dfa.byte_class + i);
     if (tid == 0) mbar_init(smem_addr(s_bar), 1);
@@ -173,8 +169,9 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
     ev.view.t32 = reinterpret_cast<const uint32_t*>(dfa.table);
     ev.view.cls = smem_addr(s_cls);
     ev.names.nv = a.names;
-    ev.start = dfa.start;
-    ev.accept_from = dfa.accept_from;
+    const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
+    ev.start = dfa.start + reloc;
+    ev.accept_from = dfa.accept_from + reloc;
     ev.invert = a.invert != 0;
     const bool want_idh = a.id_hash != nullptr;
 

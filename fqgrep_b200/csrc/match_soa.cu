@@ -43,11 +43,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_bar + 32 * STAGES);
     s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
 
-    if (TIER <= 1) {
-        const uint4* src = reinterpret_cast<const uint4*>(dfa.table);
-        uint4* dst = reinterpret_cast<uint4*>(s_tab);
-        for (uint32_t i = threadIdx.x; i < dfa.table_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
+    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
     if (lane == 0)
         for (int s = 0; s < STAGES; s++) mbar_init(smem_addr(&s_bar[warp * STAGES + s]), 1);
@@ -55,6 +51,8 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     __syncthreads();
 
     DfaView<TIER> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls)};
+    const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
+    const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
     uint8_t* my_slots = s_slots + (size_t)warp * STAGES * slot_bytes;
     const uint32_t n_batches = (b.n_reads + 31u) >> 5;
     const uint32_t stride = gridDim.x * nwarps;
@@ -102,7 +100,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
             issue(nxt, stage ^ 1u);                 // descriptors were fetched one iteration ago
             nn = load_desc(batch + 2u * stride);    // consumed next iteration
         }
-        uint32_t st = dfa.start;
+        uint32_t st = st_start;
         const uint32_t len = cur.e - cur.s;
         if (cur.fits) {
             if (cur.bytes) {
@@ -114,7 +112,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
             st = walk_global<TIER>(view, b.bases + cur.s, len, st);
         }
         const uint32_t r = batch * 32u + lane;
-        const bool sel = (r < b.n_reads) && ((st >= dfa.accept_from) != (b.invert != 0));
+        const bool sel = (r < b.n_reads) && ((st >= st_accept) != (b.invert != 0));
         uint32_t m = __ballot_sync(kFullMask, sel);
         if (lane == 0) {
             if (b.or_mask) m |= __ldg(b.or_mask + batch);

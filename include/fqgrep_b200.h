@@ -142,6 +142,11 @@ int fqg_grep_fastq_device(fqg_ctx* ctx, const fqg_matcher* m, int mode, const ui
 int fqg_write_selected(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* unit_mask,
                        uint8_t* out, size_t* out_len, uint8_t* out2, size_t* out2_len);
 
+/* Multi-GPU sharding helper (host): cut a FASTQ buffer into `parts` contiguous byte ranges that begin at record
+ * starts (the reference has no sharding; this replaces nothing, it feeds one fqg_ctx per GPU).  cuts: uint64[parts+1],
+ * cuts[0]=0, cuts[parts]=n.  Ranges hold roughly equal BYTES; record counts per range come back in fqg_result. */
+int fqg_fastq_split(const uint8_t* buf, size_t n, uint32_t parts, uint64_t* cuts);
+
 /* Benchmark utility: the synthetic-read generator of the benchmark spec as a device kernel (inputs are produced
  * in HBM, never crossing PCIe).  fastq=0: n_reads*read_len bases back to back; fastq=1: 317-byte style records
  * "@r%010d\n<bases>\n+\n<I...>\n".  plant_*: patterns planted (50% reverse-complemented) into a `plant_rate`
