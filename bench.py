@@ -130,6 +130,8 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=2_000_000, help="pairs per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-raw", action="store_true")
+    ap.add_argument("--raw-pairs", type=int, default=20_000_000, help="pairs per step of the HBM-resident raw-FASTQ leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -150,6 +152,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = _ffi.lib()
     ctx = F.context(local)
+    sampler = ClockSampler(local)      # nvidia-smi takes a second to start: launch it before the inputs are generated
+    if rank == 0:
+        sampler.start()
     matcher = F.MatcherFactory.new_matcher(None, False, PATTERNS, None, F.MatcherOpts(invert_match=False, reverse_complement=True))
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
@@ -195,12 +200,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
+    if rank == 0:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 5.0:
+            time.sleep(0.05)
     t_from = time.perf_counter()
     l0 = L.fqg_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -225,9 +231,23 @@ def main():
     reads_per_launch = 2.0 * n_pairs / len(slabs)
     launch_ms = ms / launches_timed
     achieved = ALGO_BYTES_PER_READ * reads_per_launch / (launch_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")     # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if abs(tj.get("reads_per_launch", 0) - reads_per_launch) < 1:
+            traffic = tj["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "kernel": "match_soa_kernel<tier0,2-stage>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": None,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": traffic,
                 "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ, "reads_per_launch": reads_per_launch, "launch_ms": launch_ms}
+
+    # ---- second resident layout: raw FASTQ bytes in HBM through the fused parse+match kernel (SURVEY 8(d), 2nd roofline column)
+    raw = None
+    if not args.no_raw:
+        try:
+            raw = run_raw_fastq(args, L, ctx, matcher, dev, sp, rank, world, peak)
+        except Exception as ex:
+            raw = {"value": None, "error": str(ex)[:200]}
 
     # ---- e2e through the host entry point: raw FASTQ in pinned host memory
     e2e = None
@@ -248,11 +268,57 @@ def main():
             "config": {"workload": "configs[1]: --paired -e GACGAGATTA -e GACGTGATTA --reverse-complement, %d pairs x 150bp per GPU" % n_pairs,
                        "layout": "SoA bases + u32 offsets resident in HBM (%.1f GB per GPU, >> 126 MB L2, no L2 flush needed)" % (bases_per_step_rank / 1e9),
                        "pairs_per_gpu": n_pairs, "selected_pairs_rank0": selected, "parallelism": "shard%d" % world},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed), "clocks": clocks,
+            "roofline": roofline, "raw_fastq_resident": raw, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_raw_fastq(args, L, ctx, matcher, dev, sp, rank, world, peak):
+    """Raw FASTQ resident in HBM -> fqg_grep_fastq_device (fused parse+match, pair combine).  Device-event timed."""
+    import torch
+    import torch.distributed as dist
+    from fqgrep_b200 import _ffi
+    n = args.raw_pairs
+    nbytes = n * FASTQ_BYTES_PER_READ
+    blob = "".join(PATTERNS).encode()
+    poffs = np.array([0, 10, 20], dtype=np.uint32)
+    bufs = []
+    for seed, pseed in ((1, 99), (2, 98)):
+        tb = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+        rc = L.fqg_synth_reads_device(ctx, tb.data_ptr(), n, rank * n, READ_LEN, 1, seed, blob, poffs.ctypes.data_as(C.c_void_p), 2, 0.01, pseed, sp)
+        assert rc == 0, _ffi.last_error()
+        bufs.append(tb)
+    words = n // 32 + 2
+    mask = torch.zeros(words, dtype=torch.int32, device=dev)
+    res = _ffi.Result()
+    stream = torch.cuda.current_stream()
+
+    def once():
+        rc = L.fqg_grep_fastq_device(ctx, matcher._h, 2, bufs[0].data_ptr(), nbytes, bufs[1].data_ptr(), nbytes, mask.data_ptr(), words, C.byref(res), sp)
+        if rc != 0:
+            raise RuntimeError(_ffi.last_error())
+
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    steps = max(3, args.steps // 2)
+    kms = 0.0
+    for _ in range(steps):
+        once()
+        kms += res.kernel_ms          # device events around memsets + both fused kernels + combine
+    if world > 1:
+        t = torch.tensor([kms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kms = float(t.item())
+    val = 2.0 * n * READ_LEN * world * steps / (kms / 1e3) / 1e9
+    gbs = (FASTQ_BYTES_PER_READ + 8 + 0.125) * 2.0 * n * steps / (kms / 1e3) / 1e9
+    return {"value": val, "unit": "Gbases/s", "pairs_per_step_per_gpu": n, "selected": int(res.n_selected), "ms_per_step": kms / steps,
+            "api": "fqg_grep_fastq_device (FASTQ bytes resident in HBM, mode=PAIRED)",
+            "roofline": {"bound": "hbm", "kernel": "match_fastq_kernel<tier0,128>", "algorithmic_bytes_per_record": FASTQ_BYTES_PER_READ + 8 + 0.125,
+                         "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "note": "whole call (memsets + 2 fused kernels + combine) over device events; kernel share in profiles/"}}
 
 
 def run_e2e(args, L, ctx, matcher, dev, sp, rank, world):
