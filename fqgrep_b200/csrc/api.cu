@@ -34,6 +34,9 @@ int fail(int code, const std::string& msg) {
 struct DeviceTables {
     void* table = nullptr;
     uint8_t* byte_class = nullptr;
+    // q-gram filter
+    uint32_t *g_bitmap = nullptr, *g_key = nullptr, *g_val = nullptr, *g_pat_off = nullptr;
+    uint8_t* g_pool = nullptr;
     // names
     uint64_t* slots = nullptr;
     uint32_t* slot_off = nullptr;
@@ -47,6 +50,7 @@ struct fqg_matcher {
     uint32_t opts = 0;
     Dfa dfa;
     NameTable names;
+    GramFilter gram;
     int tier = 0;
     uint32_t row = 0;
     std::vector<uint16_t> t16;
@@ -112,7 +116,7 @@ void build_tables(fqg_matcher* m) {
         for (uint64_t i = 0; i < n * nc; i++) m->t16[i] = (uint16_t)(d.next[i] * nc * 2);
         for (int b = 0; b < 256; b++) m->lut[b] = (uint8_t)(d.byte_class[b] * 2);
     } else {
-        m->tier = 2;
+        m->tier = m->gram.usable ? 3 : 2;    // tier 3 keeps the tier-2 table as its exact fallback
         m->row = (uint32_t)nc;
         m->t32.resize(((n * nc + 3) / 4) * 4);
         for (uint64_t i = 0; i < n * nc; i++) m->t32[i] = (uint32_t)(d.next[i] * nc);
@@ -133,20 +137,41 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
             CU_TRY(cudaMemcpy(t.slot_off, m->names.slot_off.data(), m->names.slot_off.size() * 4, cudaMemcpyHostToDevice));
             CU_TRY(cudaMemcpy(t.pool, m->names.pool.data(), m->names.pool.size(), cudaMemcpyHostToDevice));
         } else {
-            const void* src = m->tier == 2 ? (const void*)m->t32.data() : (const void*)m->t16.data();
-            size_t bytes = m->tier == 2 ? m->t32.size() * 4 : m->t16.size() * 2;
+            const void* src = m->tier >= 2 ? (const void*)m->t32.data() : (const void*)m->t16.data();
+            size_t bytes = m->tier >= 2 ? m->t32.size() * 4 : m->t16.size() * 2;
             CU_TRY(cudaMalloc(&t.table, bytes + 16));
             CU_TRY(cudaMemcpy(t.table, src, bytes, cudaMemcpyHostToDevice));
             CU_TRY(cudaMalloc(&t.byte_class, 256));
             CU_TRY(cudaMemcpy(t.byte_class, m->lut, 256, cudaMemcpyHostToDevice));
+            if (m->tier == 3) {
+                const GramFilter& g = m->gram;
+                auto up = [&](auto** dst, const auto& v) -> cudaError_t {
+                    cudaError_t e = cudaMalloc((void**)dst, v.size() * sizeof(v[0]) + 16);
+                    if (e != cudaSuccess) return e;
+                    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
+                };
+                CU_TRY(up(&t.g_bitmap, g.bitmap));
+                CU_TRY(up(&t.g_key, g.slot_key));
+                CU_TRY(up(&t.g_val, g.slot_val));
+                CU_TRY(up(&t.g_pat_off, g.pat_off));
+                CU_TRY(up(&t.g_pool, g.pool));
+            }
         }
         it = m->dev.emplace(c->device, t).first;
     }
     if (out) {
         out->tier = m->tier;
         out->table = it->second.table;
-        out->table_bytes = (uint32_t)(m->tier == 2 ? m->t32.size() * 4 : m->t16.size() * 2);
+        out->table_bytes = (uint32_t)(m->tier >= 2 ? m->t32.size() * 4 : m->t16.size() * 2);
         out->byte_class = it->second.byte_class;
+        if (m->tier == 3) {
+            const GramFilter& g = m->gram;
+            DeviceGram& d = out->gram;
+            d.bitmap = it->second.g_bitmap; d.bitmap_bytes = (uint32_t)g.bitmap.size() * 4; d.bitmap_shift = 32 - g.bitmap_bits_log2;
+            d.slot_key = it->second.g_key; d.slot_val = it->second.g_val; d.slot_shift = 32 - g.slots_log2; d.slot_mask = (1u << g.slots_log2) - 1;
+            d.pool = it->second.g_pool; d.pat_off = it->second.g_pat_off;
+            d.q = g.q; d.s = g.s; d.min_len = g.min_len; d.qmask = g.qmask;
+        }
         out->row = m->row;
         out->start = m->dfa.start * m->row;
         out->accept_from = m->dfa.accept_from * m->row;
@@ -445,6 +470,7 @@ int fqg_matcher_new(int kind, const uint8_t* blob, const uint64_t* offsets, uint
             // fallthrough
         case FQG_FIXED_SET:
             if (!compile_literal_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
+            build_gram_filter(pats, rc, &m->gram);     // only used when the automaton does not fit shared memory
             break;
         case FQG_REGEX:
             if (n != 1) return fail(FQG_E_INVALID_ARG, "FQG_REGEX takes exactly one pattern");
@@ -475,6 +501,7 @@ void fqg_matcher_free(fqg_matcher* m) {
         cudaFree(kv.second.slots);
         cudaFree(kv.second.slot_off);
         cudaFree(kv.second.pool);
+        cudaFree(kv.second.g_bitmap); cudaFree(kv.second.g_key); cudaFree(kv.second.g_val); cudaFree(kv.second.g_pat_off); cudaFree(kv.second.g_pool);
         cudaSetDevice(prev);
     }
     delete m;
@@ -488,7 +515,7 @@ int fqg_matcher_dfa_info(const fqg_matcher* m, fqg_dfa_info* out) {
     out->start = m->dfa.start;
     out->accept_from = m->dfa.accept_from;
     out->tier = (uint32_t)m->tier;
-    out->table_bytes = (uint32_t)(m->tier == 2 ? m->t32.size() * 4 : m->t16.size() * 2);
+    out->table_bytes = (uint32_t)(m->tier >= 2 ? m->t32.size() * 4 : m->t16.size() * 2);
     return FQG_OK;
 }
 

@@ -45,6 +45,20 @@ bool compile_literal_set(const std::vector<std::string>& patterns, bool with_rev
 void finalize_dfa(uint32_t n_states, uint32_t n_classes, std::vector<uint32_t>& next, std::vector<uint8_t>& accept, uint32_t start,
                   bool minimize, Dfa* out);
 
+// Large literal sets: q-gram sampling filter + exact verification table (gram_filter.cc).
+struct GramFilter {
+    bool usable = false;
+    uint32_t q = 0, s = 0, min_len = 0, qmask = 0;
+    uint32_t bitmap_bits_log2 = 0, slots_log2 = 0;
+    std::vector<uint32_t> bitmap;      // shared-memory resident on the device
+    std::vector<uint32_t> slot_key;    // gram code
+    std::vector<uint32_t> slot_val;    // pattern id << 5 | offset of the gram in the pattern; 0xFFFFFFFF = empty
+    std::vector<uint8_t> pool;         // patterns back to back (+ reverse complements)
+    std::vector<uint32_t> pat_off;     // n_patterns + 1
+};
+uint32_t gram_code(const uint8_t* p, uint32_t q);
+bool build_gram_filter(const std::vector<std::string>& patterns, bool with_revcomp, GramFilter* out);
+
 // validate_fixed_pattern (matcher.rs:128-147); returns empty string when ok, else the reference's message.
 std::string validate_fixed_pattern(const std::string& pattern, bool protein);
 

@@ -1,0 +1,80 @@
+// gram_filter.cc -- large literal sets (-F -f with thousands of patterns): q-gram sampling filter + exact verification.
+//
+// Replaces, for pattern sets whose Aho-Corasick automaton does not fit shared memory, the per-byte automaton walk of
+// aho_corasick::AhoCorasick::is_match (/root/reference/src/lib/matcher.rs:250, built at :297-298).  The answer is still
+// exact: the filter only decides WHERE to verify.
+//
+// Every pattern is at least `min_len` long.  Pick a gram length q and a stride s = min_len - q + 1.  Any occurrence of a
+// pattern covers >= s consecutive q-gram windows, so probing the text only at window ends q-1, q-1+s, q-1+2s, ... always
+// lands on a window that starts at pattern offset 0..s-1.  The device therefore keeps
+//   * a bitmap (shared memory) of hash(gram) for the grams at offsets 0..s-1 of every pattern: exact negative filter;
+//   * an open-addressing table gram -> (pattern id, offset) in L2 for the rare positives, verified byte by byte.
+// Grams are built from 2-bit codes (byte >> 1) & 3 of ANY byte (not only ACGT): text and patterns use the same map, so
+// aliasing (N ~ G ...) can only add candidates, never lose a match.
+#include "automata.hpp"
+
+#include <algorithm>
+
+namespace fqg {
+
+uint32_t gram_code(const uint8_t* p, uint32_t q) {
+    uint32_t g = 0;
+    for (uint32_t i = 0; i < q; i++) g = (g << 2) | ((p[i] >> 1) & 3u);
+    return g;
+}
+
+bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_revcomp, GramFilter* out) {
+    const uint8_t* comp = complement_table();
+    std::vector<std::string> pats = patterns_in;
+    if (with_revcomp)
+        for (auto& p : patterns_in) {
+            std::string r(p.rbegin(), p.rend());
+            for (auto& ch : r) ch = (char)comp[(uint8_t)ch];
+            pats.push_back(std::move(r));
+        }
+    out->usable = false;
+    if (pats.empty()) return false;
+    size_t min_len = SIZE_MAX, total = 0;
+    for (auto& p : pats) { min_len = std::min(min_len, p.size()); total += p.size(); }
+    if (min_len < 8 || pats.size() >= (1u << 26) || total >= (1ull << 31)) return false;
+    uint32_t q = (uint32_t)std::min<size_t>(16, std::max<size_t>(8, min_len / 2 + 2));
+    uint32_t s = (uint32_t)min_len - q + 1;
+    if (s > 32) { s = 32; }            // payload keeps the offset in 5 bits; a smaller stride is always valid
+    out->q = q;
+    out->s = s;
+    out->min_len = (uint32_t)min_len;
+    out->qmask = q == 16 ? 0xFFFFFFFFu : ((1u << (2 * q)) - 1u);
+    const uint64_t n_grams = (uint64_t)pats.size() * s;
+    if (n_grams > (1ull << 24)) return false;
+    // bitmap: ~10 bits per gram, between 8 KB and 128 KB of shared memory
+    uint32_t bits_log2 = 16;
+    while (bits_log2 < 20 && (1ull << bits_log2) < n_grams * 10) bits_log2++;
+    out->bitmap_bits_log2 = bits_log2;
+    out->bitmap.assign((1u << bits_log2) / 32, 0);
+    uint32_t slots_log2 = 4;
+    while ((1ull << slots_log2) < n_grams * 2 + 2) slots_log2++;
+    out->slots_log2 = slots_log2;
+    out->slot_key.assign(1u << slots_log2, 0);
+    out->slot_val.assign(1u << slots_log2, 0xFFFFFFFFu);
+    out->pool.clear();
+    out->pat_off.assign(1, 0);
+    for (size_t id = 0; id < pats.size(); id++) {
+        const std::string& p = pats[id];
+        for (uint32_t j = 0; j < s; j++) {
+            const uint32_t g = gram_code((const uint8_t*)p.data() + j, q);
+            const uint32_t hb = (g * 0x9E3779B1u) >> (32 - bits_log2);
+            out->bitmap[hb >> 5] |= 1u << (hb & 31);
+            uint32_t i = (g * 0x85EBCA6Bu) >> (32 - slots_log2);
+            while (out->slot_val[i] != 0xFFFFFFFFu) i = (i + 1) & ((1u << slots_log2) - 1);
+            out->slot_key[i] = g;
+            out->slot_val[i] = (uint32_t)(id << 5) | j;
+        }
+        out->pool.insert(out->pool.end(), p.begin(), p.end());
+        out->pat_off.push_back((uint32_t)out->pool.size());
+    }
+    out->pool.resize(out->pool.size() + 16, 0);
+    out->usable = true;
+    return true;
+}
+
+}  // namespace fqg

@@ -14,8 +14,21 @@ namespace fqg {
 //           the 256 B byte->class LUT holds class*2 (tiers 0 and 1).
 //   tier 2: uint32 table[n_states][n_classes] read through L2, entries = entry index of the next row
 //           (state * n_classes); the LUT holds the plain class.
+// Device view of the q-gram filter (tier 3); see gram_filter.cc / match_soa.cu.
+struct DeviceGram {
+    const uint32_t* bitmap = nullptr;    // device copy, staged into shared memory by the kernel
+    uint32_t bitmap_bytes = 0, bitmap_shift = 0;   // bit index = (gram * 0x9E3779B1) >> bitmap_shift
+    const uint32_t* slot_key = nullptr;
+    const uint32_t* slot_val = nullptr;
+    uint32_t slot_shift = 0, slot_mask = 0;
+    const uint8_t* pool = nullptr;
+    const uint32_t* pat_off = nullptr;
+    uint32_t q = 0, s = 0, min_len = 0, qmask = 0;
+};
+
 struct DeviceDfa {
-    int tier = 0;
+    int tier = 0;                    // 3 = q-gram filter for the SoA kernel, with the tier-2 table below as its exact fallback
+    DeviceGram gram;
     const void* table = nullptr;     // device
     uint32_t table_bytes = 0;
     const uint8_t* byte_class = nullptr;   // device, 256 B

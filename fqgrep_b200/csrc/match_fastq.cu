@@ -24,7 +24,7 @@ namespace fqg {
 namespace {
 
 constexpr uint32_t kTile = 16384;
-constexpr uint32_t kOverlap = 2048;
+constexpr uint32_t kOverlap = 1024;
 constexpr uint32_t kLoad = kTile + kOverlap;
 constexpr uint32_t kGroups = kLoad / 32;          // one bitmap word per 32 bytes
 constexpr uint32_t kListCap = kTile / 8;          // record starts per tile we can index (records >= 8 B on average)
@@ -139,30 +139,38 @@ struct RecordEval {
     }
 };
 
+// per-group shared memory: [mbarrier 8][prefix 8][misc 240][tile kLoad+32][bitmap][pre][list], 128-byte aligned
+constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u + kListCap * 2u) + 127u) & ~127u;
+
+// A CTA is up to 8 independent "tile groups" of THREADS threads (named barriers 1..8) that share one copy of the
+// automaton in shared memory; each group runs the tile loop on its own buffers, so one SM keeps up to 8 tiles in
+// different phases (copy / scan / look-back / match) in flight.
 template <int TIER, int THREADS>
-__global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+__global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t kWarps = THREADS / 32;
     constexpr uint32_t kGpt = (kGroups + THREADS - 1) / THREADS;   // contiguous groups per thread in the prefix pass
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t grp = threadIdx.x / THREADS, tid = threadIdx.x % THREADS, lane = tid & 31u, warp = tid >> 5;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1u), "n"(THREADS) : "memory"); };
 
     // ---- smem carve-up
     uint8_t* s_tab = smem;
-    uint8_t* s_cls = smem + table_smem_bytes;                                // 256 B
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cls + 256);              // 8-byte aligned: table_smem_bytes is a multiple of 128
+    uint8_t* s_cls = smem + table_smem_bytes;                                // 256 B, shared by all groups
+    uint8_t* s_grp = s_cls + 256 + (size_t)grp * kGroupBytes;                // this group's private region (128-byte aligned)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp);
     unsigned long long* s_prefix = reinterpret_cast<unsigned long long*>(s_bar + 1);
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2);               // warp sums [kWarps], [40] = tile id
-    uint8_t* s_tile = s_cls + 512;                                           // kLoad + 32, 128-byte aligned for the bulk copy
+    uint8_t* s_tile = s_grp + 256;                                           // kLoad + 32, 128-byte aligned for the bulk copy
     uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);   // kGroups + 2
     uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
     uint16_t* s_list = s_pre + kGroups + 2;                                   // kListCap
 
-    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, tid, THREADS);
+    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     if (TIER <= 2)
-        for (uint32_t i = tid; i < 256; i += THREADS) s_cls[i] = __ldg(dfa.byte_class + i);
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
     if (tid == 0) mbar_init(smem_addr(s_bar), 1);
     mbar_fence_init();
-    __syncthreads();
+    __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
 
     RecordEval<TIER> ev;
     ev.view.tab = smem_addr(s_tab);
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
 
     for (;;) {
         if (tid == 0) s_misc[40] = atomicAdd(a.tile_counter, 1u);
-        __syncthreads();
+        group_sync();
         if (s_misc[40] >= a.tile_count) break;
         const uint32_t t = a.tile_first + s_misc[40];                               // global tile id
         const uint64_t T0 = (uint64_t)t * kTile;
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
             if (real_avail < avail && (real_avail >> 5) == g) bits |= 1u << (real_avail & 31u);   // the virtual final newline
             s_bitmap[g] = bits;
         }
-        __syncthreads();
+        group_sync();
 
         // ---- exclusive prefix of newline counts per group (block scan; thread i owns groups [i*kGpt, (i+1)*kGpt))
         uint32_t cnt[kGpt], mine = 0;
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
             if (lane >= (uint32_t)d) incl += v;
         }
         if (lane == 31) s_misc[warp] = incl;
-        __syncthreads();
+        group_sync();
         uint32_t warp_base = 0;
 #pragma unroll
         for (uint32_t w = 0; w < kWarps; w++) if (w < warp) warp_base += s_misc[w];
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
             if (g <= kGroups) s_pre[g] = (uint16_t)run;
             run += cnt[k];
         }
-        __syncthreads();
+        group_sync();
         const uint32_t agg = (region & 31u) == 0 ? s_pre[region >> 5] : s_pre[region >> 5] + __popc(s_bitmap[region >> 5]);   // newlines in [0, region)
 
         // ---- decoupled look-back: newlines before this tile (within the launch)
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
                 if (T0 + region == stream_len) *a.lines_out = excl + agg;
             }
         }
-        __syncthreads();
+        group_sync();
         const unsigned long long Lt = *s_prefix;    // global index of this tile's first newline
 
         // ---- record starts in this tile -> s_list
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
             if (tid == 0) report(a, T0, kErrDensity);
             n_list = kListCap;
         }
-        __syncthreads();
+        group_sync();
 
         // ---- one thread per record
         const uint32_t n_groups_avail = (avail + 31u) >> 5;
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(THREADS) match_fastq_kernel(FastqArgs a, Devic
                 local_count += __popc(m);
             }
         }
-        __syncthreads();   // tile, bitmap and list are free for the next iteration
+        group_sync();   // tile, bitmap and list are free for the next iteration
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
@@ -436,18 +444,22 @@ template <int TIER>
 cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
     constexpr int THREADS = 128;
     const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : 0u;
-    const uint32_t smem = table_smem + 512u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u + kListCap * 2u + 128u;
+    const uint32_t budget = 227u * 1024u;
+    uint32_t groups = (budget - table_smem - 256u - 128u) / kGroupBytes;
+    if (groups > 8u) groups = 8u;
+    if (groups < 1u) groups = 1u;
+    if (a.tile_count < (uint32_t)sm_count * groups) {          // small inputs: spread the tiles over the SMs first
+        groups = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
+        if (groups < 1u) groups = 1u;
+    }
+    const uint32_t smem = table_smem + 256u + groups * kGroupBytes + 128u;
     auto kern = match_fastq_kernel<TIER, THREADS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    uint32_t grid = (uint32_t)(sm_count * per_sm);
-    if (grid > a.tile_count) grid = a.tile_count;
+    uint32_t grid = (a.tile_count + groups - 1u) / groups;
+    if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
     if (grid == 0) return cudaSuccess;
-    kern<<<grid, THREADS, smem, stream>>>(a, dfa, table_smem);
+    kern<<<grid, groups * THREADS, smem, stream>>>(a, dfa, table_smem);
     return cudaGetLastError();
 }
 
@@ -461,6 +473,7 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs
     switch (dfa.tier) {
         case 0: return launch_fastq_t<0>(dfa, a, sm_count, stream);
         case 1: return launch_fastq_t<1>(dfa, a, sm_count, stream);
+        // tier 3 (q-gram filter) is an SoA-kernel path; the fused FASTQ kernel walks its exact tier-2 table
         default: return launch_fastq_t<2>(dfa, a, sm_count, stream);
     }
 }

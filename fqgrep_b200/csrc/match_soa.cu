@@ -22,6 +22,93 @@
 namespace fqg {
 namespace {
 
+// ---- tier 3: q-gram sampling filter (gram_filter.cc) --------------------------------------------------------------
+struct GramView {
+    uint32_t bitmap;          // shared address of the bitmap
+    DeviceGram g;
+    const uint32_t* t32;      // exact fallback automaton (tier-2 encoding)
+    uint32_t cls;             // shared address of the byte -> class LUT
+    uint32_t dfa_start, dfa_accept;
+};
+constexpr int kMaxCand = 6;
+
+__device__ __forceinline__ bool gram_verify(const GramView& v, uint32_t p, uint32_t len, uint32_t gram, uint32_t e) {
+    uint32_t i = (gram * 0x85EBCA6Bu) >> v.g.slot_shift;
+    for (;;) {
+        const uint32_t val = __ldg(v.g.slot_val + i);
+        if (val == 0xFFFFFFFFu) return false;
+        if (__ldg(v.g.slot_key + i) == gram) {
+            const uint32_t id = val >> 5, j = val & 31u;
+            const uint32_t o0 = __ldg(v.g.pat_off + id), plen = __ldg(v.g.pat_off + id + 1) - o0;
+            const int32_t start = (int32_t)e - (int32_t)(v.g.q - 1u) - (int32_t)j;     // where the pattern would begin in the read
+            if (start >= 0 && (uint32_t)start + plen <= len) {
+                uint32_t k = 0;
+                while (k < plen && lds_u8(p + (uint32_t)start + k) == __ldg(v.g.pool + o0 + k)) k++;
+                if (k == plen) return true;
+            }
+        }
+        i = (i + 1u) & v.g.slot_mask;
+    }
+}
+
+// true iff some pattern of the set occurs in the read at shared address p
+__device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_t len) {
+    if (len < v.g.min_len) return false;
+    uint32_t cand_e[kMaxCand], cand_g[kMaxCand];
+    uint32_t ncand = 0;
+    const uint32_t sh0 = (p & 3u) * 8u;
+    uint32_t wp = p & ~3u;
+    uint32_t w0 = lds_u32_volatile(wp);
+    uint32_t lo = 0, hi = 0;              // 2-bit codes of the last 32 bases, newest in the low bits
+    uint32_t next_e = v.g.q - 1u;         // index of the base that ends the next sampled gram
+    const uint32_t nw = len >> 2;
+    auto probe = [&](uint32_t latest) {
+        while (next_e <= latest) {
+            const uint32_t gram = __funnelshift_r(lo, hi, 2u * (latest - next_e)) & v.g.qmask;
+            const uint32_t hb = (gram * 0x9E3779B1u) >> v.g.bitmap_shift;
+            uint32_t word;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(v.bitmap + ((hb >> 5) << 2)));
+            if ((word >> (hb & 31u)) & 1u) {
+                if (ncand < (uint32_t)kMaxCand) { cand_e[ncand] = next_e; cand_g[ncand] = gram; }
+                ncand++;
+            }
+            next_e += v.g.s;
+        }
+    };
+    for (uint32_t k = 0; k < nw; k++) {
+        wp += 4;
+        const uint32_t w1 = lds_u32_volatile(wp);
+        const uint32_t w = __funnelshift_r(w0, w1, sh0);
+        w0 = w1;
+        const uint32_t x = (w >> 1) & 0x03030303u;
+        const uint32_t p8 = (x * 0x40100401u) >> 24;      // first base of the word in the high bits
+        hi = (hi << 8) | (lo >> 24);
+        lo = (lo << 8) | p8;
+        probe(4u * k + 3u);
+    }
+    const uint32_t rem = len & 3u;
+    if (rem) {
+        const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh0);
+        for (uint32_t r = 0; r < rem; r++) {
+            const uint32_t c = (w >> (8u * r + 1u)) & 3u;
+            hi = (hi << 2) | (lo >> 30);
+            lo = (lo << 2) | c;
+            probe(4u * nw + r);
+        }
+    }
+    // exact verification of the few candidates, all lanes of the warp side by side so the L2 latencies overlap
+    // (plain per-lane loop, no warp collective: lanes of ragged batches leave this function at different points)
+    bool found = false;
+    const uint32_t rounds = ncand < (uint32_t)kMaxCand ? ncand : (uint32_t)kMaxCand;
+    for (uint32_t r = 0; r < rounds && !found; r++) found = gram_verify(v, p, len, cand_g[r], cand_e[r]);
+    if (ncand > (uint32_t)kMaxCand && !found) {          // too many candidates to remember: exact automaton walk through L2
+        uint32_t st = v.dfa_start;
+        for (uint32_t i = 0; i < len; i++) st = __ldg(v.t32 + st + lds_u8(v.cls + lds_u8(p + i)));
+        found = st >= v.dfa_accept;
+    }
+    return found;
+}
+
 struct BatchDesc {
     uint32_t s, e;        // this lane's read [s,e) as offsets into bases
     uintptr_t src;        // 16 B-aligned global address the warp's copy starts at (warp-uniform)
@@ -44,13 +131,19 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
 
     if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
+    if (TIER == 3) {
+        const uint4* src = reinterpret_cast<const uint4*>(dfa.gram.bitmap);
+        uint4* dst = reinterpret_cast<uint4*>(s_tab);
+        for (uint32_t i = threadIdx.x; i < dfa.gram.bitmap_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
     if (lane == 0)
         for (int s = 0; s < STAGES; s++) mbar_init(smem_addr(&s_bar[warp * STAGES + s]), 1);
     mbar_fence_init();
     __syncthreads();
 
-    DfaView<TIER> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls)};
+    DfaView<(TIER == 3 ? 2 : TIER)> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls)};
+    GramView gview{smem_addr(s_tab), dfa.gram, reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), dfa.start, dfa.accept_from};
     const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
     const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
     uint8_t* my_slots = s_slots + (size_t)warp * STAGES * slot_bytes;
@@ -107,9 +200,10 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
                 mbar_wait(smem_addr(&s_bar[warp * STAGES + stage]), (phase_bits >> stage) & 1u);
                 phase_bits ^= 1u << stage;
             }
-            if (len) st = walk_shared<TIER>(view, smem_addr(my_slots) + stage * slot_bytes + cur.off, len, st);
+            if (TIER == 3) st = gram_walk(gview, smem_addr(my_slots) + stage * slot_bytes + cur.off, len) ? st_accept : 0u;
+            else if (len) st = walk_shared(view, smem_addr(my_slots) + stage * slot_bytes + cur.off, len, st);
         } else if (len) {
-            st = walk_global<TIER>(view, b.bases + cur.s, len, st);
+            st = walk_global(view, b.bases + cur.s, len, st);
         }
         const uint32_t r = batch * 32u + lane;
         const bool sel = (r < b.n_reads) && ((st >= st_accept) != (b.invert != 0));
@@ -136,7 +230,7 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
     const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
     uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
     slot = (slot + 127u) & ~127u;
-    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : 0u;
+    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 3 ? ((dfa.gram.bitmap_bytes + 127u) & ~127u) : 0u;
     const uint32_t fixed = table_smem + 256u + 32u * STAGES * 8u + 128u;
     const uint32_t budget = 227u * 1024u;
     if (fixed + STAGES * slot > budget) {
@@ -164,6 +258,7 @@ cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_cou
     switch (dfa.tier) {
         case 0: return launch_t<0, 2>(dfa, b, sm_count, stream);
         case 1: return launch_t<1, 2>(dfa, b, sm_count, stream);
+        case 3: return launch_t<3, 2>(dfa, b, sm_count, stream);
         default: return launch_t<2, 2>(dfa, b, sm_count, stream);
     }
 }

@@ -74,7 +74,8 @@ int fqg_validate_fixed_pattern(const char* pattern, int protein);
 /* Compiled-automaton introspection (used by the CPU tests to check the compilers without a GPU). */
 typedef struct fqg_dfa_info {
     uint32_t n_states, n_classes, start, accept_from;
-    uint32_t tier;          /* 0: byte-indexed table in shared memory, 1: class-indexed in shared memory, 2: class-indexed in L2 */
+    uint32_t tier;          /* 0: 4-base-stride table in shared memory, 1: class-indexed table in shared memory,
+                               2: class-indexed table in L2, 3: q-gram filter in shared memory + exact verify (tier-2 table as fallback) */
     uint32_t table_bytes;   /* device table footprint */
 } fqg_dfa_info;
 int fqg_matcher_dfa_info(const fqg_matcher* m, fqg_dfa_info* out);

@@ -107,7 +107,53 @@ def test_all_three_table_tiers():
         tiers.append(m.dfa_info().tier)
         cnt = check(F.FIXED_SET, pats, False, True, bases, offs)
         assert cnt > 0
-    assert tiers == [0, 1, 2]
+    assert tiers == [0, 1, 3]     # the large set runs the q-gram filter (tier 3)
+
+
+def test_tier2_l2_automaton_for_large_sets_of_short_patterns():
+    rng = np.random.default_rng(12)
+    pats = list({"".join("ACGT"[i] for i in rng.integers(0, 4, int(L))) for L in rng.integers(6, 8, 6000)})
+    m = F.Matcher(F.FIXED_SET, pats, opts(False, False))
+    assert m.dfa_info().tier == 2
+    mat = synth.bases(20_000, L=40, seed=3)
+    bases, offs = synth.soa(mat)
+    cnt = check(F.FIXED_SET, pats, False, False, bases, offs)
+    assert 0 < cnt < 20_000
+
+
+def test_gram_filter_edge_cases():
+    """Tier 3: variable pattern lengths, reverse complement, N in patterns and reads, candidate overflow, ragged reads."""
+    rng = np.random.default_rng(21)
+    pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, int(L))) for L in rng.integers(9, 40, 4000)]
+    pats += ["ACGTNNNNACGTAC", "NNNNNNNNNN", "GATTACAGATTACAGATTACA"]
+    for rc in (False, True):
+        m = F.Matcher(F.FIXED_SET, pats, opts(False, rc))
+        assert m.dfa_info().tier == 3
+    seqs = []
+    r = random.Random(4)
+    for i in range(6000):
+        L = r.choice([0, 5, 8, 9, 10, 17, 33, 64, 150, 151, 250])
+        s = "".join(r.choice("ACGTN" if i % 5 == 0 else "ACGT") for _ in range(L))
+        if i % 11 == 0 and L >= 40:
+            p = pats[r.randrange(len(pats))]
+            if len(p) <= L:
+                o = r.randrange(L - len(p) + 1)
+                s = s[:o] + p + s[o + len(p):]
+        if i % 13 == 0 and L >= 40:      # reverse-complement plant
+            p = O.revcomp(pats[r.randrange(4000)]).decode()
+            if len(p) <= L:
+                o = r.randrange(L - len(p) + 1)
+                s = s[:o] + p + s[o + len(p):]
+        seqs.append(s)
+    # reads made of pattern prefixes: many filter hits, few real matches (exercises the candidate overflow fallback)
+    for i in range(300):
+        seqs.append("".join(pats[r.randrange(4000)][:12] for _ in range(12)))
+    seqs.append("N" * 150)
+    seqs.append("ACGTNNNNACGTAC")
+    bases, offs = soa(seqs)
+    for inv, rc in ((False, False), (False, True), (True, True)):
+        cnt = check(F.FIXED_SET, pats, inv, rc, bases, offs)
+        assert 0 < cnt < len(seqs)
 
 
 def test_protein_alphabet(kat):
