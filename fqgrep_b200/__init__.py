@@ -3,5 +3,6 @@
 The product is libfqgrep_b200.so (C ABI, include/fqgrep_b200.h); this package is the thin host-side mirror of
 the reference's Matcher / MatcherFactory API over it.  There is no CPU matching path.
 """
-from .matcher import (FIXED, FIXED_SET, INTERLEAVED, NAMES, PAIRED, REGEX, REGEX_SET, SINGLE, FqgrepError, Matcher,  # noqa: F401
-                      MatcherFactory, MatcherOpts, context, validate_fixed_pattern, write_selected)
+from .matcher import (BITMASK, BITMASK_SET, FIXED, FIXED_SET, INTERLEAVED, NAMES, PAIRED, REGEX, REGEX_SET, SINGLE, FqgrepError, Matcher,  # noqa: F401
+                      MatcherFactory, MatcherOpts, context, expand_iupac, expand_iupac_fixed_pattern, expand_iupac_regex, validate_fixed_pattern,
+                      write_selected)

@@ -478,6 +478,12 @@ int fqg_matcher_new(int kind, const uint8_t* blob, const uint64_t* offsets, uint
         case FQG_REGEX_SET:
             if (!compile_regex_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
             break;
+        case FQG_BITMASK:
+            if (n != 1) return fail(FQG_E_INVALID_ARG, "FQG_BITMASK takes exactly one pattern");
+            // fallthrough
+        case FQG_BITMASK_SET:
+            if (!compile_bitmask_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
+            break;
         case FQG_NAMES:
             for (auto& p : pats) if (p.size() >= (1u << 24)) return fail(FQG_E_TOO_LARGE, "read name longer than 2^24 bytes");
             build_name_table(pats, &m->names);
@@ -676,6 +682,24 @@ int fqg_grep_fastq_host(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_
                         uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res) {
     if (!c || !m || !res) return fail(FQG_E_INVALID_ARG, "NULL argument");
     return grep_fastq(c, m, mode, r1, n1, r2, n2, false, unit_mask_out, unit_mask_words, res, c->stream);
+}
+
+int fqg_iupac_expand(const char* pattern, int to_regex, char* out, size_t cap, size_t* out_len) {
+    if (!pattern || !out_len) return fail(FQG_E_INVALID_ARG, "NULL argument");
+    std::string joined;
+    if (to_regex) joined = iupac_to_regex(pattern);
+    else {
+        std::vector<std::string> v;
+        std::string err;
+        if (!expand_iupac_fixed(pattern, &v, &err)) return fail(FQG_E_PATTERN, err);
+        for (size_t i = 0; i < v.size(); i++) { if (i) joined.push_back('\n'); joined += v[i]; }
+    }
+    *out_len = joined.size();
+    if (out) {
+        if (cap < joined.size()) return fail(FQG_E_INVALID_ARG, "output buffer too small");
+        std::memcpy(out, joined.data(), joined.size());
+    }
+    return FQG_OK;
 }
 
 int fqg_fastq_split(const uint8_t* buf, size_t n, uint32_t parts, uint64_t* cuts) {

@@ -37,6 +37,13 @@ struct CompileError {
 // Returns false and fills err (message starts with "Invalid regular expression: '<p>'" like matcher.rs:499).
 bool compile_regex_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err);
 
+// --iupac bit-mask needles (BitMaskMatcher / BitMaskSetMatcher, matcher.rs:307-487) -> DFA.
+bool compile_bitmask_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err);
+const uint8_t* iupac_masks();   // IUPAC_MASKS, mod.rs:14-53
+// --iupac expand / regex rewrites (mod.rs:70-118, driven from main.rs:339-360)
+bool expand_iupac_fixed(const std::string& pattern, std::vector<std::string>* out, std::string* err);
+std::string iupac_to_regex(const std::string& pattern);
+
 // Literal set -> Aho-Corasick DFA (replaces aho_corasick::AhoCorasick::new, matcher.rs:297-298, and
 // bstr find, matcher.rs:204).  with_revcomp adds rc(pattern) for every pattern.
 bool compile_literal_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err);

@@ -845,20 +845,17 @@ void finalize_dfa(uint32_t n_states, uint32_t n_classes, std::vector<uint32_t>& 
     out->always = out->start >= out->accept_from && absorbing(part[start]);
 }
 
-bool compile_regex_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err) {
+namespace {
+bool determinize(Nfa& nfa, int32_t nfa_start, Dfa* out, std::string* err);
+
+// NFA for the union of the ASTs (plus their reverse-complement languages), then the shared determiniser.
+bool compile_asts(const std::vector<AstP>& asts, bool with_revcomp, Dfa* out, std::string* err) {
     Nfa nfa;
     int32_t nfa_start = -1;
     try {
         NState m{NState::Match, Look::StartText, 0, -1, -1};
         int32_t match = nfa.add(m);
-        for (auto& p : patterns) {
-            AstP ast;
-            try {
-                ast = Parser(p).parse();
-            } catch (ParseError& e) {
-                *err = "Invalid regular expression: '" + p + "' (" + e.msg + ")";
-                return false;
-            }
+        for (auto& ast : asts) {
             int32_t e1 = nfa.build(*ast, match);
             if (nfa_start < 0) nfa_start = e1;
             else { NState s{NState::Split, Look::StartText, 0, nfa_start, e1}; nfa_start = nfa.add(s); }
@@ -877,7 +874,56 @@ bool compile_regex_set(const std::vector<std::string>& patterns, bool with_revco
         *err = "Failed to build regex set from patterns (" + e.msg + ")";
         return false;
     }
+    return determinize(nfa, nfa_start, out, err);
+}
+}  // namespace
 
+bool compile_regex_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err) {
+    std::vector<AstP> asts;
+    for (auto& p : patterns) {
+        try {
+            asts.push_back(Parser(p).parse());
+        } catch (ParseError& e) {
+            *err = "Invalid regular expression: '" + p + "' (" + e.msg + ")";
+            return false;
+        }
+    }
+    return compile_asts(asts, with_revcomp, out, err);
+}
+
+// --iupac bit-mask (BitMaskMatcher / BitMaskSetMatcher, matcher.rs:307-487): a needle is a fixed-length string of
+// byte classes.  With IUPAC_MASKS m[] (mod.rs:14-53), needle symbol n_i = m[pattern byte]:
+//   needle has an ambiguity code (or a non-IUPAC byte): position i accepts every byte b with (n_i & m[b]) == m[b]
+//       (matcher.rs:343-348) -- which includes every byte whose mask is 0;
+//   needle is pure ACGT(U): the additive rolling hash (matcher.rs:320-342) only lets windows through whose masks sum to
+//       the needle's, so position i accepts exactly the bytes with m[b] == n_i.
+// The empty needle matches every read, like the loop at matcher.rs:330 does for offset 0.
+bool compile_bitmask_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err) {
+    const uint8_t* m = iupac_masks();
+    std::vector<AstP> asts;
+    for (auto& p : patterns) {
+        bool has_iupac = false;
+        for (unsigned char ch : p) {
+            const uint8_t v = m[ch];
+            if (!(v == 1 || v == 2 || v == 4 || v == 8)) has_iupac = true;
+        }
+        AstP cat;
+        for (unsigned char ch : p) {
+            auto cls = mk(Ast::Bytes);
+            bool any = false;
+            for (int b = 0; b < 256; b++) {
+                const bool ok = has_iupac ? ((m[ch] & m[b]) == m[b]) : (m[b] == m[ch]);
+                if (ok) { bs_set(cls->set, b); any = true; }
+            }
+            cat = mk_cat2(std::move(cat), any ? std::move(cls) : mk(Ast::Never));
+        }
+        asts.push_back(cat ? std::move(cat) : mk(Ast::Empty));
+    }
+    return compile_asts(asts, with_revcomp, out, err);
+}
+
+namespace {
+bool determinize(Nfa& nfa, int32_t nfa_start, Dfa* out, std::string* err) {
     Dfa d;
     compute_byte_classes(nfa, d.byte_class, &d.n_classes);
     std::vector<int> rep(d.n_classes, -1);
@@ -944,6 +990,57 @@ bool compile_regex_set(const std::vector<std::string>& patterns, bool with_revco
     finalize_dfa(n, d.n_classes, next, accept, 0, true, &d);
     *out = std::move(d);
     return true;
+}
+}  // namespace
+
+const uint8_t* iupac_masks() {
+    static uint8_t t[256];
+    static bool init = false;
+    if (!init) {
+        const struct { char c; uint8_t m; } kv[] = {{'A', 1}, {'C', 2}, {'G', 4}, {'T', 8}, {'U', 8}, {'M', 3}, {'R', 5}, {'W', 9}, {'S', 6}, {'Y', 10},
+                                                    {'K', 12}, {'V', 7}, {'H', 11}, {'D', 13}, {'B', 14}, {'N', 15}};
+        for (auto& e : kv) { t[(uint8_t)e.c] = e.m; t[(uint8_t)e.c + 32] = e.m; }
+        init = true;
+    }
+    return t;
+}
+
+// expand_iupac_fixed_pattern (mod.rs:70-97): depth-first over A,C,G,T, at most 10 000 results.
+bool expand_iupac_fixed(const std::string& pattern, std::vector<std::string>* out, std::string* err) {
+    const uint8_t* m = iupac_masks();
+    out->clear();
+    std::string prefix;
+    bool failed = false;
+    auto rec = [&](auto&& self, size_t i) -> void {
+        if (failed) return;
+        if (out->size() >= 10000) {
+            *err = "IUPAC expansion exceeded 10000 patterns for input '" + pattern + "'";
+            failed = true;
+            return;
+        }
+        if (i == pattern.size()) { out->push_back(prefix); return; }
+        for (char base : {'A', 'C', 'G', 'T'})
+            if (m[(uint8_t)base] & m[(uint8_t)pattern[i]]) {
+                prefix.push_back(base);
+                self(self, i + 1);
+                prefix.pop_back();
+            }
+    };
+    rec(rec, 0);
+    return !failed;
+}
+
+// expand_iupac_regex (mod.rs:101-118)
+std::string iupac_to_regex(const std::string& pattern) {
+    const uint8_t* m = iupac_masks();
+    std::string o;
+    for (unsigned char ch : pattern) {
+        std::string bases;
+        for (char base : {'A', 'C', 'G', 'T'}) if (m[(uint8_t)base] & m[ch]) bases.push_back(base);
+        if (bases.size() == 1) o += bases;
+        else { o.push_back('['); o += bases; o.push_back(']'); }
+    }
+    return o;
 }
 
 std::string validate_fixed_pattern(const std::string& pattern, bool protein) {

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _ffi
 
-FIXED, FIXED_SET, REGEX, REGEX_SET, NAMES = 0, 1, 2, 3, 4
+FIXED, FIXED_SET, REGEX, REGEX_SET, NAMES, BITMASK, BITMASK_SET = 0, 1, 2, 3, 4, 5, 6
 SINGLE, INTERLEAVED, PAIRED = 0, 1, 2
 INVERT_MATCH, REVERSE_COMPLEMENT = 1, 2
 
@@ -172,13 +172,49 @@ def write_selected(mask_words, r1, r2=None, mode=SINGLE, split=False):
     return out[:n1.value].tobytes()
 
 
+def expand_iupac_fixed_pattern(pattern):
+    """expand_iupac_fixed_pattern (src/lib/mod.rs:70-97): all ACGT strings an IUPAC pattern stands for (<= 10 000)."""
+    n = C.c_size_t(0)
+    _check(_ffi.lib().fqg_iupac_expand(pattern.encode(), 0, None, 0, C.byref(n)))
+    buf = C.create_string_buffer(n.value + 1)
+    _check(_ffi.lib().fqg_iupac_expand(pattern.encode(), 0, buf, n.value, C.byref(n)))
+    return buf.raw[:n.value].decode().split("\n")
+
+
+def expand_iupac_regex(pattern):
+    """expand_iupac_regex (src/lib/mod.rs:101-118): "GATK" -> "GAT[GT]"."""
+    n = C.c_size_t(0)
+    _check(_ffi.lib().fqg_iupac_expand(pattern.encode(), 1, None, 0, C.byref(n)))
+    buf = C.create_string_buffer(n.value + 1)
+    _check(_ffi.lib().fqg_iupac_expand(pattern.encode(), 1, buf, n.value, C.byref(n)))
+    return buf.raw[:n.value].decode()
+
+
+def expand_iupac(pattern, regexp, fixed_strings, iupac):
+    """expand_iupac of the reference (src/main.rs:315-372).  iupac in {"never","expand","regex","bit-mask"}.
+    Returns (pattern, regexp, fixed_strings, bitencs) ready for MatcherFactory.new_matcher."""
+    if iupac == "never" or not fixed_strings:
+        return pattern, list(regexp), fixed_strings, None
+    patterns = [pattern] if pattern is not None else list(regexp)
+    if iupac == "expand":
+        return None, [e for p in patterns for e in expand_iupac_fixed_pattern(p)], True, None
+    if iupac == "regex":
+        return None, [expand_iupac_regex(p) for p in patterns], False, None
+    if iupac == "bit-mask":
+        if len(patterns) == 1:
+            return patterns[0], [], True, patterns
+        return None, patterns, True, patterns
+    raise ValueError(iupac)
+
+
 class MatcherFactory:
-    """MatcherFactory of the reference (matcher.rs:641-686); the bitmask variants are out of scope."""
+    """MatcherFactory of the reference (matcher.rs:641-686).  `bitencs` (the reference passes Vec<BitEnc>) is the list
+    of IUPAC pattern strings; encoding to 4-bit masks happens inside the library."""
 
     @staticmethod
     def new_matcher(pattern, fixed_strings, regexp, bitencs=None, match_opts=MatcherOpts()):
         if bitencs is not None:
-            raise FqgrepError(-1, "--iupac bit-mask matchers are not part of the B200 hot path yet")
+            return Matcher(BITMASK if pattern is not None else BITMASK_SET, list(bitencs), match_opts)
         if pattern is not None:
             return Matcher(FIXED if fixed_strings else REGEX, [pattern], match_opts)
         return Matcher(FIXED_SET if fixed_strings else REGEX_SET, list(regexp), match_opts)

@@ -41,7 +41,9 @@ typedef enum fqg_kind {
     FQG_FIXED_SET = 1,  /* FixedStringSetMatcher   matcher.rs:240-305  (-F with -e/-f)                    */
     FQG_REGEX = 2,      /* RegexMatcher            matcher.rs:489-532  (positional pattern)               */
     FQG_REGEX_SET = 3,  /* RegexSetMatcher         matcher.rs:534-599  (-e/-f without -F)                 */
-    FQG_NAMES = 4       /* QueryNameMatcher        matcher.rs:601-639  (-N)                               */
+    FQG_NAMES = 4,      /* QueryNameMatcher        matcher.rs:601-639  (-N)                               */
+    FQG_BITMASK = 5,    /* BitMaskMatcher          matcher.rs:384-432  (--iupac bit-mask, one pattern)    */
+    FQG_BITMASK_SET = 6 /* BitMaskSetMatcher       matcher.rs:434-487  (--iupac bit-mask, -e/-f)          */
 } fqg_kind;
 
 /* MatcherOpts, src/lib/matcher.rs:20-28 */
@@ -70,6 +72,11 @@ void fqg_matcher_free(fqg_matcher* m);
 /* Replaces validate_fixed_pattern (matcher.rs:128-147).  0 if valid; FQG_E_PATTERN and the reference's
  * message ("Fixed pattern must contain only DNA bases: A .. [X] .. GTG") in fqg_last_error() otherwise. */
 int fqg_validate_fixed_pattern(const char* pattern, int protein);
+
+/* --iupac expand / regex (src/lib/mod.rs:70-118, applied at src/main.rs:339-360): rewrites ONE -F pattern.
+ * to_regex=0: the expanded fixed strings joined by '\n' (error beyond 10 000, same text as the reference);
+ * to_regex=1: the character-class regex ("GATK" -> "GAT[GT]").  Call with out=NULL to size the buffer. */
+int fqg_iupac_expand(const char* pattern, int to_regex, char* out, size_t cap, size_t* out_len);
 
 /* Compiled-automaton introspection (used by the CPU tests to check the compilers without a GPU). */
 typedef struct fqg_dfa_info {

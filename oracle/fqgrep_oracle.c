@@ -617,7 +617,33 @@ static int regex_is_match(const Regex *re, const uint8_t *h, size_t n) {
 }
 
 /* ------------------------------------------------------------------ matcher */
-enum { FQO_FIXED = 0, FQO_FIXED_SET = 1, FQO_REGEX = 2, FQO_REGEX_SET = 3, FQO_NAMES = 4 };
+enum { FQO_FIXED = 0, FQO_FIXED_SET = 1, FQO_REGEX = 2, FQO_REGEX_SET = 3, FQO_NAMES = 4, FQO_BITMASK = 5, FQO_BITMASK_SET = 6 };
+
+/* IUPAC_MASKS, src/lib/mod.rs:14-53 */
+static uint8_t IUPAC[256]; static int iupac_init = 0;
+static void init_iupac(void) {
+    if (iupac_init) return;
+    const char *k = "ACGTUMRWSYKVHDBN"; const uint8_t v[] = {1, 2, 4, 8, 8, 3, 5, 9, 6, 10, 12, 7, 11, 13, 14, 15};
+    for (int i = 0; k[i]; i++) { IUPAC[(uint8_t)k[i]] = v[i]; IUPAC[(uint8_t)k[i] + 32] = v[i]; }
+    iupac_init = 1;
+}
+/* bitenc_match_offsets / bitenc_find, src/lib/matcher.rs:307-375, restated literally (rolling additive hash included) */
+static int bitenc_find(const uint8_t *bases, size_t nb, const uint8_t *needle, size_t nn, int has_iupac) {
+    if (nb < nn) return 0;
+    size_t bases_hash = 0, needle_hash = 0;
+    if (!has_iupac) for (size_t i = 0; i < nn; i++) needle_hash += needle[i];
+    for (size_t offset = 0; offset <= nb - nn; offset++) {
+        if (!has_iupac) {
+            if (offset == 0) { bases_hash = 0; for (size_t i = 0; i < nn; i++) bases_hash += bases[i]; }
+            else { bases_hash += bases[offset + nn - 1]; bases_hash -= bases[offset - 1]; }
+            if (bases_hash != needle_hash) continue;
+        }
+        size_t i = 0;
+        for (; i < nn; i++) { uint8_t base = bases[offset + i]; if ((needle[i] & base) != base) break; }
+        if (i == nn) return 1;
+    }
+    return 0;
+}
 typedef struct fqo_matcher {
     int kind, invert, revcomp, npat;
     uint8_t **pat; size_t *plen;
@@ -679,6 +705,21 @@ static int found_in(const fqo_matcher *m, const uint8_t *s, size_t n) {
         case FQO_FIXED_SET: for (int i = 0; i < m->npat; i++) if (m->plen[i] == 0 || memmem(s, n, m->pat[i], m->plen[i])) return 1; return 0;
         case FQO_REGEX: return regex_is_match(&m->re[0], s, n);
         case FQO_REGEX_SET: for (int i = 0; i < m->npat; i++) if (regex_is_match(&m->re[i], s, n)) return 1; return 0;
+        case FQO_BITMASK: case FQO_BITMASK_SET: {      /* matcher.rs:392-395, 442-450: encode(bases) then any needle */
+            init_iupac();
+            uint8_t stackbuf[512], *enc = n <= sizeof stackbuf ? stackbuf : malloc(n);
+            for (size_t i = 0; i < n; i++) enc[i] = IUPAC[s[i]];
+            int found = 0;
+            for (int k = 0; k < m->npat && !found; k++) {
+                uint8_t nbuf[512], *ne = m->plen[k] <= sizeof nbuf ? nbuf : malloc(m->plen[k]);
+                int has_iupac = 0;
+                for (size_t i = 0; i < m->plen[k]; i++) { ne[i] = IUPAC[m->pat[k][i]]; if (!(ne[i] == 1 || ne[i] == 2 || ne[i] == 4 || ne[i] == 8)) has_iupac = 1; }
+                found = bitenc_find(enc, n, ne, m->plen[k], has_iupac);
+                if (ne != nbuf) free(ne);
+            }
+            if (enc != stackbuf) free(enc);
+            return found;
+        }
         default: return 1;   /* names: bases_match is `!invert` (matcher.rs:616-618) */
     }
 }
@@ -724,6 +765,39 @@ int fqo_validate_fixed(const char *pattern, int protein, char *err, int errlen) 
         i += l;
     }
     return 0;
+}
+
+/* expand_iupac_fixed_pattern (mod.rs:70-97) and expand_iupac_regex (mod.rs:101-118).  Results joined by '\n'.
+ * Returns length, or -1 when the 10 000 limit is hit (err gets the reference's message). */
+static int expand_rec(const uint8_t *p, size_t n, size_t i, char *prefix, char *out, size_t cap, size_t *olen, int *count, const char *orig, char *err, int errlen) {
+    if (*count >= 10000) { if (err) snprintf(err, errlen, "IUPAC expansion exceeded 10000 patterns for input '%s'", orig); return -1; }
+    if (i == n) {
+        if (*olen + n + 1 > cap) return -1;
+        if (*count) out[(*olen)++] = '\n';
+        memcpy(out + *olen, prefix, n); *olen += n; (*count)++;
+        return 0;
+    }
+    for (const char *b = "ACGT"; *b; b++)
+        if (IUPAC[(uint8_t)*b] & IUPAC[p[i]]) { prefix[i] = *b; if (expand_rec(p, n, i + 1, prefix, out, cap, olen, count, orig, err, errlen)) return -1; }
+    return 0;
+}
+long fqo_iupac_expand(const char *pattern, int to_regex, char *out, size_t cap, char *err, int errlen) {
+    init_iupac();
+    size_t n = strlen(pattern), olen = 0;
+    if (to_regex) {
+        for (size_t i = 0; i < n; i++) {
+            char bases[5]; int nb = 0;
+            for (const char *b = "ACGT"; *b; b++) if (IUPAC[(uint8_t)*b] & IUPAC[(uint8_t)pattern[i]]) bases[nb++] = *b;
+            if (olen + 8 > cap) return -1;
+            if (nb == 1) out[olen++] = bases[0];
+            else { out[olen++] = '['; memcpy(out + olen, bases, nb); olen += nb; out[olen++] = ']'; }
+        }
+        return (long)olen;
+    }
+    char *prefix = malloc(n + 1); int count = 0;
+    int rc = expand_rec((const uint8_t *)pattern, n, 0, prefix, out, cap, &olen, &count, pattern, err, errlen);
+    free(prefix);
+    return rc ? -1 : (long)olen;
 }
 
 /* ------------------------------------------------------------- FASTQ records */

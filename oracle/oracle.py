@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfqgrep_oracle.so")
 
-FIXED, FIXED_SET, REGEX, REGEX_SET, NAMES = 0, 1, 2, 3, 4
+FIXED, FIXED_SET, REGEX, REGEX_SET, NAMES, BITMASK, BITMASK_SET = 0, 1, 2, 3, 4, 5, 6
 SINGLE, INTERLEAVED, PAIRED = 0, 1, 2
 ERRORS = {-1: "InvalidStart", -2: "InvalidSep", -3: "UnequalLengths", -4: "UnexpectedEnd",
           -5: "OddInterleaved", -6: "OutOfSync", -7: "IdMismatch"}
@@ -44,6 +44,8 @@ def lib():
         L.fqo_grep.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int,
                                C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p,
                                C.POINTER(C.c_size_t)]
+        L.fqo_iupac_expand.restype = C.c_long
+        L.fqo_iupac_expand.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_int]
         L.fqo_match_soa.restype = C.c_int64
         L.fqo_match_soa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         _lib = L
@@ -142,6 +144,23 @@ def validate_fixed(pattern, protein=False):
     err = C.create_string_buffer(1024)
     rc = lib().fqo_validate_fixed(pattern.encode("utf-8"), int(protein), err, 1024)
     return None if rc == 0 else err.value.decode("utf-8", "replace")
+
+
+def expand_iupac_fixed_pattern(pattern):
+    """mod.rs:70-97 -> list of expanded fixed strings; raises OracleError beyond 10 000."""
+    out = C.create_string_buffer(1 << 22)
+    err = C.create_string_buffer(512)
+    n = lib().fqo_iupac_expand(pattern.encode(), 0, out, len(out), err, 512)
+    if n < 0:
+        raise OracleError(err.value.decode())
+    return out.raw[:n].decode().split("\n")
+
+
+def expand_iupac_regex(pattern):
+    """mod.rs:101-118"""
+    out = C.create_string_buffer(16 * len(pattern) + 16)
+    n = lib().fqo_iupac_expand(pattern.encode(), 1, out, len(out), None, 0)
+    return out.raw[:n].decode()
 
 
 def new_matcher(pattern, fixed_strings, regexp, invert=False, revcomp=False):

@@ -63,6 +63,25 @@ kat = {
   "e2e_exit": {"src": "src/main.rs:1303-1318", "files": [["GTCAGC"],["AGTGCG"],["GGGTCTG"]],
     "cases": [{"pattern": "*", "fixed": F, "exit": 2}, {"pattern": "^T", "fixed": F, "exit": 1},
               {"pattern": "GTCAGC", "fixed": T, "exit": 0}, {"pattern": "^T", "fixed": T, "exit": 2}]},
+  # (rc, pattern, seq, expect), invert=0 only
+  "bitmask_iupac": {"src": "src/lib/matcher.rs:1148-1190", "cases": [
+    [F,"GATK","GATG",T],[F,"GATK","GATT",T],[F,"GATK","GATA",F],[F,"GATK","GATC",F],[F,"GATR","GATGA",T],[F,"GATR","GATA",T],
+    [F,"GATR","GATGT",T],[F,"N","A",T],[F,"N","C",T],[F,"N","G",T],[F,"N","T",T],[F,"ANA","ACA",T],[F,"ANA","AAA",T],[T,"GATK","CATC",T]]},
+  "bitmask_set_iupac": {"src": "src/lib/matcher.rs:1234-1270", "cases": [
+    [F,["GATK","ANA"],"GATG",T],[F,["GATK","ANA"],"ACA",T],[F,["GATK","ANA"],"CCCC",F],[F,["R","Y"],"A",T],[F,["R","Y"],"C",T],[F,["R","Y"],"AAAA",T]]},
+  "bitmask_short_read": {"src": "src/lib/matcher.rs:1079-1110", "pattern": "ACGTACGT", "seq": "ACG", "expect": F},
+  "iupac_expand": {"src": "src/lib/mod.rs:236-262", "fixed": [
+      ["GATTACA", ["GATTACA"]], ["GATMACA", ["GATAACA","GATCACA"]],
+      ["GRTBANA", ["GATCAAA","GATCACA","GATCAGA","GATCATA","GATGAAA","GATGACA","GATGAGA","GATGATA","GATTAAA","GATTACA","GATTAGA","GATTATA",
+                   "GGTCAAA","GGTCACA","GGTCAGA","GGTCATA","GGTGAAA","GGTGACA","GGTGAGA","GGTGATA","GGTTAAA","GGTTACA","GGTTAGA","GGTTATA"]]],
+    "regex": [["GATTACA","GATTACA"],["GATMACA","GAT[AC]ACA"],["GRTBANA","G[AG]T[CGT]A[ACGT]A"],["GATUCA","GATTCA"]],
+    "limit": {"pattern": "NNNNNNNN", "message_contains": "10000"}},
+  # every mode in {expand, regex, bit-mask} must give the same count (main.rs:1408-1522); -F set
+  "e2e_iupac_modes": {"src": "src/main.rs:1408-1522", "cases": [
+    {"seqs": ["GATG","GATT","GATA","GATC"], "patterns": ["GATK"], "invert": F, "count": 2},
+    {"seqs": ["GATG","ACCA","TTTT","CCCC"], "patterns": ["GATK","ACS"], "invert": F, "count": 2},
+    {"seqs": ["GATG","GATT","GATA","GATC"], "patterns": ["GATK"], "invert": T, "count": 2},
+    {"seqs": ["AAAT","ACGT","TTTT"], "patterns": ["AN"], "invert": F, "count": 2}]},
   "e2e_protein": {"src": "src/main.rs:1023-1057", "reads": ["MQRFPW","MQRHKD","RHKDEW","WYFPQL"],
     "cases": [[T,["MQR"],["MQRFPW","MQRHKD"]],[T,["FPW"],["MQRFPW"]],[T,["ZZZ"],[]],
               [F,["^MQR"],["MQRFPW","MQRHKD"]],[F,["^MQR","^RHK"],["MQRFPW","MQRHKD","RHKDEW"]],[F,["^ZZZ","^YYY"],[]]]},
