@@ -123,6 +123,8 @@ def main():
     run_soa("cfg1_fixed_10M", F.FIXED, ["GACGAGATTA"], False, False, 10_000_000, lit, out)
     run_soa("cfg2_two_regex_rc_25M", F.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], False, True, 25_000_000, lit, out)
     run_soa("cfg4_class_regex_invert_25M", F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, False, 25_000_000, lit, out)
+    p200 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 12)) for _ in range(200)]
+    run_soa("extra_tier1_200x12mers_25M", F.FIXED_SET, p200, False, True, 25_000_000, p200[:20], out)
     run_soa("cfg5a_1000_fixed_25M", F.FIXED_SET, p1k, False, False, 25_000_000, p1k[:50], out)
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
     run_names(out)

@@ -151,6 +151,19 @@ def test_names_one_million_ids_scaled_down():
     both(F.NAMES, names, False, False, f1, f2, mode=F.PAIRED, check_output=False)
 
 
+def test_large_pattern_set_through_fastq_path():
+    """A tier-3 matcher (q-gram filter in the SoA kernel) runs its exact tier-2 automaton inside the fused FASTQ kernel."""
+    rng = np.random.default_rng(17)
+    pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(5000)]
+    n = 40_000
+    mat = synth.bases(n, seed=6)
+    synth.plant(mat, pats[:100], rate=0.03)
+    f1 = synth.fastq(mat)
+    assert F.Matcher(F.FIXED_SET, pats, opts(False, True)).dfa_info().tier == 3
+    g = both(F.FIXED_SET, pats, False, True, f1, check_output=False)
+    assert 0 < g["count"] < n
+
+
 def test_format_edge_cases():
     seqs = ["ACGT", "", "TTACGG", "N", "ACGTACGTAC" * 30]
     for crlf in (False, True):
