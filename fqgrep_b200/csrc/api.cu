@@ -167,7 +167,7 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
         if (m->tier == 3) {
             const GramFilter& g = m->gram;
             DeviceGram& d = out->gram;
-            d.bitmap = it->second.g_bitmap; d.bitmap_bytes = (uint32_t)g.bitmap.size() * 4; d.bitmap_shift = 32 - g.bitmap_bits_log2;
+            d.bitmap = it->second.g_bitmap; d.bitmap_bytes = (uint32_t)g.bitmap.size() * 4; d.bitmap_shift = 32 - (g.bitmap_bits_log2 - 5);     // hash -> WORD index
             d.slot_key = it->second.g_key; d.slot_val = it->second.g_val; d.slot_shift = 32 - g.slots_log2; d.slot_mask = (1u << g.slots_log2) - 1;
             d.pool = it->second.g_pool; d.pat_off = it->second.g_pat_off;
             d.q = g.q; d.s = g.s; d.min_len = g.min_len; d.qmask = g.qmask;

@@ -17,7 +17,7 @@ namespace fqg {
 // Device view of the q-gram filter (tier 3); see gram_filter.cc / match_soa.cu.
 struct DeviceGram {
     const uint32_t* bitmap = nullptr;    // device copy, staged into shared memory by the kernel
-    uint32_t bitmap_bytes = 0, bitmap_shift = 0;   // bit index = (gram * 0x9E3779B1) >> bitmap_shift
+    uint32_t bitmap_bytes = 0, bitmap_shift = 0;   // word index = (gram * 0x9E3779B1) >> bitmap_shift; 2 bits from a second hash
     const uint32_t* slot_key = nullptr;
     const uint32_t* slot_val = nullptr;
     uint32_t slot_shift = 0, slot_mask = 0;

@@ -65,10 +65,12 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
     auto probe = [&](uint32_t latest) {
         while (next_e <= latest) {
             const uint32_t gram = __funnelshift_r(lo, hi, 2u * (latest - next_e)) & v.g.qmask;
-            const uint32_t hb = (gram * 0x9E3779B1u) >> v.g.bitmap_shift;
+            const uint32_t wi = (gram * 0x9E3779B1u) >> v.g.bitmap_shift;      // word of the blocked Bloom filter
+            const uint32_t h2 = (gram * 0xC2B2AE35u) >> 22;                   // two bit positions inside it
+            const uint32_t need = (1u << (h2 & 31u)) | (1u << (h2 >> 5));
             uint32_t word;
-            asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(v.bitmap + ((hb >> 5) << 2)));
-            if ((word >> (hb & 31u)) & 1u) {
+            asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(v.bitmap + (wi << 2)));
+            if ((word & need) == need) {
                 if (ncand < (uint32_t)kMaxCand) { cand_e[ncand] = next_e; cand_g[ncand] = gram; }
                 ncand++;
             }
