@@ -15,6 +15,7 @@
 #include "automata.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace fqg {
 
@@ -41,6 +42,10 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     uint32_t q = (uint32_t)std::min<size_t>(16, std::max<size_t>(8, min_len / 2 + 2));
     uint32_t s = (uint32_t)min_len - q + 1;
     if (s > 32) { s = 32; }            // payload keeps the offset in 5 bits; a smaller stride is always valid
+    if (s >= 4) {                      // word-aligned sampling (one probe every s/4 input words, no sub-word shifts);
+        s &= ~3u;                      // the slack goes back into a longer, more selective gram
+        q = (uint32_t)std::min<size_t>(16, min_len - s + 1);
+    }
     out->q = q;
     out->s = s;
     out->min_len = (uint32_t)min_len;
@@ -49,8 +54,12 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     if (n_grams > (1ull << 24)) return false;
     // blocked 2-bit Bloom filter in shared memory: one hash picks a 32-bit word, a second one two bits inside it.
     // ~40 bits per gram keeps the false-positive rate near 0.2 %; capped at 128 KB (2^20 bits), floor 8 KB.
-    uint32_t bits_log2 = 16;
-    while (bits_log2 < 20 && (1ull << bits_log2) < n_grams * 40) bits_log2++;
+    uint32_t bits_log2 = 16, cap_log2 = 20;
+    if (const char* e = std::getenv("FQG_GRAM_BITS_LOG2_MAX")) {      // tuning knob for experiments
+        int v = std::atoi(e);
+        if (v >= 16 && v <= 20) cap_log2 = (uint32_t)v;
+    }
+    while (bits_log2 < cap_log2 && (1ull << bits_log2) < n_grams * 40) bits_log2++;
     out->bitmap_bits_log2 = bits_log2;
     out->bitmap.assign((1u << bits_log2) / 32, 0);
     uint32_t slots_log2 = 4;

@@ -53,52 +53,74 @@ __device__ __forceinline__ bool gram_verify(const GramView& v, uint32_t p, uint3
 
 // true iff some pattern of the set occurs in the read at shared address p
 __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_t len) {
-    if (len < v.g.min_len) return false;
+    const uint32_t bitmap = v.bitmap, bshift = v.g.bitmap_shift, qmask = v.g.qmask, q = v.g.q, stride = v.g.s;
     uint32_t cand_e[kMaxCand], cand_g[kMaxCand];
     uint32_t ncand = 0;
-    const uint32_t sh0 = (p & 3u) * 8u;
-    uint32_t wp = p & ~3u;
-    uint32_t w0 = lds_u32_volatile(wp);
-    uint32_t lo = 0, hi = 0;              // 2-bit codes of the last 32 bases, newest in the low bits
-    uint32_t next_e = v.g.q - 1u;         // index of the base that ends the next sampled gram
-    const uint32_t nw = len >> 2;
-    auto probe = [&](uint32_t latest) {
-        while (next_e <= latest) {
-            const uint32_t gram = __funnelshift_r(lo, hi, 2u * (latest - next_e)) & v.g.qmask;
-            const uint32_t wi = (gram * 0x9E3779B1u) >> v.g.bitmap_shift;      // word of the blocked Bloom filter
-            const uint32_t h2 = (gram * 0xC2B2AE35u) >> 22;                   // two bit positions inside it
-            const uint32_t need = (1u << (h2 & 31u)) | (1u << (h2 >> 5));
-            uint32_t word;
-            asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(v.bitmap + (wi << 2)));
-            if ((word & need) == need) {
-                if (ncand < (uint32_t)kMaxCand) { cand_e[ncand] = next_e; cand_g[ncand] = gram; }
-                ncand++;
-            }
-            next_e += v.g.s;
+    auto probe = [&](uint32_t gram, uint32_t e) {
+        const uint32_t wi = (gram * 0x9E3779B1u) >> bshift;              // word of the blocked Bloom filter
+        const uint32_t h2 = (gram * 0xC2B2AE35u) >> 22;                  // two bit positions inside it
+        const uint32_t need = (1u << (h2 & 31u)) | (1u << (h2 >> 5));
+        uint32_t word;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bitmap + (wi << 2)));
+        if ((word & need) == need) {
+            if (ncand < (uint32_t)kMaxCand) { cand_e[ncand] = e; cand_g[ncand] = gram; }
+            ncand++;
         }
     };
-    for (uint32_t k = 0; k < nw; k++) {
-        wp += 4;
-        const uint32_t w1 = lds_u32_volatile(wp);
-        const uint32_t w = __funnelshift_r(w0, w1, sh0);
-        w0 = w1;
-        const uint32_t x = (w >> 1) & 0x03030303u;
-        const uint32_t p8 = (x * 0x40100401u) >> 24;      // first base of the word in the high bits
-        hi = (hi << 8) | (lo >> 24);
-        lo = (lo << 8) | p8;
-        probe(4u * k + 3u);
-    }
-    const uint32_t rem = len & 3u;
-    if (rem) {
-        const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh0);
-        for (uint32_t r = 0; r < rem; r++) {
-            const uint32_t c = (w >> (8u * r + 1u)) & 3u;
-            hi = (hi << 2) | (lo >> 30);
-            lo = (lo << 2) | c;
-            probe(4u * nw + r);
+    if (len >= v.g.min_len) {
+        const uint32_t sh0 = (p & 3u) * 8u;
+        uint32_t wp = p & ~3u;
+        uint32_t w0 = lds_u32_volatile(wp);
+        uint32_t lo = 0, hi = 0;              // 2-bit codes of the last 32 bases, newest in the low bits
+        const uint32_t nw = len >> 2;
+        if ((stride & 3u) == 0) {
+            // word-aligned sampling: grams end on the last base of a word, one probe every stride/4 words.
+            // (the <4-base tail never ends a sampled gram, and every occurrence still covers >= stride gram ends)
+            const uint32_t every = stride >> 2;
+            uint32_t countdown = ((q - 1u) >> 2) + 1u;     // first probe after the word that completes base q-1
+#pragma unroll 2
+            for (uint32_t k = 0; k < nw; k++) {
+                wp += 4;
+                const uint32_t w1 = lds_u32_volatile(wp);
+                const uint32_t w = __funnelshift_r(w0, w1, sh0);
+                w0 = w1;
+                const uint32_t x = (w >> 1) & 0x03030303u;
+                lo = (lo << 8) | ((x * 0x40100401u) >> 24);      // first base of the word in the high bits
+                if (--countdown == 0) {
+                    countdown = every;
+                    probe(lo & qmask, 4u * k + 3u);
+                }
+            }
+        } else {
+            uint32_t next_e = q - 1u;         // index of the base that ends the next sampled gram
+            auto probe_upto = [&](uint32_t latest) {
+                while (next_e <= latest) {
+                    probe(__funnelshift_r(lo, hi, 2u * (latest - next_e)) & qmask, next_e);
+                    next_e += stride;
+                }
+            };
+            for (uint32_t k = 0; k < nw; k++) {
+                wp += 4;
+                const uint32_t w1 = lds_u32_volatile(wp);
+                const uint32_t w = __funnelshift_r(w0, w1, sh0);
+                w0 = w1;
+                const uint32_t x = (w >> 1) & 0x03030303u;
+                hi = (hi << 8) | (lo >> 24);
+                lo = (lo << 8) | ((x * 0x40100401u) >> 24);
+                probe_upto(4u * k + 3u);
+            }
+            const uint32_t rem = len & 3u;
+            if (rem) {
+                const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh0);
+                for (uint32_t r = 0; r < rem; r++) {
+                    hi = (hi << 2) | (lo >> 30);
+                    lo = (lo << 2) | ((w >> (8u * r + 1u)) & 3u);
+                    probe_upto(4u * nw + r);
+                }
+            }
         }
     }
-    // exact verification of the few candidates, all lanes of the warp side by side so the L2 latencies overlap
+    // exact verification of the few candidates; lanes run the loop side by side so their L2 latencies overlap
     // (plain per-lane loop, no warp collective: lanes of ragged batches leave this function at different points)
     bool found = false;
     const uint32_t rounds = ncand < (uint32_t)kMaxCand ? ncand : (uint32_t)kMaxCand;

@@ -67,6 +67,8 @@ def check_sample(kind, pats, inv, rc, tb, mask, n_check=200_000):
 
 
 def run_soa(name, kind, pats, inv, rc, n, plant, out):
+    if ONLY and ONLY not in name:
+        return
     tb = gen(n, 1, plant, 0.01, 99)
     t0 = time.perf_counter()
     m = F.Matcher(kind, pats, F.MatcherOpts(inv, rc))
@@ -112,6 +114,9 @@ def run_names(out, n=20_000_000, n_names=1_000_000):
     print("cfg5b", json.dumps(out["cfg5b_names_1M_ids_fastq"]), flush=True)
 
 
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     out = {"peak_gbs": PEAK}
@@ -127,7 +132,8 @@ def main():
     run_soa("extra_tier1_200x12mers_25M", F.FIXED_SET, p200, False, True, 25_000_000, p200[:20], out)
     run_soa("cfg5a_1000_fixed_25M", F.FIXED_SET, p1k, False, False, 25_000_000, p1k[:50], out)
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
-    run_names(out)
+    if not ONLY or ONLY in "cfg5b_names":
+        run_names(out)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_%s.json" % tag), "w"), indent=1)
 
