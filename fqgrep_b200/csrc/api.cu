@@ -35,7 +35,7 @@ struct DeviceTables {
     void* table = nullptr;
     uint8_t* byte_class = nullptr;
     // q-gram filter
-    uint32_t *g_bitmap = nullptr, *g_key = nullptr, *g_val = nullptr, *g_pat_off = nullptr;
+    uint32_t *g_bitmap = nullptr, *g_kv = nullptr, *g_pat_off = nullptr;
     uint8_t* g_pool = nullptr;
     // names
     uint64_t* slots = nullptr;
@@ -151,8 +151,7 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
                     return cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
                 };
                 CU_TRY(up(&t.g_bitmap, g.bitmap));
-                CU_TRY(up(&t.g_key, g.slot_key));
-                CU_TRY(up(&t.g_val, g.slot_val));
+                CU_TRY(up(&t.g_kv, g.slot_kv));
                 CU_TRY(up(&t.g_pat_off, g.pat_off));
                 CU_TRY(up(&t.g_pool, g.pool));
             }
@@ -168,7 +167,7 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
             const GramFilter& g = m->gram;
             DeviceGram& d = out->gram;
             d.bitmap = it->second.g_bitmap; d.bitmap_bytes = (uint32_t)g.bitmap.size() * 4; d.bitmap_shift = 32 - (g.bitmap_bits_log2 - 5);     // hash -> WORD index
-            d.slot_key = it->second.g_key; d.slot_val = it->second.g_val; d.slot_shift = 32 - g.slots_log2; d.slot_mask = (1u << g.slots_log2) - 1;
+            d.slot_kv = it->second.g_kv; d.slot_shift = 32 - g.slots_log2; d.slot_mask = (1u << g.slots_log2) - 1;
             d.pool = it->second.g_pool; d.pat_off = it->second.g_pat_off;
             d.q = g.q; d.s = g.s; d.min_len = g.min_len; d.qmask = g.qmask;
         }
@@ -507,7 +506,7 @@ void fqg_matcher_free(fqg_matcher* m) {
         cudaFree(kv.second.slots);
         cudaFree(kv.second.slot_off);
         cudaFree(kv.second.pool);
-        cudaFree(kv.second.g_bitmap); cudaFree(kv.second.g_key); cudaFree(kv.second.g_val); cudaFree(kv.second.g_pat_off); cudaFree(kv.second.g_pool);
+        cudaFree(kv.second.g_bitmap); cudaFree(kv.second.g_kv); cudaFree(kv.second.g_pat_off); cudaFree(kv.second.g_pool);
         cudaSetDevice(prev);
     }
     delete m;

@@ -58,8 +58,7 @@ struct GramFilter {
     uint32_t q = 0, s = 0, min_len = 0, qmask = 0;
     uint32_t bitmap_bits_log2 = 0, slots_log2 = 0;
     std::vector<uint32_t> bitmap;      // shared-memory resident on the device
-    std::vector<uint32_t> slot_key;    // gram code
-    std::vector<uint32_t> slot_val;    // pattern id << 5 | offset of the gram in the pattern; 0xFFFFFFFF = empty
+    std::vector<uint32_t> slot_kv;     // pairs {gram code, pattern id << 5 | offset in the pattern}; value 0xFFFFFFFF = empty
     std::vector<uint8_t> pool;         // patterns back to back (+ reverse complements)
     std::vector<uint32_t> pat_off;     // n_patterns + 1
 };

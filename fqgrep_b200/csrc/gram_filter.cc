@@ -63,10 +63,9 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     out->bitmap_bits_log2 = bits_log2;
     out->bitmap.assign((1u << bits_log2) / 32, 0);
     uint32_t slots_log2 = 4;
-    while ((1ull << slots_log2) < n_grams * 2 + 2) slots_log2++;
+    while ((1ull << slots_log2) < n_grams * 4 + 2) slots_log2++;        // load <= 0.25: a miss ends after ~1.2 slots
     out->slots_log2 = slots_log2;
-    out->slot_key.assign(1u << slots_log2, 0);
-    out->slot_val.assign(1u << slots_log2, 0xFFFFFFFFu);
+    out->slot_kv.assign((size_t)2 << slots_log2, 0xFFFFFFFFu);
     out->pool.clear();
     out->pat_off.assign(1, 0);
     for (size_t id = 0; id < pats.size(); id++) {
@@ -77,9 +76,9 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
             const uint32_t h2 = (g * 0xC2B2AE35u) >> 22;
             out->bitmap[word] |= (1u << (h2 & 31u)) | (1u << (h2 >> 5));
             uint32_t i = (g * 0x85EBCA6Bu) >> (32 - slots_log2);
-            while (out->slot_val[i] != 0xFFFFFFFFu) i = (i + 1) & ((1u << slots_log2) - 1);
-            out->slot_key[i] = g;
-            out->slot_val[i] = (uint32_t)(id << 5) | j;
+            while (out->slot_kv[2 * (size_t)i + 1] != 0xFFFFFFFFu) i = (i + 1) & ((1u << slots_log2) - 1);
+            out->slot_kv[2 * (size_t)i] = g;
+            out->slot_kv[2 * (size_t)i + 1] = (uint32_t)(id << 5) | j;
         }
         out->pool.insert(out->pool.end(), p.begin(), p.end());
         out->pat_off.push_back((uint32_t)out->pool.size());

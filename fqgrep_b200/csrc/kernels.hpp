@@ -18,8 +18,7 @@ namespace fqg {
 struct DeviceGram {
     const uint32_t* bitmap = nullptr;    // device copy, staged into shared memory by the kernel
     uint32_t bitmap_bytes = 0, bitmap_shift = 0;   // word index = (gram * 0x9E3779B1) >> bitmap_shift; 2 bits from a second hash
-    const uint32_t* slot_key = nullptr;
-    const uint32_t* slot_val = nullptr;
+    const uint32_t* slot_kv = nullptr;     // pairs {gram, pattern id << 5 | offset}; value 0xFFFFFFFF = empty
     uint32_t slot_shift = 0, slot_mask = 0;
     const uint8_t* pool = nullptr;
     const uint32_t* pat_off = nullptr;

@@ -30,15 +30,13 @@ struct GramView {
     uint32_t cls;             // shared address of the byte -> class LUT
     uint32_t dfa_start, dfa_accept;
 };
-constexpr int kMaxCand = 6;
-
 __device__ __forceinline__ bool gram_verify(const GramView& v, uint32_t p, uint32_t len, uint32_t gram, uint32_t e) {
     uint32_t i = (gram * 0x85EBCA6Bu) >> v.g.slot_shift;
     for (;;) {
-        const uint32_t val = __ldg(v.g.slot_val + i);
-        if (val == 0xFFFFFFFFu) return false;
-        if (__ldg(v.g.slot_key + i) == gram) {
-            const uint32_t id = val >> 5, j = val & 31u;
+        const uint2 kv = __ldg(reinterpret_cast<const uint2*>(v.g.slot_kv) + i);      // {gram, pattern id << 5 | offset}
+        if (kv.y == 0xFFFFFFFFu) return false;
+        if (kv.x == gram) {
+            const uint32_t id = kv.y >> 5, j = kv.y & 31u;
             const uint32_t o0 = __ldg(v.g.pat_off + id), plen = __ldg(v.g.pat_off + id + 1) - o0;
             const int32_t start = (int32_t)e - (int32_t)(v.g.q - 1u) - (int32_t)j;     // where the pattern would begin in the read
             if (start >= 0 && (uint32_t)start + plen <= len) {
@@ -51,81 +49,100 @@ __device__ __forceinline__ bool gram_verify(const GramView& v, uint32_t p, uint3
     }
 }
 
+// 2-bit codes of the q bases ending at base index e of the read at shared address p (only for the rare filter hits)
+__device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q) {
+    uint32_t g = 0;
+    for (uint32_t i = e + 1u - q; i <= e; i++) g = (g << 2) | ((lds_u8(p + i) >> 1) & 3u);
+    return g;
+}
+
 // true iff some pattern of the set occurs in the read at shared address p
 __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_t len) {
     const uint32_t bitmap = v.bitmap, bshift = v.g.bitmap_shift, qmask = v.g.qmask, q = v.g.q, stride = v.g.s;
-    uint32_t cand_e[kMaxCand], cand_g[kMaxCand];
-    uint32_t ncand = 0;
-    auto probe = [&](uint32_t gram, uint32_t e) {
-        const uint32_t wi = (gram * 0x9E3779B1u) >> bshift;              // word of the blocked Bloom filter
-        const uint32_t h2 = (gram * 0xC2B2AE35u) >> 22;                  // two bit positions inside it
-        const uint32_t need = (1u << (h2 & 31u)) | (1u << (h2 >> 5));
-        uint32_t word;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bitmap + (wi << 2)));
-        if ((word & need) == need) {
-            if (ncand < (uint32_t)kMaxCand) { cand_e[ncand] = e; cand_g[ncand] = gram; }
-            ncand++;
-        }
-    };
+    bool found = false, exact_walk = false;
     if (len >= v.g.min_len) {
+        // Filter hits are recorded branch-free as one bit per probe (probe i ends at base e0 + i*stride); the gram of a
+        // hit is re-read from shared memory later.  64 probes cover reads up to ~64*stride bases; longer reads take
+        // the exact automaton walk.
+        uint64_t hits = 0;
+        auto probe = [&](uint32_t gram, uint32_t idx) {
+            const uint32_t wi = (gram * 0x9E3779B1u) >> bshift;              // word of the blocked Bloom filter
+            const uint32_t h2 = (gram * 0xC2B2AE35u) >> 22;                  // two bit positions inside it
+            const uint32_t need = (1u << (h2 & 31u)) | (1u << (h2 >> 5));
+            uint32_t word;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bitmap + (wi << 2)));
+            hits |= (uint64_t)((word & need) == need) << idx;
+        };
         const uint32_t sh0 = (p & 3u) * 8u;
         uint32_t wp = p & ~3u;
         uint32_t w0 = lds_u32_volatile(wp);
         uint32_t lo = 0, hi = 0;              // 2-bit codes of the last 32 bases, newest in the low bits
         const uint32_t nw = len >> 2;
+        uint32_t e0, n_probes = 0;
         if ((stride & 3u) == 0) {
             // word-aligned sampling: grams end on the last base of a word, one probe every stride/4 words.
             // (the <4-base tail never ends a sampled gram, and every occurrence still covers >= stride gram ends)
-            const uint32_t every = stride >> 2;
-            uint32_t countdown = ((q - 1u) >> 2) + 1u;     // first probe after the word that completes base q-1
-#pragma unroll 2
-            for (uint32_t k = 0; k < nw; k++) {
-                wp += 4;
-                const uint32_t w1 = lds_u32_volatile(wp);
-                const uint32_t w = __funnelshift_r(w0, w1, sh0);
-                w0 = w1;
-                const uint32_t x = (w >> 1) & 0x03030303u;
-                lo = (lo << 8) | ((x * 0x40100401u) >> 24);      // first base of the word in the high bits
-                if (--countdown == 0) {
-                    countdown = every;
-                    probe(lo & qmask, 4u * k + 3u);
+            const uint32_t every = stride >> 2, k0 = (q - 1u) >> 2;
+            e0 = 4u * k0 + 3u;
+            if ((nw > k0 ? (nw - 1u - k0) / every + 1u : 0u) > 64u) exact_walk = true;
+            else {
+                uint32_t countdown = k0 + 1u;     // first probe after the word that completes base q-1
+#pragma unroll 4
+                for (uint32_t k = 0; k < nw; k++) {
+                    wp += 4;
+                    const uint32_t w1 = lds_u32_volatile(wp);
+                    const uint32_t w = __funnelshift_r(w0, w1, sh0);
+                    w0 = w1;
+                    const uint32_t x = (w >> 1) & 0x03030303u;
+                    lo = (lo << 8) | ((x * 0x40100401u) >> 24);      // first base of the word in the high bits
+                    if (--countdown == 0) {
+                        countdown = every;
+                        probe(lo & qmask, n_probes++);
+                    }
                 }
             }
         } else {
-            uint32_t next_e = q - 1u;         // index of the base that ends the next sampled gram
-            auto probe_upto = [&](uint32_t latest) {
-                while (next_e <= latest) {
-                    probe(__funnelshift_r(lo, hi, 2u * (latest - next_e)) & qmask, next_e);
-                    next_e += stride;
+            e0 = q - 1u;
+            if ((len - q) / stride + 1u > 64u) exact_walk = true;
+            else {
+                uint32_t next_e = e0;         // index of the base that ends the next sampled gram
+                auto probe_upto = [&](uint32_t latest) {
+                    while (next_e <= latest) {
+                        probe(__funnelshift_r(lo, hi, 2u * (latest - next_e)) & qmask, n_probes++);
+                        next_e += stride;
+                    }
+                };
+                for (uint32_t k = 0; k < nw; k++) {
+                    wp += 4;
+                    const uint32_t w1 = lds_u32_volatile(wp);
+                    const uint32_t w = __funnelshift_r(w0, w1, sh0);
+                    w0 = w1;
+                    const uint32_t x = (w >> 1) & 0x03030303u;
+                    hi = (hi << 8) | (lo >> 24);
+                    lo = (lo << 8) | ((x * 0x40100401u) >> 24);
+                    probe_upto(4u * k + 3u);
                 }
-            };
-            for (uint32_t k = 0; k < nw; k++) {
-                wp += 4;
-                const uint32_t w1 = lds_u32_volatile(wp);
-                const uint32_t w = __funnelshift_r(w0, w1, sh0);
-                w0 = w1;
-                const uint32_t x = (w >> 1) & 0x03030303u;
-                hi = (hi << 8) | (lo >> 24);
-                lo = (lo << 8) | ((x * 0x40100401u) >> 24);
-                probe_upto(4u * k + 3u);
-            }
-            const uint32_t rem = len & 3u;
-            if (rem) {
-                const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh0);
-                for (uint32_t r = 0; r < rem; r++) {
-                    hi = (hi << 2) | (lo >> 30);
-                    lo = (lo << 2) | ((w >> (8u * r + 1u)) & 3u);
-                    probe_upto(4u * nw + r);
+                const uint32_t rem = len & 3u;
+                if (rem) {
+                    const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh0);
+                    for (uint32_t r = 0; r < rem; r++) {
+                        hi = (hi << 2) | (lo >> 30);
+                        lo = (lo << 2) | ((w >> (8u * r + 1u)) & 3u);
+                        probe_upto(4u * nw + r);
+                    }
                 }
             }
         }
+        // exact verification of the few hits; lanes run the loop side by side so their L2 latencies overlap
+        // (plain per-lane loop, no warp collective: lanes of ragged batches leave this function at different points)
+        while (hits && !found) {
+            const uint32_t idx = (uint32_t)__ffsll((long long)hits) - 1u;
+            hits &= hits - 1ull;
+            const uint32_t e = e0 + idx * stride;
+            found = gram_verify(v, p, len, gram_at(p, e, q), e);
+        }
     }
-    // exact verification of the few candidates; lanes run the loop side by side so their L2 latencies overlap
-    // (plain per-lane loop, no warp collective: lanes of ragged batches leave this function at different points)
-    bool found = false;
-    const uint32_t rounds = ncand < (uint32_t)kMaxCand ? ncand : (uint32_t)kMaxCand;
-    for (uint32_t r = 0; r < rounds && !found; r++) found = gram_verify(v, p, len, cand_g[r], cand_e[r]);
-    if (ncand > (uint32_t)kMaxCand && !found) {          // too many candidates to remember: exact automaton walk through L2
+    if (exact_walk) {          // very long read: exact automaton walk through L2
         uint32_t st = v.dfa_start;
         for (uint32_t i = 0; i < len; i++) st = __ldg(v.t32 + st + lds_u8(v.cls + lds_u8(p + i)));
         found = st >= v.dfa_accept;

@@ -151,6 +151,10 @@ def test_gram_filter_edge_cases():
         seqs.append("".join(pats[r.randrange(4000)][:12] for _ in range(12)))
     seqs.append("N" * 150)
     seqs.append("ACGTNNNNACGTAC")
+    for L in (600, 2000):        # more than 64 sampled grams: exact automaton walk
+        body = "".join(r.choice("ACGT") for _ in range(L))
+        seqs.append(body)
+        seqs.append(body[: L - 30] + pats[7] + body[L - 30 + len(pats[7]):] if len(pats[7]) <= 30 else body + pats[7])
     bases, offs = soa(seqs)
     for inv, rc in ((False, False), (False, True), (True, True)):
         cnt = check(F.FIXED_SET, pats, inv, rc, bases, offs)
