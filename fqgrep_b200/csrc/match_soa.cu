@@ -16,6 +16,8 @@
 //     per lane, out of shared memory (aligned 32-bit LDS + funnel shift, 4 bases per load);
 //   * epilogue: ballot -> one mask word per batch (optionally OR-ed with the mate's mask: the pair rule of
 //     src/main.rs:749-755), popcount accumulated per warp and added to the global count once.
+#include <type_traits>
+
 #include "dfa_device.cuh"
 #include "kernels.hpp"
 
@@ -58,7 +60,12 @@ __device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q) 
 
 // true iff some pattern of the set occurs in the read at shared address p
 __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_t len) {
-    const uint32_t bitmap = v.bitmap, bshift = v.g.bitmap_shift, qmask = v.g.qmask, q = v.g.q, stride = v.g.s;
+    // pinned into registers (asm volatile cannot be rematerialised) so the probe does not re-derive them per gram
+    uint32_t bitmap, bshift, qmask;
+    asm volatile("mov.u32 %0, %1;" : "=r"(bitmap) : "r"(v.bitmap));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bshift) : "r"(v.g.bitmap_shift));
+    asm volatile("mov.u32 %0, %1;" : "=r"(qmask) : "r"(v.g.qmask));
+    const uint32_t q = v.g.q, stride = v.g.s;
     bool found = false, exact_walk = false;
     if (len >= v.g.min_len) {
         // Filter hits are recorded branch-free as one bit per probe (probe i ends at base e0 + i*stride); the gram of a
@@ -84,21 +91,38 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
             // (the <4-base tail never ends a sampled gram, and every occurrence still covers >= stride gram ends)
             const uint32_t every = stride >> 2, k0 = (q - 1u) >> 2;
             e0 = 4u * k0 + 3u;
-            if ((nw > k0 ? (nw - 1u - k0) / every + 1u : 0u) > 64u) exact_walk = true;
-            else {
-                uint32_t countdown = k0 + 1u;     // first probe after the word that completes base q-1
-#pragma unroll 4
-                for (uint32_t k = 0; k < nw; k++) {
+            n_probes = nw > k0 ? (nw - 1u - k0) / every + 1u : 0u;
+            if (n_probes > 64u) exact_walk = true;
+            else if (n_probes) {
+                auto append = [&]() {
                     wp += 4;
                     const uint32_t w1 = lds_u32_volatile(wp);
                     const uint32_t w = __funnelshift_r(w0, w1, sh0);
                     w0 = w1;
                     const uint32_t x = (w >> 1) & 0x03030303u;
                     lo = (lo << 8) | ((x * 0x40100401u) >> 24);      // first base of the word in the high bits
-                    if (--countdown == 0) {
-                        countdown = every;
-                        probe(lo & qmask, n_probes++);
+                };
+                for (uint32_t k = 0; k <= k0; k++) append();
+                probe(lo & qmask, 0u);
+                // one probe per `every` words, no per-word branch: the common strides are unrolled
+                auto groups = [&](auto every_c) {
+                    constexpr uint32_t E = decltype(every_c)::value;
+                    for (uint32_t g = 1; g < n_probes; g++) {
+#pragma unroll
+                        for (uint32_t j = 0; j < E; j++) append();
+                        probe(lo & qmask, g);
                     }
+                };
+                switch (every) {
+                    case 1: groups(std::integral_constant<uint32_t, 1>{}); break;
+                    case 2: groups(std::integral_constant<uint32_t, 2>{}); break;
+                    case 3: groups(std::integral_constant<uint32_t, 3>{}); break;
+                    case 4: groups(std::integral_constant<uint32_t, 4>{}); break;
+                    default:
+                        for (uint32_t g = 1; g < n_probes; g++) {
+                            for (uint32_t j = 0; j < every; j++) append();
+                            probe(lo & qmask, g);
+                        }
                 }
             }
         } else {
