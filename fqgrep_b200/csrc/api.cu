@@ -109,7 +109,7 @@ void build_tables(fqg_matcher* m) {
             for (uint64_t c = 0; c < nc; c++) m->t16[s * row0 + 256 + c] = (uint16_t)(d.next[s * nc + c] * row0 * 2);
         }
         for (int b = 0; b < 256; b++) m->lut[b] = (uint8_t)(d.byte_class[b] * 2);
-    } else if (n * nc * 2 <= 60 * 1024 && nc <= 127) {
+    } else if (!m->gram.usable && n * nc * 2 <= 60 * 1024 && nc <= 127) {     // literal sets prefer the q-gram filter (tier 3)
         m->tier = 1;
         m->row = (uint32_t)nc * 2;
         m->t16.assign(((n * nc + 7) / 8) * 8, 0);

@@ -7,7 +7,7 @@
 // Every pattern is at least `min_len` long.  Pick a gram length q and a stride s = min_len - q + 1.  Any occurrence of a
 // pattern covers >= s consecutive q-gram windows, so probing the text only at window ends q-1, q-1+s, q-1+2s, ... always
 // lands on a window that starts at pattern offset 0..s-1.  The device therefore keeps
-//   * a blocked Bloom filter (shared memory, 2 bits per gram inside one 32-bit word) of the grams at offsets 0..s-1
+//   * a blocked Bloom filter (shared memory, 3 bits per gram inside one 32-bit word) of the grams at offsets 0..s-1
 //     of every pattern: exact negative filter;
 //   * an open-addressing table gram -> (pattern id, offset) in L2 for the rare positives, verified byte by byte.
 // Grams are built from 2-bit codes (byte >> 1) & 3 of ANY byte (not only ACGT): text and patterns use the same map, so
@@ -52,7 +52,7 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     out->qmask = q == 16 ? 0xFFFFFFFFu : ((1u << (2 * q)) - 1u);
     const uint64_t n_grams = (uint64_t)pats.size() * s;
     if (n_grams > (1ull << 24)) return false;
-    // blocked 2-bit Bloom filter in shared memory: one hash picks a 32-bit word, a second one two bits inside it.
+    // blocked 3-bit Bloom filter in shared memory: one hash picks a 32-bit word, a second one three bits inside it.
     // ~40 bits per gram keeps the false-positive rate near 0.2 %; capped at 128 KB (2^20 bits), floor 8 KB.
     uint32_t bits_log2 = 16, cap_log2 = 20;
     if (const char* e = std::getenv("FQG_GRAM_BITS_LOG2_MAX")) {      // tuning knob for experiments
@@ -73,8 +73,8 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
         for (uint32_t j = 0; j < s; j++) {
             const uint32_t g = gram_code((const uint8_t*)p.data() + j, q);
             const uint32_t word = (g * 0x9E3779B1u) >> (32 - (bits_log2 - 5));
-            const uint32_t h2 = (g * 0xC2B2AE35u) >> 22;
-            out->bitmap[word] |= (1u << (h2 & 31u)) | (1u << (h2 >> 5));
+            const uint32_t h2 = (g * 0xC2B2AE35u) >> 17;
+            out->bitmap[word] |= (1u << (h2 & 31u)) | (1u << ((h2 >> 5) & 31u)) | (1u << (h2 >> 10));
             uint32_t i = (g * 0x85EBCA6Bu) >> (32 - slots_log2);
             while (out->slot_kv[2 * (size_t)i + 1] != 0xFFFFFFFFu) i = (i + 1) & ((1u << slots_log2) - 1);
             out->slot_kv[2 * (size_t)i] = g;

@@ -74,8 +74,8 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
         uint64_t hits = 0;
         auto probe = [&](uint32_t gram, uint32_t idx) {
             const uint32_t wi = (gram * 0x9E3779B1u) >> bshift;              // word of the blocked Bloom filter
-            const uint32_t h2 = (gram * 0xC2B2AE35u) >> 22;                  // two bit positions inside it
-            const uint32_t need = (1u << (h2 & 31u)) | (1u << (h2 >> 5));
+            const uint32_t h2 = (gram * 0xC2B2AE35u) >> 17;                  // three bit positions inside it
+            const uint32_t need = (1u << (h2 & 31u)) | (1u << ((h2 >> 5) & 31u)) | (1u << (h2 >> 10));
             uint32_t word;
             asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bitmap + (wi << 2)));
             hits |= (uint64_t)((word & need) == need) << idx;

@@ -97,7 +97,7 @@ def test_all_three_table_tiers():
     mat = synth.bases(50_000, seed=9)
     rng = np.random.default_rng(3)
     small = ["ACGTAC", "TTTTT"]
-    medium = ["".join("ACGT"[i] for i in rng.integers(0, 4, 12)) for _ in range(200)]
+    medium = ["".join("ACGT"[i] for i in rng.integers(0, 4, 7)) for _ in range(300)]      # too short for the q-gram filter -> tier 1
     large = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(10_000)]
     synth.plant(mat, small + medium[:20] + large[:200], rate=0.05)
     bases, offs = synth.soa(mat)
