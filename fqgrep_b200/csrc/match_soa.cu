@@ -71,14 +71,20 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
         // Filter hits are recorded branch-free as one bit per probe (probe i ends at base e0 + i*stride); the gram of a
         // hit is re-read from shared memory later.  64 probes cover reads up to ~64*stride bases; longer reads take
         // the exact automaton walk.
-        uint64_t hits = 0;
-        auto probe = [&](uint32_t gram, uint32_t idx) {
+        // hits0 takes probes 0..31 (first probe ends up in the highest used bit), hits1 probes 32..63.
+        uint32_t hits0 = 0, hits1 = 0;
+        auto probe_into = [&](uint32_t gram, uint32_t& acc) {
             const uint32_t wi = (gram * 0x9E3779B1u) >> bshift;              // word of the blocked Bloom filter
             const uint32_t h2 = (gram * 0xC2B2AE35u) >> 17;                  // three bit positions inside it
             const uint32_t need = (1u << (h2 & 31u)) | (1u << ((h2 >> 5) & 31u)) | (1u << (h2 >> 10));
             uint32_t word;
             asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bitmap + (wi << 2)));
-            hits |= (uint64_t)((word & need) == need) << idx;
+            acc = (acc << 1) | (uint32_t)((word & need) == need);
+        };
+        uint32_t probes_done = 0;
+        auto probe = [&](uint32_t gram, uint32_t) {
+            if (probes_done < 32u) probe_into(gram, hits0); else probe_into(gram, hits1);
+            probes_done++;
         };
         const uint32_t sh0 = (p & 3u) * 8u;
         uint32_t wp = p & ~3u;
@@ -103,15 +109,22 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
                     lo = (lo << 8) | ((x * 0x40100401u) >> 24);      // first base of the word in the high bits
                 };
                 for (uint32_t k = 0; k <= k0; k++) append();
-                probe(lo & qmask, 0u);
+                probe_into(lo & qmask, hits0);
                 // one probe per `every` words, no per-word branch: the common strides are unrolled
+                const uint32_t n_first = n_probes < 32u ? n_probes : 32u;
                 auto groups = [&](auto every_c) {
                     constexpr uint32_t E = decltype(every_c)::value;
-                    for (uint32_t g = 1; g < n_probes; g++) {
+                    for (uint32_t g = 1; g < n_first; g++) {
 #pragma unroll
                         for (uint32_t j = 0; j < E; j++) append();
-                        probe(lo & qmask, g);
+                        probe_into(lo & qmask, hits0);
                     }
+                    for (uint32_t g = 32; g < n_probes; g++) {
+#pragma unroll
+                        for (uint32_t j = 0; j < E; j++) append();
+                        probe_into(lo & qmask, hits1);
+                    }
+                    probes_done = n_probes;
                 };
                 switch (every) {
                     case 1: groups(std::integral_constant<uint32_t, 1>{}); break;
@@ -119,6 +132,7 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
                     case 3: groups(std::integral_constant<uint32_t, 3>{}); break;
                     case 4: groups(std::integral_constant<uint32_t, 4>{}); break;
                     default:
+                        probes_done = 1;
                         for (uint32_t g = 1; g < n_probes; g++) {
                             for (uint32_t j = 0; j < every; j++) append();
                             probe(lo & qmask, g);
@@ -132,7 +146,7 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
                 uint32_t next_e = e0;         // index of the base that ends the next sampled gram
                 auto probe_upto = [&](uint32_t latest) {
                     while (next_e <= latest) {
-                        probe(__funnelshift_r(lo, hi, 2u * (latest - next_e)) & qmask, n_probes++);
+                        probe(__funnelshift_r(lo, hi, 2u * (latest - next_e)) & qmask, 0u);
                         next_e += stride;
                     }
                 };
@@ -159,10 +173,18 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
         }
         // exact verification of the few hits; lanes run the loop side by side so their L2 latencies overlap
         // (plain per-lane loop, no warp collective: lanes of ragged batches leave this function at different points)
-        while (hits && !found) {
-            const uint32_t idx = (uint32_t)__ffsll((long long)hits) - 1u;
-            hits &= hits - 1ull;
-            const uint32_t e = e0 + idx * stride;
+        // bit b of hits0 is probe (n0 - 1 - b), bit b of hits1 is probe (32 + n1 - 1 - b)
+        const uint32_t n0 = probes_done < 32u ? probes_done : 32u, n1 = probes_done - n0;
+        while (hits0 && !found) {
+            const uint32_t b = (uint32_t)__ffs((int)hits0) - 1u;
+            hits0 &= hits0 - 1u;
+            const uint32_t e = e0 + (n0 - 1u - b) * stride;
+            found = gram_verify(v, p, len, gram_at(p, e, q), e);
+        }
+        while (hits1 && !found) {
+            const uint32_t b = (uint32_t)__ffs((int)hits1) - 1u;
+            hits1 &= hits1 - 1u;
+            const uint32_t e = e0 + (32u + n1 - 1u - b) * stride;
             found = gram_verify(v, p, len, gram_at(p, e, q), e);
         }
     }
@@ -323,7 +345,7 @@ cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_cou
     switch (dfa.tier) {
         case 0: return launch_t<0, 2>(dfa, b, sm_count, stream);
         case 1: return launch_t<1, 2>(dfa, b, sm_count, stream);
-        case 3: return launch_t<3, 2>(dfa, b, sm_count, stream);
+        case 3: return launch_t<3, 1>(dfa, b, sm_count, stream);     // filter bitmap takes the smem: single staging slot, twice the warps
         default: return launch_t<2, 2>(dfa, b, sm_count, stream);
     }
 }
