@@ -175,6 +175,11 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
         out->start = m->dfa.start * m->row;
         out->accept_from = m->dfa.accept_from * m->row;
         out->n_states = m->dfa.n_states;
+        if (m->tier >= 2) {     // rows of the first (shallowest, BFS order) states that fit 60 KB of shared memory
+            uint64_t rows = (60ull * 1024) / (m->dfa.n_classes * 4ull);
+            if (rows > m->dfa.n_states) rows = m->dfa.n_states;
+            out->hot_entries = (uint32_t)(rows * m->dfa.n_classes);
+        }
     }
     return 0;
 }
@@ -474,9 +479,17 @@ int fqg_matcher_new(int kind, const uint8_t* blob, const uint64_t* offsets, uint
         case FQG_REGEX:
             if (n != 1) return fail(FQG_E_INVALID_ARG, "FQG_REGEX takes exactly one pattern");
             // fallthrough
-        case FQG_REGEX_SET:
-            if (!compile_regex_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
+        case FQG_REGEX_SET: {
+            // a set of plain literals (e.g. -f patterns.txt without -F) is the same language as the fixed-string set
+            std::vector<std::string> lits(pats.size());
+            bool all_literal = !pats.empty();
+            for (size_t i = 0; i < pats.size() && all_literal; i++) all_literal = regex_as_literal(pats[i], &lits[i]);
+            if (all_literal) {
+                if (!compile_literal_set(lits, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
+                build_gram_filter(lits, rc, &m->gram);
+            } else if (!compile_regex_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
             break;
+        }
         case FQG_BITMASK:
             if (n != 1) return fail(FQG_E_INVALID_ARG, "FQG_BITMASK takes exactly one pattern");
             // fallthrough

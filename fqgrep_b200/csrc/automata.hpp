@@ -44,6 +44,8 @@ const uint8_t* iupac_masks();   // IUPAC_MASKS, mod.rs:14-53
 bool expand_iupac_fixed(const std::string& pattern, std::vector<std::string>* out, std::string* err);
 std::string iupac_to_regex(const std::string& pattern);
 
+bool regex_as_literal(const std::string& pattern, std::string* literal);
+
 // Literal set -> Aho-Corasick DFA (replaces aho_corasick::AhoCorasick::new, matcher.rs:297-298, and
 // bstr find, matcher.rs:204).  with_revcomp adds rc(pattern) for every pattern.
 bool compile_literal_set(const std::vector<std::string>& patterns, bool with_revcomp, Dfa* out, std::string* err);

@@ -39,11 +39,19 @@ struct DfaView {
     uint32_t tab;          // smem address of the table (tiers 0,1)
     const uint32_t* t32;   // global (tier 2)
     uint32_t cls;          // smem address of the byte -> class LUT (tier 0,1: class*2; tier 2: class)
+    uint32_t hot_limit;    // tier 2: states (entry indices) below this have their rows cached in shared memory at `tab`
 
     __device__ __forceinline__ uint32_t step1(uint32_t st, uint32_t byte) const {
         if (TIER == 0) return lds_u16(st + 512u + lds_u8(cls + byte));
         if (TIER == 1) return lds_u16(st + lds_u8(cls + byte));
-        return __ldg(t32 + st + lds_u8(cls + byte));
+        // tier 2: breadth-first state numbering puts the shallow (hot) states first; their rows live in shared memory
+        const uint32_t idx = st + lds_u8(cls + byte);
+        if (st < hot_limit) {
+            uint32_t v;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tab + (idx << 2)));
+            return v;
+        }
+        return __ldg(t32 + idx);
     }
     // Four stream-ordered bytes in one little-endian word, tier 0 only: ONE lookup, taken unconditionally.
     // `bad` accumulates, exactly, whether any byte was not one of ACGT; the caller then re-walks the read with

@@ -35,6 +35,7 @@ struct DeviceDfa {
     uint32_t start = 0;              // premultiplied
     uint32_t accept_from = 0;        // premultiplied
     uint32_t n_states = 0;
+    uint32_t hot_entries = 0;        // tiers 2/3: leading table entries (whole rows of the shallowest states) cached in smem
 };
 
 struct SoaBatch {

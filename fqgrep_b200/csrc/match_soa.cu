@@ -218,6 +218,8 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
 
     if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
+    if (TIER == 2)
+        for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
     if (TIER == 3) {
         const uint4* src = reinterpret_cast<const uint4*>(dfa.gram.bitmap);
         uint4* dst = reinterpret_cast<uint4*>(s_tab);
@@ -229,7 +231,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     mbar_fence_init();
     __syncthreads();
 
-    DfaView<(TIER == 3 ? 2 : TIER)> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls)};
+    DfaView<(TIER == 3 ? 2 : TIER)> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), TIER == 2 ? dfa.hot_entries : 0u};
     GramView gview{smem_addr(s_tab), dfa.gram, reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), dfa.start, dfa.accept_from};
     const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
     const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
@@ -317,7 +319,7 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
     const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
     uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
     slot = (slot + 127u) & ~127u;
-    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 3 ? ((dfa.gram.bitmap_bytes + 127u) & ~127u) : 0u;
+    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 3 ? ((dfa.gram.bitmap_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
     const uint32_t fixed = table_smem + 256u + 32u * STAGES * 8u + 128u;
     const uint32_t budget = 227u * 1024u;
     if (fixed + STAGES * slot > budget) {

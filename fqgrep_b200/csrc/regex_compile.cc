@@ -891,6 +891,33 @@ bool compile_regex_set(const std::vector<std::string>& patterns, bool with_revco
     return compile_asts(asts, with_revcomp, out, err);
 }
 
+// True when the regex is nothing but a literal byte string (what the regex crate's literal optimisations also detect):
+// such sets are routed to the Aho-Corasick / q-gram machinery, which is the same language, compiled faster and --
+// for large pattern files given without -F -- eligible for the shared-memory filter tier.
+bool regex_as_literal(const std::string& pattern, std::string* literal) {
+    AstP ast;
+    try {
+        ast = Parser(pattern).parse();
+    } catch (ParseError&) {
+        return false;
+    }
+    literal->clear();
+    auto one_byte = [&](const Ast& a) -> bool {
+        if (a.kind != Ast::Bytes) return false;
+        int found = -1;
+        for (int b = 0; b < 256; b++)
+            if (bs_has(a.set, b)) { if (found >= 0) return false; found = b; }
+        if (found < 0) return false;
+        literal->push_back((char)found);
+        return true;
+    };
+    if (ast->kind == Ast::Empty) return true;
+    if (ast->kind == Ast::Bytes) return one_byte(*ast);
+    if (ast->kind != Ast::Cat) return false;
+    for (auto& k : ast->kids) if (!one_byte(*k)) return false;
+    return true;
+}
+
 // --iupac bit-mask (BitMaskMatcher / BitMaskSetMatcher, matcher.rs:307-487): a needle is a fixed-length string of
 // byte classes.  With IUPAC_MASKS m[] (mod.rs:14-53), needle symbol n_i = m[pattern byte]:
 //   needle has an ambiguity code (or a non-IUPAC byte): position i accepts every byte b with (n_i & m[b]) == m[b]

@@ -130,6 +130,10 @@ def main():
     run_soa("cfg4_class_regex_invert_25M", F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, False, 25_000_000, lit, out)
     p200 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 12)) for _ in range(200)]
     run_soa("extra_tier1_200x12mers_25M", F.FIXED_SET, p200, False, True, 25_000_000, p200[:20], out)
+    mixed = p10k[:300] + ["AC.G[AT]C"]
+    run_soa("extra_tier2_regexset_301_25M", F.REGEX_SET, mixed, False, True, 25_000_000, p10k[:20], out)
+    r60 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 8)) + "[AC]" + "".join("ACGT"[i] for i in rng.integers(0, 4, 6)) for _ in range(60)]
+    run_soa("extra_tier1_regexset_60_25M", F.REGEX_SET, r60, False, False, 25_000_000, p10k[:20], out)
     run_soa("cfg5a_1000_fixed_25M", F.FIXED_SET, p1k, False, False, 25_000_000, p1k[:50], out)
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
     if not ONLY or ONLY in "cfg5b_names":
