@@ -109,7 +109,23 @@ void build_tables(fqg_matcher* m) {
             for (uint64_t c = 0; c < nc; c++) m->t16[s * row0 + 256 + c] = (uint16_t)(d.next[s * nc + c] * row0 * 2);
         }
         for (int b = 0; b < 256; b++) m->lut[b] = (uint8_t)(d.byte_class[b] * 2);
-    } else if (!m->gram.usable && n * nc * 2 <= 60 * 1024 && nc <= 127) {     // literal sets prefer the q-gram filter (tier 3)
+    } else if (!m->gram.usable && nc <= 127 && n * (16 + ((nc + 7) / 8) * 8) * 2 <= 60 * 1024) {
+        // tier 4: 16 two-base entries + the one-byte entries per row (literal sets prefer the q-gram filter, tier 3)
+        const uint64_t row4 = 16 + ((nc + 7) / 8) * 8;
+        m->tier = 4;
+        m->row = (uint32_t)row4 * 2;
+        m->t16.assign(((n * row4 + 7) / 8) * 8, 0);
+        static const char kLetter[4] = {'A', 'C', 'T', 'G'};
+        for (uint64_t s = 0; s < n; s++) {
+            for (uint32_t p = 0; p < 16; p++) {      // index = c0 << 2 | c1, c0 = first base
+                uint64_t t = d.next[s * nc + d.byte_class[(uint8_t)kLetter[(p >> 2) & 3]]];
+                t = d.next[t * nc + d.byte_class[(uint8_t)kLetter[p & 3]]];
+                m->t16[s * row4 + p] = (uint16_t)(t * row4 * 2);
+            }
+            for (uint64_t c = 0; c < nc; c++) m->t16[s * row4 + 16 + c] = (uint16_t)(d.next[s * nc + c] * row4 * 2);
+        }
+        for (int b = 0; b < 256; b++) m->lut[b] = (uint8_t)(d.byte_class[b] * 2);
+    } else if (!m->gram.usable && n * nc * 2 <= 60 * 1024 && nc <= 127) {
         m->tier = 1;
         m->row = (uint32_t)nc * 2;
         m->t16.assign(((n * nc + 7) / 8) * 8, 0);
@@ -137,8 +153,8 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
             CU_TRY(cudaMemcpy(t.slot_off, m->names.slot_off.data(), m->names.slot_off.size() * 4, cudaMemcpyHostToDevice));
             CU_TRY(cudaMemcpy(t.pool, m->names.pool.data(), m->names.pool.size(), cudaMemcpyHostToDevice));
         } else {
-            const void* src = m->tier >= 2 ? (const void*)m->t32.data() : (const void*)m->t16.data();
-            size_t bytes = m->tier >= 2 ? m->t32.size() * 4 : m->t16.size() * 2;
+            const void* src = (m->tier == 2 || m->tier == 3) ? (const void*)m->t32.data() : (const void*)m->t16.data();
+            size_t bytes = (m->tier == 2 || m->tier == 3) ? m->t32.size() * 4 : m->t16.size() * 2;
             CU_TRY(cudaMalloc(&t.table, bytes + 16));
             CU_TRY(cudaMemcpy(t.table, src, bytes, cudaMemcpyHostToDevice));
             CU_TRY(cudaMalloc(&t.byte_class, 256));
@@ -161,7 +177,7 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
     if (out) {
         out->tier = m->tier;
         out->table = it->second.table;
-        out->table_bytes = (uint32_t)(m->tier >= 2 ? m->t32.size() * 4 : m->t16.size() * 2);
+        out->table_bytes = (uint32_t)((m->tier == 2 || m->tier == 3) ? m->t32.size() * 4 : m->t16.size() * 2);
         out->byte_class = it->second.byte_class;
         if (m->tier == 3) {
             const GramFilter& g = m->gram;
@@ -175,7 +191,7 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
         out->start = m->dfa.start * m->row;
         out->accept_from = m->dfa.accept_from * m->row;
         out->n_states = m->dfa.n_states;
-        if (m->tier >= 2) {     // rows of the first (shallowest, BFS order) states that fit 60 KB of shared memory
+        if (m->tier == 2 || m->tier == 3) {     // rows of the first (shallowest, BFS order) states that fit 60 KB of shared memory
             uint64_t rows = (60ull * 1024) / (m->dfa.n_classes * 4ull);
             if (rows > m->dfa.n_states) rows = m->dfa.n_states;
             out->hot_entries = (uint32_t)(rows * m->dfa.n_classes);
@@ -533,7 +549,7 @@ int fqg_matcher_dfa_info(const fqg_matcher* m, fqg_dfa_info* out) {
     out->start = m->dfa.start;
     out->accept_from = m->dfa.accept_from;
     out->tier = (uint32_t)m->tier;
-    out->table_bytes = (uint32_t)(m->tier >= 2 ? m->t32.size() * 4 : m->t16.size() * 2);
+    out->table_bytes = (uint32_t)((m->tier == 2 || m->tier == 3) ? m->t32.size() * 4 : m->t16.size() * 2);
     return FQG_OK;
 }
 

@@ -32,8 +32,17 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
 //           lookup on the state-dependency chain; a word holding anything but ACGT (N, lowercase, protein,
 //           IUPAC ...) is detected exactly by rebuilding the four letters from the codes, and takes the
 //           one-byte path, so results never depend on the input being DNA.
+//   tier 4: same idea for automata too large for 256-entry rows (up to ~1300 states): rows of 16 two-base entries
+//           (+ the one-byte entries), two lookups per four bases.
 //   tier 1: byte offset of the row in a class-indexed shared-memory table (one lookup per byte + class LUT).
 //   tier 2: entry index of the row in a class-indexed table read through L2.
+// tiers whose table is staged whole into shared memory with states = shared addresses
+template <int TIER>
+constexpr bool kSmemTable = (TIER == 0 || TIER == 1 || TIER == 4);
+// tiers that consume packed 2-bit base codes (4 bases per lookup in tier 0, 2 per lookup in tier 4)
+template <int TIER>
+constexpr bool kPackedCodes = (TIER == 0 || TIER == 4);
+
 template <int TIER>
 struct DfaView {
     uint32_t tab;          // smem address of the table (tiers 0,1)
@@ -43,6 +52,7 @@ struct DfaView {
 
     __device__ __forceinline__ uint32_t step1(uint32_t st, uint32_t byte) const {
         if (TIER == 0) return lds_u16(st + 512u + lds_u8(cls + byte));
+        if (TIER == 4) return lds_u16(st + 32u + lds_u8(cls + byte));
         if (TIER == 1) return lds_u16(st + lds_u8(cls + byte));
         // tier 2: breadth-first state numbering puts the shallow (hot) states first; their rows live in shared memory
         const uint32_t idx = st + lds_u8(cls + byte);
@@ -63,7 +73,12 @@ struct DfaView {
         const uint32_t x = (w >> 1) & 0x03030303u;
         const uint32_t t = (x >> 1) & ~x & 0x01010101u;
         bad |= ((w & 0xF9F9F9F9u) ^ 0x41414141u) ^ (t * 0x11u);
-        return lds_u16(st + ((x * 0x40100401u) >> 23));
+        const uint32_t idx2 = (x * 0x40100401u) >> 23;                       // packed codes of the word, times two
+        if (TIER == 4) {                                                     // tier 4: rows of 16 two-base entries
+            st = lds_u16(st + ((idx2 >> 4) & 0x1Eu));                        // first two bases
+            return lds_u16(st + (idx2 & 0x1Eu));                             // last two bases
+        }
+        return lds_u16(st + idx2);
     }
 };
 
@@ -107,7 +122,7 @@ __device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t
         const uint32_t w1 = lds_u32_volatile(wp);
         const uint32_t w = __funnelshift_r(w0, w1, sh);
         w0 = w1;
-        if (TIER == 0) st = d.step4_acgt(st, w, bad);
+        if (kPackedCodes<TIER>) st = d.step4_acgt(st, w, bad);
         else {
             st = d.step1(st, w & 0xFFu);
             st = d.step1(st, (w >> 8) & 0xFFu);
@@ -115,7 +130,7 @@ __device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t
             st = d.step1(st, w >> 24);
         }
     }
-    if (TIER == 0 && bad) return walk_shared_bytes(d, p, len, st0);
+    if (kPackedCodes<TIER> && bad) return walk_shared_bytes(d, p, len, st0);
     const uint32_t rem = len & 3u;
     if (rem) {
         const uint32_t w = __funnelshift_r(w0, lds_u32_volatile(wp + 4), sh);

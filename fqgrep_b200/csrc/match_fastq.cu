@@ -107,7 +107,7 @@ __device__ __forceinline__ uint32_t id_hash32_global(const uint8_t* p, uint32_t 
 // TIER 0..2: DFA tiers (see kernels.hpp); TIER 3: read-name lookup.
 template <int TIER>
 struct RecordEval {
-    DfaView<(TIER < 3 ? TIER : 0)> view;
+    DfaView<(TIER != 3 ? TIER : 0)> view;
     NamesProbe names;
     uint32_t start, accept_from;
     bool invert;
@@ -165,10 +165,10 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
     uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
     uint16_t* s_list = s_pre + kGroups + 2;                                   // kListCap
 
-    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
+    if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     if (TIER == 2)
         for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
-    if (TIER <= 2)
+    if (TIER != 3)
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
     if (tid == 0) mbar_init(smem_addr(s_bar), 1);
     mbar_fence_init();
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
     ev.view.cls = smem_addr(s_cls);
     ev.view.hot_limit = TIER == 2 ? dfa.hot_entries : 0u;
     ev.names.nv = a.names;
-    const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
+    const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
     ev.start = dfa.start + reloc;
     ev.accept_from = dfa.accept_from + reloc;
     ev.invert = a.invert != 0;
@@ -446,7 +446,7 @@ __global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uin
 template <int TIER>
 cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
     constexpr int THREADS = 128;
-    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
+    const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
     uint32_t groups = (budget - table_smem - 256u - 128u) / kGroupBytes;
     if (groups > 8u) groups = 8u;
@@ -476,6 +476,7 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs
     switch (dfa.tier) {
         case 0: return launch_fastq_t<0>(dfa, a, sm_count, stream);
         case 1: return launch_fastq_t<1>(dfa, a, sm_count, stream);
+        case 4: return launch_fastq_t<4>(dfa, a, sm_count, stream);
         // tier 3 (q-gram filter) is an SoA-kernel path; the fused FASTQ kernel walks its exact tier-2 table
         default: return launch_fastq_t<2>(dfa, a, sm_count, stream);
     }

@@ -218,7 +218,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_bar + 32 * STAGES);
     s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
 
-    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
+    if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     if (TIER == 2)
         for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
     if (TIER == 3) {
@@ -234,7 +234,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
 
     DfaView<(TIER == 3 ? 2 : TIER)> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), TIER == 2 ? dfa.hot_entries : 0u};
     GramView gview{smem_addr(s_tab), dfa.gram, reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), dfa.start, dfa.accept_from};
-    const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
+    const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
     const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
     uint8_t* my_slots = s_slots + (size_t)warp * STAGES * slot_bytes;
     const uint32_t n_batches = (b.n_reads + 31u) >> 5;
@@ -334,7 +334,7 @@ match_soa_ring_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t t
     uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_empty + 64);
     s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
 
-    if (TIER <= 1) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
+    if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     if (TIER == 2)
         for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
@@ -346,7 +346,7 @@ match_soa_ring_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t t
     __syncthreads();
 
     DfaView<TIER> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), TIER == 2 ? dfa.hot_entries : 0u};
-    const uint32_t reloc = TIER <= 1 ? smem_addr(s_tab) : 0u;
+    const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;
     const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
     const uint32_t n_batches = (b.n_reads + 31u) >> 5;
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
@@ -433,7 +433,7 @@ cudaError_t launch_ring_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count,
     const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
     uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
     slot = (slot + 127u) & ~127u;
-    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
+    const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
     const uint32_t fixed = table_smem + 256u + 128u * 8u + 128u;
     const uint32_t budget = 227u * 1024u;
     if (fixed + 3u * slot > budget) return cudaErrorInvalidConfiguration;      // caller falls back to the double-buffered kernel
@@ -460,7 +460,7 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
     const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
     uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
     slot = (slot + 127u) & ~127u;
-    const uint32_t table_smem = TIER <= 1 ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 3 ? ((dfa.gram.bitmap_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
+    const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 3 ? ((dfa.gram.bitmap_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
     const uint32_t fixed = table_smem + 256u + 32u * STAGES * 8u + 128u;
     const uint32_t budget = 227u * 1024u;
     if (fixed + STAGES * slot > budget) {
@@ -485,14 +485,16 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
 }  // namespace
 
 cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
-    static const int use_ring = [] { const char* e = std::getenv("FQG_SOA_RING"); return e ? std::atoi(e) : 1; }();
-    if (use_ring && dfa.tier <= 2) {
-        cudaError_t e = dfa.tier == 0 ? launch_ring_t<0>(dfa, b, sm_count, stream) : dfa.tier == 1 ? launch_ring_t<1>(dfa, b, sm_count, stream) : launch_ring_t<2>(dfa, b, sm_count, stream);
+    // Measured on B200 (profiles/README.md): the ring variant matches the double-buffered kernel on the issue-bound
+    // shared-memory tiers (0.81 vs 0.81) and wins 25 % on the latency-bound L2 tier, so only tier 2 takes it.
+    if (dfa.tier == 2) {
+        cudaError_t e = launch_ring_t<2>(dfa, b, sm_count, stream);
         if (e != cudaErrorInvalidConfiguration) return e;
     }
     switch (dfa.tier) {
         case 0: return launch_t<0, 2>(dfa, b, sm_count, stream);
         case 1: return launch_t<1, 2>(dfa, b, sm_count, stream);
+        case 4: return launch_t<4, 2>(dfa, b, sm_count, stream);
         case 3: return launch_t<3, 1>(dfa, b, sm_count, stream);     // filter bitmap takes the smem: single staging slot, twice the warps
         default: return launch_t<2, 2>(dfa, b, sm_count, stream);
     }

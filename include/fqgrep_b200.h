@@ -82,7 +82,8 @@ int fqg_iupac_expand(const char* pattern, int to_regex, char* out, size_t cap, s
 typedef struct fqg_dfa_info {
     uint32_t n_states, n_classes, start, accept_from;
     uint32_t tier;          /* 0: 4-base-stride table in shared memory, 1: class-indexed table in shared memory,
-                               2: class-indexed table in L2, 3: q-gram filter in shared memory + exact verify (tier-2 table as fallback) */
+                               2: class-indexed table in L2 (hot rows cached in shared memory), 3: q-gram filter in shared memory +
+                               exact verify (tier-2 table as fallback), 4: 2-base-stride table in shared memory */
     uint32_t table_bytes;   /* device table footprint */
 } fqg_dfa_info;
 int fqg_matcher_dfa_info(const fqg_matcher* m, fqg_dfa_info* out);

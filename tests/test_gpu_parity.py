@@ -97,17 +97,33 @@ def test_all_three_table_tiers():
     mat = synth.bases(50_000, seed=9)
     rng = np.random.default_rng(3)
     small = ["ACGTAC", "TTTTT"]
-    medium = ["".join("ACGT"[i] for i in rng.integers(0, 4, 7)) for _ in range(300)]      # too short for the q-gram filter -> tier 1
+    medium = ["".join("ACGT"[i] for i in rng.integers(0, 4, 7)) for _ in range(300)]      # too short for the q-gram filter -> tier 4
+    medium2 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 7)) for _ in range(1500)]    # too many states for 2-base rows -> tier 1
     large = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(10_000)]
     synth.plant(mat, small + medium[:20] + large[:200], rate=0.05)
     bases, offs = synth.soa(mat)
     tiers = []
-    for pats in (small, medium, large):
+    for pats in (small, medium, medium2, large):
         m = F.Matcher(F.FIXED_SET, pats, opts(False, True))
         tiers.append(m.dfa_info().tier)
         cnt = check(F.FIXED_SET, pats, False, True, bases, offs)
         assert cnt > 0
-    assert tiers == [0, 1, 3]     # the large set runs the q-gram filter (tier 3)
+    assert tiers == [0, 4, 1, 3]     # 4-base rows, 2-base rows, class-indexed, q-gram filter
+
+
+def test_tier4_two_base_rows_with_non_acgt_reads_and_regex_sets():
+    rng = np.random.default_rng(31)
+    pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, 8)) + "[AC]N?" + "".join("ACGT"[i] for i in rng.integers(0, 4, 6)) for _ in range(40)]
+    assert F.Matcher(F.REGEX_SET, pats, opts(False, True)).dfa_info().tier == 4
+    mat = synth.bases(60_000, seed=8)
+    mat[::7, 30] = ord("N")
+    mat[::11, 3:9] = np.frombuffer(b"acgtnn", dtype=np.uint8)
+    lit = [p.replace("[AC]N?", "A") for p in pats[:10]] + [p.replace("[AC]N?", "CN") for p in pats[10:20]]
+    synth.plant(mat, lit, rate=0.05)
+    bases, offs = synth.soa(mat)
+    for inv, rc in ((False, False), (False, True), (True, True)):
+        cnt = check(F.REGEX_SET, pats, inv, rc, bases, offs)
+        assert 0 < cnt < 60_000
 
 
 def test_tier2_l2_automaton_for_large_sets_of_short_patterns():
