@@ -93,17 +93,6 @@ struct NamesProbe {
     }
 };
 
-__device__ __forceinline__ uint32_t id_hash32_shared(uint32_t p, uint32_t len) {
-    uint32_t h = 0x811C9DC5u ^ len;
-    for (uint32_t i = 0; i < len; i++) h = (h ^ lds_u8_volatile(p + i)) * 0x01000193u;
-    return h ^ (h >> 15);
-}
-__device__ __forceinline__ uint32_t id_hash32_global(const uint8_t* p, uint32_t len) {
-    uint32_t h = 0x811C9DC5u ^ len;
-    for (uint32_t i = 0; i < len; i++) h = (h ^ p[i]) * 0x01000193u;
-    return h ^ (h >> 15);
-}
-
 // TIER 0..2: DFA tiers (see kernels.hpp); TIER 3: read-name lookup.
 template <int TIER>
 struct RecordEval {
@@ -117,9 +106,16 @@ struct RecordEval {
         uint32_t head_end = p0;
         if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
         uint32_t id_len = 0;
-        if (TIER == 3 || want_idh) {
-            while (s + 1 + id_len < head_end && lds_u8_volatile(tile + s + 1 + id_len) != ' ') id_len++;
-            if (want_idh) *idh = id_hash32_shared(tile + s + 1, id_len);
+        if (TIER == 3 || want_idh) {      // one pass: find the end of the id (first space) and hash it on the way
+            uint32_t h = 0x811C9DC5u;
+            for (;;) {
+                if (s + 1 + id_len >= head_end) break;
+                const uint32_t c = lds_u8_volatile(tile + s + 1 + id_len);
+                if (c == ' ') break;
+                h = (h ^ c) * 0x01000193u;
+                id_len++;
+            }
+            if (want_idh) { h ^= id_len; *idh = h ^ (h >> 15); }
         }
         bool found;
         if (TIER == 3) found = names.contains_shared(tile + s + 1, id_len);
@@ -129,8 +125,9 @@ struct RecordEval {
     __device__ __noinline__ bool eval_global(const uint8_t* head, uint32_t head_len, const uint8_t* seq, uint32_t seq_len, uint32_t* idh, bool want_idh) const {
         uint32_t id_len = 0;
         if (TIER == 3 || want_idh) {
-            while (id_len < head_len && head[id_len] != ' ') id_len++;
-            if (want_idh) *idh = id_hash32_global(head, id_len);
+            uint32_t h = 0x811C9DC5u;
+            while (id_len < head_len && head[id_len] != ' ') { h = (h ^ head[id_len]) * 0x01000193u; id_len++; }
+            if (want_idh) { h ^= id_len; *idh = h ^ (h >> 15); }
         }
         bool found;
         if (TIER == 3) found = names.contains_global(head, id_len);
