@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfqgrep_b200.so")
-SOURCES = ["api.cu", "match_soa.cu", "match_fastq.cu", "synth.cu", "regex_compile.cc", "ac_build.cc", "gram_filter.cc", "names.cc", "fastq_host.cc"]
+SOURCES = ["api.cu", "match_soa.cu", "match_fastq.cu", "synth.cu", "regex_compile.cc", "ac_build.cc", "gram_filter.cc", "names.cc", "fastq_host.cc", "input_host.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz"]
     subprocess.check_call(cmd)
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))

@@ -730,6 +730,17 @@ int fqg_iupac_expand(const char* pattern, int to_regex, char* out, size_t cap, s
     return FQG_OK;
 }
 
+int fqg_read_input(const char* path, int decompress, int pinned, uint8_t** out, size_t* n_out) {
+    if (!path || !out || !n_out) return fail(FQG_E_INVALID_ARG, "NULL argument");
+    std::string err;
+    int rc = read_input(path, decompress, pinned, out, n_out, &err);
+    if (rc) return fail(rc, err);
+    return FQG_OK;
+}
+void fqg_free_input(uint8_t* p, int pinned) { free_input(p, pinned); }
+int fqg_is_gzip_path(const char* path) { return path && is_gzip_path(path) ? 1 : 0; }
+int fqg_is_fastq_path(const char* path) { return path && is_fastq_path(path) ? 1 : 0; }
+
 int fqg_fastq_split(const uint8_t* buf, size_t n, uint32_t parts, uint64_t* cuts) {
     if (!cuts || parts == 0 || (n && !buf)) return fail(FQG_E_INVALID_ARG, "bad argument");
     cuts[0] = 0;

@@ -21,6 +21,12 @@ struct HostRecord {
 // Returns 1 (record), 0 (clean end of input), <0 = FQG_E_FASTQ with *err set.
 int next_host_record(const uint8_t* buf, size_t n, size_t* pos, HostRecord* rec, std::string* err);
 
+// input plumbing (input_host.cc)
+bool is_gzip_path(const char* path);
+bool is_fastq_path(const char* path);
+int read_input(const char* path, int decompress, int pinned, uint8_t** out, size_t* n_out, std::string* err);
+void free_input(uint8_t* p, int pinned);
+
 size_t find_record_start(const uint8_t* buf, size_t n, size_t pos);
 
 // Ordered write-back of selected units (src/main.rs:641-657, 682-727).

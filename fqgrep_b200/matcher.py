@@ -156,6 +156,45 @@ class Matcher:
         return bool(bits[0])
 
 
+def is_gzip_path(path):
+    """is_gzip_path (src/lib/mod.rs:170-175)."""
+    return bool(_ffi.lib().fqg_is_gzip_path(str(path).encode()))
+
+
+def is_fastq_path(path):
+    """is_fastq_path (src/lib/mod.rs:177-183)."""
+    return bool(_ffi.lib().fqg_is_fastq_path(str(path).encode()))
+
+
+def read_input(path, decompress=False, pinned=False):
+    """spawn_reader of the reference (src/main.rs:61-87): file -> optional (multi-member) gunzip -> bytes as a numpy array.
+    pinned=True keeps the bytes in CUDA pinned memory (the caller must keep the returned array alive and not resize it)."""
+    p = C.c_void_p()
+    n = C.c_size_t(0)
+    _check(_ffi.lib().fqg_read_input(str(path).encode(), int(decompress), int(pinned), C.byref(p), C.byref(n)))
+    view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n.value, 1),))[: n.value]
+    if pinned:
+        return _PinnedInput(view, p)
+    out = view.copy()
+    _ffi.lib().fqg_free_input(p, 0)
+    return out
+
+
+class _PinnedInput(np.ndarray):
+    """numpy view of a pinned input buffer; frees it with the library when collected."""
+
+    def __new__(cls, view, handle):
+        obj = np.asarray(view).view(cls)
+        obj._handle = handle
+        return obj
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            _ffi.lib().fqg_free_input(h, 1)
+            self._handle = None
+
+
 def write_selected(mask_words, r1, r2=None, mode=SINGLE, split=False):
     """Selected records in input order, seq_io write_to form (src/main.rs:641-657, 682-727)."""
     a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)

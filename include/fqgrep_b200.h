@@ -151,6 +151,15 @@ int fqg_grep_fastq_device(fqg_ctx* ctx, const fqg_matcher* m, int mode, const ui
 int fqg_write_selected(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* unit_mask,
                        uint8_t* out, size_t* out_len, uint8_t* out2, size_t* out2_len);
 
+/* Input plumbing, host side: replaces spawn_reader (src/main.rs:61-87).  Reads `path` ("-" = stdin) completely into one
+ * buffer (pinned=1: cudaHostAlloc, the fast path for fqg_grep_fastq_host; pinned=0: malloc, no CUDA needed).  The input is
+ * gunzipped (multi-member gzip / BGZF, like flate2's MultiGzDecoder) when the extension is .gz/.bgz, or when `decompress`
+ * (-Z) is set and the extension is not .fq/.fastq (src/main.rs:77, src/lib/mod.rs:157-183).  Free with fqg_free_input. */
+int fqg_read_input(const char* path, int decompress, int pinned, uint8_t** out, size_t* n_out);
+void fqg_free_input(uint8_t* p, int pinned);
+int fqg_is_gzip_path(const char* path);    /* src/lib/mod.rs:170-175 */
+int fqg_is_fastq_path(const char* path);   /* src/lib/mod.rs:177-183 */
+
 /* Multi-GPU sharding helper (host): cut a FASTQ buffer into `parts` contiguous byte ranges that begin at record
  * starts (the reference has no sharding; this replaces nothing, it feeds one fqg_ctx per GPU).  cuts: uint64[parts+1],
  * cuts[0]=0, cuts[parts]=n.  Ranges hold roughly equal BYTES; record counts per range come back in fqg_result. */

@@ -1,0 +1,65 @@
+"""Input plumbing: extension rules and host-side gunzip, against the reference's vectors
+(src/lib/mod.rs:209-233, src/main.rs:1279-1297) and Python's gzip.  CPU only except the end-to-end count."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import fqgrep_b200 as F
+from oracle import oracle as O
+from tests.fq_util import fastq
+
+
+def test_extension_rules_match_reference_vectors():
+    for name, exp in (("test_fastq.fq.gz", True), ("test_fastq.fq.bgz", True), ("test_fastq.fq.tar", False)):
+        assert F.is_gzip_path("/tmp/x/" + name) == exp
+    for name, exp in (("test_fastq.fq", True), ("test_fastq.fastq", True), ("test_fastq.sam", False)):
+        assert F.is_fastq_path("/tmp/x/" + name) == exp
+    assert not F.is_gzip_path("/tmp/.gz") and not F.is_gzip_path("/tmp/a.b/gz")
+
+
+def _write(path, data, mode):
+    if mode == "plain":
+        open(path, "wb").write(data)
+    elif mode == "gz":
+        with gzip.open(path, "wb") as f:
+            f.write(data)
+    else:   # multi-member (what bgzip / concatenated gzips look like)
+        with open(path, "wb") as f:
+            for i in range(0, len(data), 700):
+                f.write(gzip.compress(data[i:i + 700]))
+
+
+def test_read_input_plain_gzip_multimember_and_decompress_flag(tmp_path):
+    data = fastq(["ACGT" * 40, "TTTTGGGGCCCC" * 12, "N" * 7] * 200)
+    cases = [("a.fq", "plain", False), ("a.fastq", "plain", True),     # -Z does not apply to .fq/.fastq (main.rs:77)
+             ("a.fq.gz", "gz", False), ("a.fq.bgz", "multi", False), ("a.dat", "gz", True), ("a.txt", "plain", False)]
+    for name, mode, z in cases:
+        p = str(tmp_path / name)
+        _write(p, data, mode)
+        got = F.read_input(p, decompress=z)
+        assert got.tobytes() == data, name
+    with pytest.raises(F.FqgrepError):
+        F.read_input(str(tmp_path / "missing.fq"))
+    bad = str(tmp_path / "bad.fq.gz")
+    open(bad, "wb").write(b"this is not gzip")
+    with pytest.raises(F.FqgrepError):
+        F.read_input(bad)
+    empty = str(tmp_path / "empty.fq")
+    open(empty, "wb").write(b"")
+    assert F.read_input(empty).size == 0
+
+
+@pytest.mark.gpu
+def test_count_is_the_same_for_fq_fastq_gz_bgz(tmp_path, kat):
+    """main.rs:1279-1297: the same reads behind .fq / .fastq / .fq.gz / .fq.bgz give the same count."""
+    seqs = ["AAAA", "TTTT", "GGGG", "CCCC", "ACGT"] * 50
+    data = fastq(seqs)
+    m = F.MatcherFactory.new_matcher(None, False, ["A"])
+    exp = O.Matcher(O.REGEX_SET, ["A"]).grep(data)["count"]
+    for name, mode in (("r.fq", "plain"), ("r.fastq", "plain"), ("r.fq.gz", "gz"), ("r.fq.bgz", "multi")):
+        p = str(tmp_path / name)
+        _write(p, data, mode)
+        buf = F.read_input(p, pinned=True)
+        assert m.grep_fastq(buf)["count"] == exp == 100
