@@ -206,8 +206,11 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + T0, bytes, bar);
             }
-            mbar_wait(bar, phase);
+            // one thread polls the transaction barrier; the rest of the group sleeps on the (hardware) named barrier
+            // instead of spinning on try_wait and stealing issue slots from the other groups of the SM
+            if (tid == 0) mbar_wait(bar, phase);
             phase ^= 1u;
+            group_sync();
         }
 
         // ---- newline bitmap: one word per 32 bytes
