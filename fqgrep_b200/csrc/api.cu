@@ -246,7 +246,6 @@ const char* fastq_err_name(unsigned code) {
         case 2: return "expected '+' separator line (InvalidSep)";
         case 3: return "sequence and quality lengths differ (UnequalLengths)";
         case 4: return "truncated record (UnexpectedEnd)";
-        case 5: return "records shorter than 8 bytes on average are not supported on the device path";
         case 6: return "record bitmask capacity exceeded (records shorter than 8 bytes, or 16 bytes with pair id check)";
     }
     return "unknown";
@@ -405,7 +404,7 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
     if (h_ctl[0] != ~0ull) {
         unsigned code = (unsigned)(h_ctl[0] & 15);
         if (code == 6) *capacity_hit = true;
-        return fail(code >= 5 ? FQG_E_TOO_LARGE : FQG_E_FASTQ, std::string("FASTQ parse error at byte ") + std::to_string(h_ctl[0] >> 4) + ": " + fastq_err_name(code));
+        return fail(code >= 6 ? FQG_E_TOO_LARGE : FQG_E_FASTQ, std::string("FASTQ parse error at byte ") + std::to_string(h_ctl[0] >> 4) + ": " + fastq_err_name(code));
     }
     uint64_t lines[2] = {sp[0].n ? h_ctl[3] : 0, sp[1].n ? h_ctl[4] : 0};
     for (int i = 0; i < n_streams; i++)

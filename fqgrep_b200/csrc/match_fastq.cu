@@ -23,14 +23,13 @@
 namespace fqg {
 namespace {
 
-constexpr uint32_t kTile = 16384;
+constexpr uint32_t kTile = 19456;            // 19 KB: ~61 records of 317 B, i.e. two almost full warps in the record phase
 constexpr uint32_t kOverlap = 1024;
 constexpr uint32_t kLoad = kTile + kOverlap;
 constexpr uint32_t kGroups = kLoad / 32;          // one bitmap word per 32 bytes
-constexpr uint32_t kListCap = kTile / 8;          // record starts per tile we can index (records >= 8 B on average)
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
-enum : uint32_t { kErrInvalidStart = 1, kErrInvalidSep = 2, kErrUnequal = 3, kErrUnexpectedEnd = 4, kErrDensity = 5, kErrMaskOverflow = 6 };
+enum : uint32_t { kErrInvalidStart = 1, kErrInvalidSep = 2, kErrUnequal = 3, kErrUnexpectedEnd = 4, kErrMaskOverflow = 6 };
 
 __device__ __forceinline__ void report(const FastqArgs& a, uint64_t pos, uint32_t code) {
     atomicMin(a.err, (unsigned long long)((pos << 4) | code));
@@ -106,16 +105,30 @@ struct RecordEval {
         uint32_t head_end = p0;
         if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
         uint32_t id_len = 0;
-        if (TIER == 3 || want_idh) {      // one pass: find the end of the id (first space) and hash it on the way
-            uint32_t h = 0x811C9DC5u;
-            for (;;) {
-                if (s + 1 + id_len >= head_end) break;
-                const uint32_t c = lds_u8_volatile(tile + s + 1 + id_len);
-                if (c == ' ') break;
-                h = (h ^ c) * 0x01000193u;
-                id_len++;
+        if (TIER == 3 || want_idh) {      // id = header up to the first space; scanned and hashed four bytes at a time
+            const uint32_t a0 = tile + s + 1u, n = head_end - (s + 1u), sh = (a0 & 3u) * 8u;
+            uint32_t wp = a0 & ~3u, w0 = lds_u32_volatile(wp), h = 0x811C9DC5u;
+            id_len = n;
+            for (uint32_t i = 0; i < n; i += 4u) {
+                wp += 4u;
+                const uint32_t w1 = lds_u32_volatile(wp);
+                uint32_t w = __funnelshift_r(w0, w1, sh);
+                w0 = w1;
+                const uint32_t v = n - i < 4u ? n - i : 4u;                          // id bytes in this word
+                const uint32_t x = w ^ 0x20202020u;
+                uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where the byte is ' '
+                if (v < 4u) z &= (1u << (8u * v)) - 1u;
+                if (z) {                                                            // the id ends at the first space
+                    const uint32_t bidx = ((uint32_t)__ffs(z) - 1u) >> 3;
+                    if (bidx) h = (h ^ (w & ((1u << (8u * bidx)) - 1u))) * 0x01000193u;
+                    id_len = i + bidx;
+                    break;
+                }
+                if (v < 4u) w &= (1u << (8u * v)) - 1u;
+                h = (h ^ w) * 0x01000193u;
             }
-            if (want_idh) { h ^= id_len; *idh = h ^ (h >> 15); }
+            h ^= id_len;
+            if (want_idh) *idh = h ^ (h >> 15);
         }
         bool found;
         if (TIER == 3) found = names.contains_shared(tile + s + 1, id_len);
@@ -124,10 +137,16 @@ struct RecordEval {
     }
     __device__ __noinline__ bool eval_global(const uint8_t* head, uint32_t head_len, const uint8_t* seq, uint32_t seq_len, uint32_t* idh, bool want_idh) const {
         uint32_t id_len = 0;
-        if (TIER == 3 || want_idh) {
+        while (id_len < head_len && head[id_len] != ' ') id_len++;
+        if (want_idh) {                 // same word-wise hash as eval_shared, assembled from bytes
             uint32_t h = 0x811C9DC5u;
-            while (id_len < head_len && head[id_len] != ' ') { h = (h ^ head[id_len]) * 0x01000193u; id_len++; }
-            if (want_idh) { h ^= id_len; *idh = h ^ (h >> 15); }
+            for (uint32_t i = 0; i < id_len; i += 4u) {
+                uint32_t w = 0;
+                for (uint32_t b = 0; b < 4u && i + b < id_len; b++) w |= (uint32_t)head[i + b] << (8u * b);
+                h = (h ^ w) * 0x01000193u;
+            }
+            h ^= id_len;
+            *idh = h ^ (h >> 15);
         }
         bool found;
         if (TIER == 3) found = names.contains_global(head, id_len);
@@ -136,8 +155,8 @@ struct RecordEval {
     }
 };
 
-// per-group shared memory: [mbarrier 8][prefix 8][misc 240][tile kLoad+32][bitmap][pre][list], 128-byte aligned
-constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u + kListCap * 2u) + 127u) & ~127u;
+// per-group shared memory: [mbarrier 8][prefix 8][misc 240][tile kLoad+32][bitmap][pre], 128-byte aligned
+constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u) + 127u) & ~127u;
 
 // A CTA is up to 8 independent "tile groups" of THREADS threads (named barriers 1..8) that share one copy of the
 // automaton in shared memory; each group runs the tile loop on its own buffers, so one SM keeps up to 8 tiles in
@@ -160,7 +179,6 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
     uint8_t* s_tile = s_grp + 256;                                           // kLoad + 32, 128-byte aligned for the bulk copy
     uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);   // kGroups + 2
     uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
-    uint16_t* s_list = s_pre + kGroups + 2;                                   // kListCap
 
     if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     if (TIER == 2)
@@ -287,37 +305,25 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
         group_sync();
         const unsigned long long Lt = *s_prefix;    // global index of this tile's first newline
 
-        // ---- record starts in this tile -> s_list
+        // ---- records that start in this tile: record k begins right after the newline of local rank j0 + 4 (k - extra)
         const bool first_global = t == 0;
         const uint32_t extra = first_global ? 1u : 0u;
         const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
         const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
         uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
         if (T0 + region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
-        if (first_global && tid == 0) s_list[0] = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < kGpt; k++) {
-            const uint32_t g = tid * kGpt + k;
-            if (g < kGroups && g * 32u < region) {
-                uint32_t bits = s_bitmap[g];
-                if (g * 32u + 32u > region) bits &= (1u << (region - g * 32u)) - 1u;
-                uint32_t j = s_pre[g];
-                while (bits) {
-                    const uint32_t b = __ffs(bits) - 1u;
-                    bits &= bits - 1u;
-                    if (j >= j0 && ((j - j0) & 3u) == 0) {
-                        const uint32_t k2 = ((j - j0) >> 2) + extra;
-                        if (k2 < kListCap) s_list[k2] = (uint16_t)(g * 32u + b + 1u);
-                    }
-                    j++;
-                }
+        // position of the newline with local rank r (< agg): binary search in the per-group prefix counts, then bit select
+        const uint32_t n_groups_region = (region + 31u) >> 5;
+        auto newline_of_rank = [&](uint32_t r) -> uint32_t {
+            uint32_t lo = 0, hi = n_groups_region;             // s_pre[lo] <= r < s_pre[hi]
+            while (hi - lo > 1u) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_pre[mid] <= r) lo = mid; else hi = mid;
             }
-        }
-        if (n_list > kListCap) {
-            if (tid == 0) report(a, T0, kErrDensity);
-            n_list = kListCap;
-        }
-        group_sync();
+            uint32_t bits = s_bitmap[lo];
+            for (uint32_t n = r - s_pre[lo]; n; n--) bits &= bits - 1u;
+            return lo * 32u + (uint32_t)__ffs(bits) - 1u;
+        };
 
         // ---- one thread per record
         const uint32_t n_groups_avail = (avail + 31u) >> 5;
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
             bool sel = false;
             uint32_t idh = 0;
             if (valid) {
-                const uint32_t s = s_list[k];
+                const uint32_t s = k < extra ? 0u : newline_of_rank(j0 + 4u * (k - extra)) + 1u;
                 const uint32_t p0 = next_nl(s);
                 const uint32_t p1 = p0 == kNone ? kNone : next_nl(p0 + 1u);
                 const uint32_t p2 = p1 == kNone ? kNone : next_nl(p1 + 1u);
