@@ -53,7 +53,20 @@ __device__ __forceinline__ bool gram_verify(const GramView& v, uint32_t p, uint3
 }
 
 // 2-bit codes of the q bases ending at base index e of the read at shared address p (only for the rare filter hits)
-__device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q) {
+__device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q, uint32_t qmask) {
+    if ((e & 3u) == 3u && e >= 15u) {          // word-aligned sampling: re-pack the four words that end at base e
+        const uint32_t a = p + e - 15u, sh = (a & 3u) * 8u;
+        uint32_t wp = a & ~3u, w0 = lds_u32_volatile(wp), g = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            wp += 4u;
+            const uint32_t w1 = lds_u32_volatile(wp);
+            const uint32_t x = (__funnelshift_r(w0, w1, sh) >> 1) & 0x03030303u;
+            w0 = w1;
+            g = (g << 8) | ((x * 0x40100401u) >> 24);
+        }
+        return g & qmask;
+    }
     uint32_t g = 0;
     for (uint32_t i = e + 1u - q; i <= e; i++) g = (g << 2) | ((lds_u8(p + i) >> 1) & 3u);
     return g;
@@ -180,13 +193,13 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
             const uint32_t b = (uint32_t)__ffs((int)hits0) - 1u;
             hits0 &= hits0 - 1u;
             const uint32_t e = e0 + (n0 - 1u - b) * stride;
-            found = gram_verify(v, p, len, gram_at(p, e, q), e);
+            found = gram_verify(v, p, len, gram_at(p, e, q, qmask), e);
         }
         while (hits1 && !found) {
             const uint32_t b = (uint32_t)__ffs((int)hits1) - 1u;
             hits1 &= hits1 - 1u;
             const uint32_t e = e0 + (32u + n1 - 1u - b) * stride;
-            found = gram_verify(v, p, len, gram_at(p, e, q), e);
+            found = gram_verify(v, p, len, gram_at(p, e, q, qmask), e);
         }
     }
     if (exact_walk) {          // very long read: exact automaton walk through L2
