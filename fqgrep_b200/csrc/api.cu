@@ -58,6 +58,11 @@ struct fqg_matcher {
     uint8_t lut[256] = {0};   // byte -> class in the form the tier's kernel wants
     std::mutex mu;
     std::map<int, DeviceTables> dev;
+    // Mixed -e/-f sets (many plain literals + a few real regexes) determinise into automata far too large for shared
+    // memory.  For the SoA kernels they are split: `split_lit` (the literal members: q-gram filter) runs first and leaves
+    // its "found" bits in the mask, `split_rest` (the regex members: small automaton) ORs them in before invert_match.
+    // `dfa` above is still the automaton of the WHOLE set (fused FASTQ kernel, introspection).
+    std::unique_ptr<fqg_matcher> split_lit, split_rest;
 };
 
 struct fqg_ctx {
@@ -502,7 +507,28 @@ int fqg_matcher_new(int kind, const uint8_t* blob, const uint64_t* offsets, uint
             if (all_literal) {
                 if (!compile_literal_set(lits, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
                 build_gram_filter(lits, rc, &m->gram);
-            } else if (!compile_regex_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
+            } else {
+                if (!compile_regex_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
+                std::vector<std::string> lit_members, rest_members;
+                for (size_t i = 0; i < pats.size(); i++) {
+                    std::string l;
+                    if (regex_as_literal(pats[i], &l) && l.size() >= 8) lit_members.push_back(l); else rest_members.push_back(pats[i]);
+                }
+                if (lit_members.size() >= 16 && !rest_members.empty()) {
+                    auto a = std::make_unique<fqg_matcher>();
+                    auto r = std::make_unique<fqg_matcher>();
+                    a->kind = FQG_FIXED_SET; a->opts = opts & ~FQG_INVERT_MATCH;
+                    r->kind = FQG_REGEX_SET; r->opts = opts;
+                    std::string e2;
+                    if (compile_literal_set(lit_members, rc, &a->dfa, &e2) && build_gram_filter(lit_members, rc, &a->gram) &&
+                        compile_regex_set(rest_members, rc, &r->dfa, &e2)) {
+                        build_tables(a.get());
+                        build_tables(r.get());
+                        m->split_lit = std::move(a);
+                        m->split_rest = std::move(r);
+                    }
+                }
+            }
             break;
         }
         case FQG_BITMASK:
@@ -519,12 +545,16 @@ int fqg_matcher_new(int kind, const uint8_t* blob, const uint64_t* offsets, uint
             return fail(FQG_E_INVALID_ARG, "unknown matcher kind");
     }
     if (kind != FQG_NAMES) build_tables(m.get());
+    // the split only pays when the whole-set automaton would walk L2 and the parts do not
+    if (m->split_lit && !(m->tier == 2 && m->split_lit->tier != 2 && m->split_rest->tier != 2)) { m->split_lit.reset(); m->split_rest.reset(); }
     *out = m.release();
     return FQG_OK;
 }
 
 void fqg_matcher_free(fqg_matcher* m) {
     if (!m) return;
+    if (m->split_lit) fqg_matcher_free(m->split_lit.release());
+    if (m->split_rest) fqg_matcher_free(m->split_rest.release());
     for (auto& kv : m->dev) {
         int prev = 0;
         cudaGetDevice(&prev);
@@ -547,7 +577,7 @@ int fqg_matcher_dfa_info(const fqg_matcher* m, fqg_dfa_info* out) {
     out->n_classes = m->dfa.n_classes;
     out->start = m->dfa.start;
     out->accept_from = m->dfa.accept_from;
-    out->tier = (uint32_t)m->tier;
+    out->tier = m->split_lit ? 5u : (uint32_t)m->tier;
     out->table_bytes = (uint32_t)((m->tier == 2 || m->tier == 3) ? m->t32.size() * 4 : m->t16.size() * 2);
     return FQG_OK;
 }
@@ -622,8 +652,20 @@ int fqg_match_bases_device(fqg_ctx* c, const fqg_matcher* m, const uint8_t* d_ba
     DeviceDfa dd;
     int rc = get_device_dfa(c, m, &dd);
     if (rc) return rc;
+    if (m->split_lit) {
+        // pass 1: literal members -> "found" bits in d_mask_out; pass 2: regex members, OR those bits in before invert
+        DeviceDfa d1, d2;
+        if ((rc = get_device_dfa(c, m->split_lit.get(), &d1)) || (rc = get_device_dfa(c, m->split_rest.get(), &d2))) return rc;
+        SoaBatch b1{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, nullptr, nullptr, 0u, avg_read_len, nullptr};
+        CU_TRY(launch_match_soa(d1, b1, c->sm_count, (cudaStream_t)stream));
+        SoaBatch b2{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
+                    (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, d_mask_out};
+        CU_TRY(launch_match_soa(d2, b2, c->sm_count, (cudaStream_t)stream));
+        g_launches += 2;
+        return FQG_OK;
+    }
     SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
-               (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len};
+               (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr};
     CU_TRY(launch_match_soa(dd, b, c->sm_count, (cudaStream_t)stream));
     g_launches++;
     return FQG_OK;

@@ -48,6 +48,7 @@ struct SoaBatch {
     unsigned long long* count;
     uint32_t invert;
     uint32_t avg_read_len;
+    const uint32_t* pre_or_mask;   // optional: "pattern found" bits of another matcher, OR-ed in BEFORE invert_match is applied
 };
 
 // K3/K2/K1: per-read DFA walk over SoA reads (bases + start/end), bitmask + count epilogue (K5 fused).

@@ -309,7 +309,9 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
             st = walk_global(view, b.bases + cur.s, len, st);
         }
         const uint32_t r = batch * 32u + lane;
-        const bool sel = (r < b.n_reads) && ((st >= st_accept) != (b.invert != 0));
+        bool found = st >= st_accept;
+        if (b.pre_or_mask) found |= ((__ldg(b.pre_or_mask + batch) >> lane) & 1u) != 0;     // split pattern sets, see api.cu
+        const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
         uint32_t m = __ballot_sync(kFullMask, sel);
         if (lane == 0) {
             if (b.or_mask) m |= __ldg(b.or_mask + batch);
@@ -427,7 +429,9 @@ match_soa_ring_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t t
         else if (len) st = walk_global(view, b.bases + cur.s, len, st_start);
 
         const uint32_t r = batch * 32u + lane;
-        const bool sel = (r < b.n_reads) && ((st >= st_accept) != (b.invert != 0));
+        bool found = st >= st_accept;
+        if (b.pre_or_mask) found |= ((__ldg(b.pre_or_mask + batch) >> lane) & 1u) != 0;     // split pattern sets, see api.cu
+        const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
         uint32_t m = __ballot_sync(kFullMask, sel);
         if (lane == 0) {
             if (b.or_mask) m |= __ldg(b.or_mask + batch);

@@ -83,7 +83,8 @@ typedef struct fqg_dfa_info {
     uint32_t n_states, n_classes, start, accept_from;
     uint32_t tier;          /* 0: 4-base-stride table in shared memory, 1: class-indexed table in shared memory,
                                2: class-indexed table in L2 (hot rows cached in shared memory), 3: q-gram filter in shared memory +
-                               exact verify (tier-2 table as fallback), 4: 2-base-stride table in shared memory */
+                               exact verify (tier-2 table as fallback), 4: 2-base-stride table in shared memory,
+                               5: mixed set split into a literal part (tier 3) and a regex part (small table), two SoA passes */
     uint32_t table_bytes;   /* device table footprint */
 } fqg_dfa_info;
 int fqg_matcher_dfa_info(const fqg_matcher* m, fqg_dfa_info* out);

@@ -127,6 +127,21 @@ def test_tier4_two_base_rows_with_non_acgt_reads_and_regex_sets():
         assert 0 < cnt < 60_000
 
 
+def test_mixed_literal_and_regex_set_is_split_into_two_passes():
+    """-f file with hundreds of plain literals plus a few real regexes: literal part via the q-gram filter, regex part via
+    a small automaton, found-bits OR-ed before invert_match (tier 5)."""
+    rng = np.random.default_rng(41)
+    lits = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(250)]
+    pats = lits + ["AC.G[AT]CA{2}T", "^TTTT", "GG$"]
+    assert F.Matcher(F.REGEX_SET, pats, opts(False, True)).dfa_info().tier == 5
+    mat = synth.bases(80_000, seed=14)
+    synth.plant(mat, lits[:30], rate=0.03)
+    bases, offs = synth.soa(mat)
+    for inv, rc in ((False, False), (False, True), (True, False), (True, True)):
+        cnt = check(F.REGEX_SET, pats, inv, rc, bases, offs)
+        assert 0 < cnt < 80_000
+
+
 def test_tier2_l2_automaton_for_large_sets_of_short_patterns():
     rng = np.random.default_rng(12)
     pats = list({"".join("ACGTN"[i] for i in rng.integers(0, 5, 7)) for _ in range(14000)})     # 7-mers: too short for the q-gram filter
