@@ -1,0 +1,98 @@
+"""Parity at benchmark scale (BASELINE.json configs[1] shape): millions of device-generated reads, full mask compared with
+the oracle, and the three product paths (SoA kernel, fused FASTQ kernel on HBM-resident bytes, host streaming pipeline)
+compared with each other bit for bit -- a size-independent cross-check that holds at any N."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fqgrep_b200 as F
+from fqgrep_b200 import _ffi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PATS = ["GACGAGATTA", "GACGTGATTA"]
+RL = 150
+
+
+def _gen(torch, n, seed, pseed, fastq):
+    L = _ffi.lib()
+    dev = torch.device("cuda:0")
+    blob = "".join(PATS).encode()
+    offs = np.array([0, 10, 20], dtype=np.uint32)
+    rec = (2 * RL + 17) if fastq else RL
+    t = torch.empty(n * rec + 64, dtype=torch.uint8, device=dev)
+    rc = L.fqg_synth_reads_device(F.context(0), t.data_ptr(), n, 0, RL, fastq, seed, blob, offs.ctypes.data_as(C.c_void_p), 2, 0.01, pseed,
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, _ffi.last_error()
+    torch.cuda.synchronize()
+    return t
+
+
+def test_device_generator_is_bit_identical_to_the_numpy_one():
+    import torch
+    from tests import synth
+    n = 50_000
+    for seed, pseed in ((1, 99), (2, 98)):
+        mat = synth.bases(n, RL, seed=seed)
+        synth.plant(mat, PATS, rate=0.01, seed=pseed)
+        got = _gen(torch, n, seed, pseed, 0)[: n * RL].cpu().numpy()
+        assert (got == mat.reshape(-1)).all()
+        gotq = _gen(torch, n, seed, pseed, 1)[: n * (2 * RL + 17)].cpu().numpy()
+        assert (gotq == synth.fastq(mat)).all()
+
+
+def test_four_million_pairs_three_paths_and_oracle_agree():
+    import torch
+    L = _ffi.lib()
+    ctx = F.context(0)
+    n = 4_000_000
+    m = F.MatcherFactory.new_matcher(None, False, PATS, None, F.MatcherOpts(False, True))
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dev = torch.device("cuda:0")
+    words = n // 32 + 2
+    # path 1: SoA kernel, mate masks OR-ed (main.rs:749-755)
+    masks = []
+    offs = (torch.arange(n + 1, dtype=torch.int64, device=dev) * RL).to(torch.int32)
+    m1 = torch.zeros(words, dtype=torch.int32, device=dev)
+    m2 = torch.zeros(words, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    host_bases = []
+    for (seed, pseed), out, orm in (((1, 99), m1, None), ((2, 98), m2, m1)):
+        tb = _gen(torch, n, seed, pseed, 0)
+        rc = L.fqg_match_bases_device(ctx, m._h, tb.data_ptr(), offs.data_ptr(), offs.data_ptr() + 4, n, out.data_ptr(),
+                                      orm.data_ptr() if orm is not None else None, cnt.data_ptr() if orm is not None else None, RL, sp)
+        assert rc == 0, _ffi.last_error()
+        torch.cuda.synchronize()
+        host_bases.append(tb[: n * RL].cpu().numpy())
+        del tb
+    soa_mask = m2.cpu().numpy().view(np.uint32)[: (n + 31) // 32].copy()
+    soa_count = int(cnt.item())
+    # oracle on the very same bytes, every bit
+    o = O.Matcher(O.REGEX_SET, PATS, False, True)
+    ho = np.arange(n + 1, dtype=np.uint64) * RL
+    f1 = o.match_soa(host_bases[0], ho, threads=32)[1] != 0
+    f2 = o.match_soa(host_bases[1], ho, threads=32)[1] != 0
+    exp = f1 | f2
+    got = np.unpackbits(soa_mask.view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert (got == exp).all() and soa_count == int(exp.sum())
+    del host_bases
+    # path 2: fused FASTQ kernel on HBM-resident bytes; path 3: host streaming pipeline (pinned FASTQ)
+    q1, q2 = _gen(torch, n, 1, 99, 1), _gen(torch, n, 2, 98, 1)
+    nbytes = n * (2 * RL + 17)
+    dm = torch.zeros(words, dtype=torch.int32, device=dev)
+    res = _ffi.Result()
+    rc = L.fqg_grep_fastq_device(ctx, m._h, F.PAIRED, q1.data_ptr(), nbytes, q2.data_ptr(), nbytes, dm.data_ptr(), words, C.byref(res), sp)
+    assert rc == 0, _ffi.last_error()
+    assert res.n_units == n and res.n_selected == soa_count
+    assert (dm.cpu().numpy().view(np.uint32)[: (n + 31) // 32] == soa_mask).all()
+    h1, h2 = q1[:nbytes].cpu().numpy(), q2[:nbytes].cpu().numpy()
+    del q1, q2
+    r = m.grep_fastq(h1, h2, mode=F.PAIRED)
+    assert r["count"] == soa_count and (r["mask_words"][: (n + 31) // 32] == soa_mask).all()
+    # idempotence: a second pass over the selected records selects all of them
+    sel = F.write_selected(r["mask_words"], h1[: 317 * 200_000], h2[: 317 * 200_000], mode=F.PAIRED)
+    il = np.frombuffer(sel, dtype=np.uint8)
+    again = m.grep_fastq(il, mode=F.INTERLEAVED)
+    assert again["count"] == again["units"] == int(exp[:200_000].sum())
