@@ -16,6 +16,8 @@
 // the four line ends come from the bitmap, the sequence line is walked through the DFA straight out of
 // shared memory, and the selection bit is OR-ed into the global record bitmask.  Records that do not end
 // inside tile+overlap (reads longer than ~1 kb) fall back to a global-memory walk.
+#include <cstdlib>
+
 #include "dfa_device.cuh"
 #include "kernels.hpp"
 #include "names_hash.h"
@@ -155,6 +157,223 @@ struct RecordEval {
     }
 };
 
+// ---- the phases of one tile, shared by the two kernel shapes below ---------------------------------------------------
+
+struct TileGeom {
+    uint32_t t;            // global tile id
+    uint64_t T0;           // stream offset of the tile
+    uint32_t avail;        // stream positions visible in shared memory (tile + overlap)
+    uint32_t region;       // stream positions this tile owns
+    uint32_t real_avail;   // real bytes among `avail` (the rest is the virtual final newline)
+};
+__device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, uint64_t stream_len) {
+    TileGeom g;
+    g.t = t;
+    g.T0 = (uint64_t)t * kTile;
+    const uint64_t remaining = stream_len - g.T0;
+    g.avail = remaining < kLoad ? (uint32_t)remaining : kLoad;
+    g.region = remaining < kTile ? (uint32_t)remaining : kTile;
+    const uint64_t real_left = a.nbytes > g.T0 ? a.nbytes - g.T0 : 0;
+    g.real_avail = real_left < kLoad ? (uint32_t)real_left : kLoad;
+    return g;
+}
+
+// newline bitmap: one word per 32 bytes, built by `nthreads` cooperating threads
+__device__ __forceinline__ void build_bitmap(uint32_t tile_sa, uint32_t* s_bitmap, const TileGeom& g, uint32_t rtid, uint32_t nthreads) {
+    for (uint32_t grp32 = rtid; grp32 < kGroups + 2; grp32 += nthreads) {
+        uint32_t bits = 0;
+        if (grp32 * 32u < g.real_avail) {
+            const uint4 lo = lds_v4_volatile(tile_sa + grp32 * 32u), hi = lds_v4_volatile(tile_sa + grp32 * 32u + 16u);
+            bits = newline_nibble(lo.x) | (newline_nibble(lo.y) << 4) | (newline_nibble(lo.z) << 8) | (newline_nibble(lo.w) << 12) |
+                   (newline_nibble(hi.x) << 16) | (newline_nibble(hi.y) << 20) | (newline_nibble(hi.z) << 24) | (newline_nibble(hi.w) << 28);
+            if (grp32 * 32u + 32u > g.real_avail) bits &= (1u << (g.real_avail - grp32 * 32u)) - 1u;
+        }
+        if (g.real_avail < g.avail && (g.real_avail >> 5) == grp32) bits |= 1u << (g.real_avail & 31u);   // the virtual final newline
+        s_bitmap[grp32] = bits;
+    }
+}
+
+// exclusive prefix of newline counts per 32-byte group (thread i owns groups [i*GPT, (i+1)*GPT)); `sync` is the team barrier
+template <uint32_t NTHREADS, typename Sync>
+__device__ __forceinline__ void prefix_counts(const uint32_t* s_bitmap, uint16_t* s_pre, uint32_t* s_wsum, uint32_t rtid, Sync sync) {
+    constexpr uint32_t GPT = (kGroups + NTHREADS - 1) / NTHREADS, NW = NTHREADS / 32;
+    const uint32_t lane = rtid & 31u, warp = rtid >> 5;
+    uint32_t cnt[GPT], mine = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < GPT; k++) {
+        const uint32_t grp32 = rtid * GPT + k;
+        cnt[k] = grp32 < kGroups ? __popc(s_bitmap[grp32]) : 0u;
+        mine += cnt[k];
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    sync();
+    uint32_t warp_base = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < NW; w++) if (w < warp) warp_base += s_wsum[w];
+    uint32_t run = warp_base + incl - mine;
+#pragma unroll
+    for (uint32_t k = 0; k < GPT; k++) {
+        const uint32_t grp32 = rtid * GPT + k;
+        if (grp32 <= kGroups) s_pre[grp32] = (uint16_t)run;
+        run += cnt[k];
+    }
+    sync();
+}
+__device__ __forceinline__ uint32_t region_newlines(const uint32_t* s_bitmap, const uint16_t* s_pre, uint32_t region) {
+    return (region & 31u) == 0 ? s_pre[region >> 5] : s_pre[region >> 5] + __popc(s_bitmap[region >> 5]);
+}
+
+// decoupled look-back by one warp: number of newlines before tile t; publishes this tile's aggregate / inclusive prefix
+__device__ __forceinline__ unsigned long long lookback(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
+    unsigned long long excl = 0;
+    if (t > 0) {
+        if (lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
+        int32_t look = (int32_t)t - 1;
+        for (;;) {
+            const int32_t idx = look - (int32_t)lane;
+            unsigned long long st = (2ull << 62);   // before the stream: prefix 0
+            if (idx >= 0) {
+                do { st = *reinterpret_cast<volatile unsigned long long*>(a.tile_state + idx); } while ((st >> 62) == 0);
+            }
+            const uint32_t has_prefix = __ballot_sync(kFullMask, (st >> 62) == 2);
+            const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
+            unsigned long long v = lane <= first ? (st & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+            excl += v;
+            if (has_prefix) break;
+            look -= 32;
+        }
+    }
+    if (lane == 0) atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
+    return excl;
+}
+
+// one thread per record that starts in the tile; `rwarp`/`nthreads` describe the team of warps that shares the records
+template <int TIER>
+__device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, const RecordEval<TIER>& ev, uint32_t tile_sa, const uint32_t* s_bitmap,
+                                                            const uint16_t* s_pre, const TileGeom& g, unsigned long long Lt, uint32_t agg,
+                                                            uint64_t stream_len, uint32_t rwarp, uint32_t lane, uint32_t nthreads) {
+    const bool want_idh = a.id_hash != nullptr;
+    unsigned long long local_count = 0;
+    // record k begins right after the newline of local rank j0 + 4 (k - extra)
+    const bool first_global = g.t == 0;
+    const uint32_t extra = first_global ? 1u : 0u;
+    const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
+    const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
+    uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
+    if (g.T0 + g.region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
+    // position of the newline with local rank r (< agg): binary search in the per-group prefix counts, then bit select
+    const uint32_t n_groups_region = (g.region + 31u) >> 5;
+    auto newline_of_rank = [&](uint32_t r) -> uint32_t {
+        uint32_t lo = 0, hi = n_groups_region;             // s_pre[lo] <= r < s_pre[hi]
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_pre[mid] <= r) lo = mid; else hi = mid;
+        }
+        uint32_t bits = s_bitmap[lo];
+        for (uint32_t n = r - s_pre[lo]; n; n--) bits &= bits - 1u;
+        return lo * 32u + (uint32_t)__ffs(bits) - 1u;
+    };
+    const uint32_t n_groups_avail = (g.avail + 31u) >> 5;
+    auto next_nl = [&](uint32_t p) -> uint32_t {
+        uint32_t grp32 = p >> 5;
+        if (grp32 >= n_groups_avail) return kNone;
+        uint32_t w = s_bitmap[grp32] & (0xFFFFFFFFu << (p & 31u));
+        while (!w) {
+            if (++grp32 >= n_groups_avail) return kNone;
+            w = s_bitmap[grp32];
+        }
+        return grp32 * 32u + (uint32_t)__ffs(w) - 1u;
+    };
+    const uint64_t T0 = g.T0;
+    for (uint32_t k0 = rwarp * 32u; k0 < n_list; k0 += nthreads) {
+        const uint32_t k = k0 + lane;
+        const bool valid = k < n_list;
+        bool sel = false;
+        uint32_t idh = 0;
+        if (valid) {
+            const uint32_t s = k < extra ? 0u : newline_of_rank(j0 + 4u * (k - extra)) + 1u;
+            const uint32_t p0 = next_nl(s);
+            const uint32_t p1 = p0 == kNone ? kNone : next_nl(p0 + 1u);
+            const uint32_t p2 = p1 == kNone ? kNone : next_nl(p1 + 1u);
+            const uint32_t p3 = p2 == kNone ? kNone : next_nl(p2 + 1u);
+            if (p3 != kNone) {
+                const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
+                const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
+                const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
+                if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
+                else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
+                else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
+                sel = ev.eval_shared(tile_sa, s, p0, p1, seq_len, &idh, want_idh);
+            } else {
+                // record runs past tile+overlap (or the stream is truncated): walk it in global memory
+                const uint8_t* base = a.buf;
+                const uint64_t gs = T0 + s;
+                uint64_t q[4];
+                uint64_t p = gs;
+                int found = 0;
+                for (; found < 4 && p < stream_len; p++)
+                    if (p == a.nbytes || base[p] == '\n') q[found++] = p;
+                if (found < 4) report(a, gs, kErrUnexpectedEnd);
+                else {
+                    const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
+                    const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
+                    const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
+                    const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
+                    if (base[gs] != '@') report(a, gs, kErrInvalidStart);
+                    else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
+                    else if (seq_len != qual_len) report(a, gs, kErrUnequal);
+                    sel = ev.eval_global(base + gs + 1, (uint32_t)(q[0] - gs - 1 - cr0), base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
+                }
+            }
+        }
+        const unsigned long long R_w = R_base + k0;      // record number of lane 0
+        if (valid) {
+            if (R_base + k >= a.mask_bits || (want_idh && R_base + k >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
+            else if (want_idh) a.id_hash[R_base + k] = idh;
+        }
+        const uint32_t m = __ballot_sync(kFullMask, sel);
+        if (lane == 0 && m) {
+            const uint32_t sh = (uint32_t)(R_w & 31ull);
+            atomicOr(a.mask + (R_w >> 5), m << sh);
+            if (sh && (m >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, m >> (32u - sh));
+            local_count += __popc(m);
+        }
+    }
+    return local_count;
+}
+
+template <int TIER>
+__device__ __forceinline__ RecordEval<TIER> make_eval(const FastqArgs& a, const DeviceDfa& dfa, uint8_t* s_tab, uint8_t* s_cls) {
+    RecordEval<TIER> ev;
+    ev.view.tab = smem_addr(s_tab);
+    ev.view.t32 = reinterpret_cast<const uint32_t*>(dfa.table);
+    ev.view.cls = smem_addr(s_cls);
+    ev.view.hot_limit = TIER == 2 ? dfa.hot_entries : 0u;
+    ev.names.nv = a.names;
+    const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in the smem-table tiers
+    ev.start = dfa.start + reloc;
+    ev.accept_from = dfa.accept_from + reloc;
+    ev.invert = a.invert != 0;
+    return ev;
+}
+template <int TIER>
+__device__ __forceinline__ void stage_automaton(const DeviceDfa& dfa, uint8_t* s_tab, uint8_t* s_cls) {
+    if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
+    if (TIER == 2)
+        for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
+    if (TIER != 3)
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
+}
+
+// ---- kernel shape 1: symmetric tile groups -----------------------------------------------------------------------------
 // per-group shared memory: [mbarrier 8][prefix 8][misc 240][tile kLoad+32][bitmap][pre], 128-byte aligned
 constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u) + 127u) & ~127u;
 
@@ -164,8 +383,6 @@ constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + 
 template <int TIER, int THREADS>
 __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t kWarps = THREADS / 32;
-    constexpr uint32_t kGpt = (kGroups + THREADS - 1) / THREADS;   // contiguous groups per thread in the prefix pass
     const uint32_t grp = threadIdx.x / THREADS, tid = threadIdx.x % THREADS, lane = tid & 31u, warp = tid >> 5;
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1u), "n"(THREADS) : "memory"); };
 
@@ -175,32 +392,17 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
     uint8_t* s_grp = s_cls + 256 + (size_t)grp * kGroupBytes;                // this group's private region (128-byte aligned)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp);
     unsigned long long* s_prefix = reinterpret_cast<unsigned long long*>(s_bar + 1);
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2);               // warp sums [kWarps], [40] = tile id
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2);               // warp sums, [40] = tile id
     uint8_t* s_tile = s_grp + 256;                                           // kLoad + 32, 128-byte aligned for the bulk copy
     uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);   // kGroups + 2
     uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
 
-    if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
-    if (TIER == 2)
-        for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
-    if (TIER != 3)
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
+    stage_automaton<TIER>(dfa, s_tab, s_cls);
     if (tid == 0) mbar_init(smem_addr(s_bar), 1);
     mbar_fence_init();
     __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
 
-    RecordEval<TIER> ev;
-    ev.view.tab = smem_addr(s_tab);
-    ev.view.t32 = reinterpret_cast<const uint32_t*>(dfa.table);
-    ev.view.cls = smem_addr(s_cls);
-    ev.view.hot_limit = TIER == 2 ? dfa.hot_entries : 0u;
-    ev.names.nv = a.names;
-    const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
-    ev.start = dfa.start + reloc;
-    ev.accept_from = dfa.accept_from + reloc;
-    ev.invert = a.invert != 0;
-    const bool want_idh = a.id_hash != nullptr;
-
+    const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
     const uint32_t tile_sa = smem_addr(s_tile), bar = smem_addr(s_bar);
     // the stream always ends with a newline: a real one, or a virtual one at offset nbytes (missing final '\n')
     const uint64_t stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
@@ -211,189 +413,142 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
         if (tid == 0) s_misc[40] = atomicAdd(a.tile_counter, 1u);
         group_sync();
         if (s_misc[40] >= a.tile_count) break;
-        const uint32_t t = a.tile_first + s_misc[40];                               // global tile id
-        const uint64_t T0 = (uint64_t)t * kTile;
-        const uint64_t remaining = stream_len - T0;
-        const uint32_t avail = remaining < kLoad ? (uint32_t)remaining : kLoad;      // stream positions visible in smem
-        const uint32_t region = remaining < kTile ? (uint32_t)remaining : kTile;    // stream positions this tile owns
-        const uint64_t real_left = a.nbytes > T0 ? a.nbytes - T0 : 0;
-        const uint32_t real_avail = real_left < kLoad ? (uint32_t)real_left : kLoad;  // real bytes among them
-        if (real_avail) {
+        const TileGeom g = tile_geom(a, a.tile_first + s_misc[40], stream_len);
+        if (g.real_avail) {
             if (tid == 0) {
-                const uint32_t bytes = (real_avail + 15u) & ~15u;
+                const uint32_t bytes = (g.real_avail + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
-                bulk_copy_g2s(tile_sa, a.buf + T0, bytes, bar);
+                bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
+                // one thread polls the transaction barrier; the rest of the group sleeps on the (hardware) named barrier
+                // instead of spinning on try_wait and stealing issue slots from the other groups of the SM
+                mbar_wait(bar, phase);
             }
-            // one thread polls the transaction barrier; the rest of the group sleeps on the (hardware) named barrier
-            // instead of spinning on try_wait and stealing issue slots from the other groups of the SM
-            if (tid == 0) mbar_wait(bar, phase);
             phase ^= 1u;
             group_sync();
         }
-
-        // ---- newline bitmap: one word per 32 bytes
-        for (uint32_t g = tid; g < kGroups + 2; g += THREADS) {
-            uint32_t bits = 0;
-            if (g * 32u < real_avail) {
-                const uint4 lo = lds_v4_volatile(tile_sa + g * 32u), hi = lds_v4_volatile(tile_sa + g * 32u + 16u);
-                bits = newline_nibble(lo.x) | (newline_nibble(lo.y) << 4) | (newline_nibble(lo.z) << 8) | (newline_nibble(lo.w) << 12) |
-                       (newline_nibble(hi.x) << 16) | (newline_nibble(hi.y) << 20) | (newline_nibble(hi.z) << 24) | (newline_nibble(hi.w) << 28);
-                if (g * 32u + 32u > real_avail) bits &= (1u << (real_avail - g * 32u)) - 1u;
-            }
-            if (real_avail < avail && (real_avail >> 5) == g) bits |= 1u << (real_avail & 31u);   // the virtual final newline
-            s_bitmap[g] = bits;
-        }
+        build_bitmap(tile_sa, s_bitmap, g, tid, THREADS);
         group_sync();
-
-        // ---- exclusive prefix of newline counts per group (block scan; thread i owns groups [i*kGpt, (i+1)*kGpt))
-        uint32_t cnt[kGpt], mine = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < kGpt; k++) {
-            const uint32_t g = tid * kGpt + k;
-            cnt[k] = g < kGroups ? __popc(s_bitmap[g]) : 0u;
-            mine += cnt[k];
-        }
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
-        }
-        if (lane == 31) s_misc[warp] = incl;
-        group_sync();
-        uint32_t warp_base = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < kWarps; w++) if (w < warp) warp_base += s_misc[w];
-        uint32_t run = warp_base + incl - mine;
-#pragma unroll
-        for (uint32_t k = 0; k < kGpt; k++) {
-            const uint32_t g = tid * kGpt + k;
-            if (g <= kGroups) s_pre[g] = (uint16_t)run;
-            run += cnt[k];
-        }
-        group_sync();
-        const uint32_t agg = (region & 31u) == 0 ? s_pre[region >> 5] : s_pre[region >> 5] + __popc(s_bitmap[region >> 5]);   // newlines in [0, region)
-
-        // ---- decoupled look-back: newlines before this tile (within the launch)
+        prefix_counts<THREADS>(s_bitmap, s_pre, s_misc, tid, group_sync);
+        const uint32_t agg = region_newlines(s_bitmap, s_pre, g.region);
         if (warp == 0) {
-            unsigned long long excl = 0;
-            if (t > 0) {
-                if (lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
-                int32_t look = (int32_t)t - 1;
-                for (;;) {
-                    const int32_t idx = look - (int32_t)lane;
-                    unsigned long long st = (2ull << 62);   // before the stream: prefix 0
-                    if (idx >= 0) {
-                        do { st = *reinterpret_cast<volatile unsigned long long*>(a.tile_state + idx); } while ((st >> 62) == 0);
-                    }
-                    const uint32_t has_prefix = __ballot_sync(kFullMask, (st >> 62) == 2);
-                    const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
-                    unsigned long long v = lane <= first ? (st & ((1ull << 62) - 1)) : 0ull;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
-                    excl += v;
-                    if (has_prefix) break;
-                    look -= 32;
-                }
-            }
+            const unsigned long long excl = lookback(a, g.t, agg, lane);
             if (lane == 0) {
-                atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
                 *s_prefix = excl;
-                if (T0 + region == stream_len) *a.lines_out = excl + agg;
+                if (g.T0 + g.region == stream_len) *a.lines_out = excl + agg;
             }
         }
         group_sync();
-        const unsigned long long Lt = *s_prefix;    // global index of this tile's first newline
-
-        // ---- records that start in this tile: record k begins right after the newline of local rank j0 + 4 (k - extra)
-        const bool first_global = t == 0;
-        const uint32_t extra = first_global ? 1u : 0u;
-        const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
-        const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
-        uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
-        if (T0 + region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
-        // position of the newline with local rank r (< agg): binary search in the per-group prefix counts, then bit select
-        const uint32_t n_groups_region = (region + 31u) >> 5;
-        auto newline_of_rank = [&](uint32_t r) -> uint32_t {
-            uint32_t lo = 0, hi = n_groups_region;             // s_pre[lo] <= r < s_pre[hi]
-            while (hi - lo > 1u) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_pre[mid] <= r) lo = mid; else hi = mid;
-            }
-            uint32_t bits = s_bitmap[lo];
-            for (uint32_t n = r - s_pre[lo]; n; n--) bits &= bits - 1u;
-            return lo * 32u + (uint32_t)__ffs(bits) - 1u;
-        };
-
-        // ---- one thread per record
-        const uint32_t n_groups_avail = (avail + 31u) >> 5;
-        auto next_nl = [&](uint32_t p) -> uint32_t {
-            uint32_t g = p >> 5;
-            if (g >= n_groups_avail) return kNone;
-            uint32_t w = s_bitmap[g] & (0xFFFFFFFFu << (p & 31u));
-            while (!w) {
-                if (++g >= n_groups_avail) return kNone;
-                w = s_bitmap[g];
-            }
-            return g * 32u + (uint32_t)__ffs(w) - 1u;
-        };
-        for (uint32_t k0 = warp * 32u; k0 < n_list; k0 += THREADS) {
-            const uint32_t k = k0 + lane;
-            const bool valid = k < n_list;
-            bool sel = false;
-            uint32_t idh = 0;
-            if (valid) {
-                const uint32_t s = k < extra ? 0u : newline_of_rank(j0 + 4u * (k - extra)) + 1u;
-                const uint32_t p0 = next_nl(s);
-                const uint32_t p1 = p0 == kNone ? kNone : next_nl(p0 + 1u);
-                const uint32_t p2 = p1 == kNone ? kNone : next_nl(p1 + 1u);
-                const uint32_t p3 = p2 == kNone ? kNone : next_nl(p2 + 1u);
-                if (p3 != kNone) {
-                    const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
-                    const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
-                    const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
-                    if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
-                    else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
-                    else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
-                    sel = ev.eval_shared(tile_sa, s, p0, p1, seq_len, &idh, want_idh);
-                } else {
-                    // record runs past tile+overlap (or the stream is truncated): walk it in global memory
-                    const uint8_t* base = a.buf;
-                    const uint64_t gs = T0 + s;
-                    uint64_t q[4];
-                    uint64_t p = gs;
-                    int found = 0;
-                    for (; found < 4 && p < stream_len; p++)
-                        if (p == a.nbytes || base[p] == '\n') q[found++] = p;
-                    if (found < 4) report(a, gs, kErrUnexpectedEnd);
-                    else {
-                        const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
-                        const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
-                        const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
-                        const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
-                        if (base[gs] != '@') report(a, gs, kErrInvalidStart);
-                        else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
-                        else if (seq_len != qual_len) report(a, gs, kErrUnequal);
-                        sel = ev.eval_global(base + gs + 1, (uint32_t)(q[0] - gs - 1 - cr0), base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
-                    }
-                }
-            }
-            const unsigned long long R_w = R_base + k0;      // record number of lane 0
-            if (valid) {
-                if (R_base + k >= a.mask_bits || (want_idh && R_base + k >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
-                else if (want_idh) a.id_hash[R_base + k] = idh;
-            }
-            const uint32_t m = __ballot_sync(kFullMask, sel);
-            if (lane == 0 && m) {
-                const uint32_t sh = (uint32_t)(R_w & 31ull);
-                atomicOr(a.mask + (R_w >> 5), m << sh);
-                if (sh && (m >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, m >> (32u - sh));
-                local_count += __popc(m);
-            }
-        }
-        group_sync();   // tile, bitmap and list are free for the next iteration
+        local_count += match_records<TIER>(a, ev, tile_sa, s_bitmap, s_pre, g, *s_prefix, agg, stream_len, warp, lane, THREADS);
+        group_sync();   // tile and bitmap are free for the next iteration
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
+}
+
+// ---- kernel shape 2: warp-specialised groups (2 scanner warps + 2 matcher warps, two tile buffers) ---------------------
+// While the matcher warps walk the records of tile j, the scanner warps already copy, scan and look back tile j+1 into
+// the other buffer, so the copy latency, the newline scan and the look-back of one tile hide behind the record phase of
+// the previous one and all four warps of a group stay busy.  Hand-over is by mbarriers (ready[b]: scanner -> matcher,
+// empty[b]: matcher -> scanner); each team synchronises internally on its own named barrier.
+constexpr uint32_t kBufBytes = (((kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u) + 127u) & ~127u;
+constexpr uint32_t kWsGroupBytes = 256u + 2u * kBufBytes;
+struct TileMeta {
+    unsigned long long Lt;     // newlines before the tile
+    uint32_t tile;             // global tile id, 0xFFFFFFFF = no more tiles
+    uint32_t agg;              // newlines in the tile's region
+};
+
+template <int TIER>
+__global__ void __launch_bounds__(512, 1) match_fastq_ws_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t TEAM = 64;
+    const uint32_t grp = threadIdx.x >> 7, tid = threadIdx.x & 127u;
+    const bool is_scanner = tid < TEAM;
+    const uint32_t rtid = tid & (TEAM - 1u), lane = rtid & 31u, rwarp = rtid >> 5;
+    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1u + 2u * grp + (is_scanner ? 0u : 1u)), "n"(TEAM) : "memory"); };
+
+    uint8_t* s_tab = smem;
+    uint8_t* s_cls = smem + table_smem_bytes;
+    uint8_t* s_grp = s_cls + 256 + (size_t)grp * kWsGroupBytes;
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_grp);            // [2] bulk-copy completion
+    uint64_t* s_ready = s_full + 2;                                   // [2] scanner -> matcher
+    uint64_t* s_empty = s_full + 4;                                   // [2] matcher -> scanner
+    TileMeta* s_meta = reinterpret_cast<TileMeta*>(s_full + 6);       // [2]
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_meta + 2);       // scanner warp sums [2], [8] = tile id
+    uint8_t* s_buf0 = s_grp + 256;
+
+    stage_automaton<TIER>(dfa, s_tab, s_cls);
+    if (tid == 0)
+        for (int i = 0; i < 6; i++) mbar_init(smem_addr(s_full + i), 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    const uint64_t stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
+    if (is_scanner) {
+        for (uint32_t it = 0;; it++) {
+            const uint32_t b = it & 1u, use = it >> 1;
+            uint8_t* buf = s_buf0 + (size_t)b * kBufBytes;
+            const uint32_t tile_sa = smem_addr(buf);
+            uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(buf + kLoad + 32);
+            uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);
+            if (rtid == 0) {
+                if (use) mbar_wait(smem_addr(s_empty + b), (use - 1u) & 1u);     // the matchers are done with this buffer
+                s_misc[8] = atomicAdd(a.tile_counter, 1u);                       // take a tile only once there is room for it
+            }
+            team_sync();
+            const uint32_t tl = s_misc[8];
+            if (tl >= a.tile_count) {
+                if (rtid == 0) { s_meta[b].tile = 0xFFFFFFFFu; mbar_arrive(smem_addr(s_ready + b)); }
+                break;
+            }
+            const TileGeom g = tile_geom(a, a.tile_first + tl, stream_len);
+            if (rtid == 0) {
+                const uint32_t fbar = smem_addr(s_full + b);
+                if (g.real_avail) {
+                    const uint32_t bytes = (g.real_avail + 15u) & ~15u;
+                    mbar_arrive_expect_tx(fbar, bytes);
+                    bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, fbar);
+                } else mbar_arrive(fbar);
+                mbar_wait(fbar, use & 1u);
+            }
+            team_sync();
+            build_bitmap(tile_sa, s_bitmap, g, rtid, TEAM);
+            team_sync();
+            prefix_counts<TEAM>(s_bitmap, s_pre, s_misc, rtid, team_sync);
+            const uint32_t agg = region_newlines(s_bitmap, s_pre, g.region);
+            if (rwarp == 0) {
+                const unsigned long long excl = lookback(a, g.t, agg, lane);
+                if (lane == 0) {
+                    s_meta[b].Lt = excl;
+                    s_meta[b].tile = g.t;
+                    s_meta[b].agg = agg;
+                    if (g.T0 + g.region == stream_len) *a.lines_out = excl + agg;
+                }
+            }
+            team_sync();                                                        // bitmap, prefix counts and meta are written
+            if (rtid == 0) mbar_arrive(smem_addr(s_ready + b));
+        }
+    } else {
+        const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
+        unsigned long long local_count = 0;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t b = it & 1u, use = it >> 1;
+            uint8_t* buf = s_buf0 + (size_t)b * kBufBytes;
+            const uint32_t* s_bitmap = reinterpret_cast<const uint32_t*>(buf + kLoad + 32);
+            const uint16_t* s_pre = reinterpret_cast<const uint16_t*>(s_bitmap + kGroups + 2);
+            if (rtid == 0) {
+                mbar_wait(smem_addr(s_ready + b), use & 1u);
+                if (s_meta[b].tile != 0xFFFFFFFFu) mbar_wait(smem_addr(s_full + b), use & 1u);   // (already complete) observe the bulk copy too
+            }
+            team_sync();
+            const TileMeta meta = s_meta[b];
+            if (meta.tile == 0xFFFFFFFFu) break;
+            const TileGeom g = tile_geom(a, meta.tile, stream_len);
+            local_count += match_records<TIER>(a, ev, smem_addr(buf), s_bitmap, s_pre, g, meta.Lt, meta.agg, stream_len, rwarp, lane, TEAM);
+            team_sync();                                                        // every matcher lane is done with the buffer
+            if (rtid == 0) mbar_arrive(smem_addr(s_empty + b));
+        }
+        if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
+    }
 }
 
 // pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747).
@@ -451,9 +606,29 @@ __global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uin
 
 template <int TIER>
 cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
-    constexpr int THREADS = 128;
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
+    static const int use_ws = [] { const char* e = std::getenv("FQG_FASTQ_WS"); return e ? std::atoi(e) : 0; }();
+    if (use_ws) {
+        uint32_t groups = (budget - table_smem - 256u - 128u) / kWsGroupBytes;
+        if (groups > 4u) groups = 4u;
+        if (groups >= 1u) {
+            if (a.tile_count < (uint32_t)sm_count * groups) {
+                groups = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
+                if (groups < 1u) groups = 1u;
+            }
+            const uint32_t smem = table_smem + 256u + groups * kWsGroupBytes + 128u;
+            auto kern = match_fastq_ws_kernel<TIER>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            uint32_t grid = (a.tile_count + groups - 1u) / groups;
+            if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
+            if (grid == 0) return cudaSuccess;
+            kern<<<grid, groups * 128u, smem, stream>>>(a, dfa, table_smem);
+            return cudaGetLastError();
+        }
+    }
+    constexpr int THREADS = 128;
     uint32_t groups = (budget - table_smem - 256u - 128u) / kGroupBytes;
     if (groups > 8u) groups = 8u;
     if (groups < 1u) groups = 1u;
