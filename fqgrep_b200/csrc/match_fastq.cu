@@ -16,8 +16,6 @@
 // the four line ends come from the bitmap, the sequence line is walked through the DFA straight out of
 // shared memory, and the selection bit is OR-ed into the global record bitmask.  Records that do not end
 // inside tile+overlap (reads longer than ~1 kb) fall back to a global-memory walk.
-#include <cstdlib>
-
 #include "dfa_device.cuh"
 #include "kernels.hpp"
 #include "names_hash.h"
@@ -373,7 +371,10 @@ __device__ __forceinline__ void stage_automaton(const DeviceDfa& dfa, uint8_t* s
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
 }
 
-// ---- kernel shape 1: symmetric tile groups -----------------------------------------------------------------------------
+// ---- the kernel: symmetric tile groups ----------------------------------------------------------------------------------
+// (A warp-specialised shape -- 2 scanner + 2 matcher warps per group over two tile buffers -- was built and measured this
+// round: same results, 0.95x on the DFA path and 0.83x on -N, because two buffers per group halve the groups an SM can hold
+// and the 16 remaining warps hide less latency than the overlap wins.  It was removed; see DESIGN.md.)
 // per-group shared memory: [mbarrier 8][prefix 8][misc 240][tile kLoad+32][bitmap][pre], 128-byte aligned
 constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u) + 127u) & ~127u;
 
@@ -444,113 +445,6 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
 
-// ---- kernel shape 2: warp-specialised groups (2 scanner warps + 2 matcher warps, two tile buffers) ---------------------
-// While the matcher warps walk the records of tile j, the scanner warps already copy, scan and look back tile j+1 into
-// the other buffer, so the copy latency, the newline scan and the look-back of one tile hide behind the record phase of
-// the previous one and all four warps of a group stay busy.  Hand-over is by mbarriers (ready[b]: scanner -> matcher,
-// empty[b]: matcher -> scanner); each team synchronises internally on its own named barrier.
-constexpr uint32_t kBufBytes = (((kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u) + 127u) & ~127u;
-constexpr uint32_t kWsGroupBytes = 256u + 2u * kBufBytes;
-struct TileMeta {
-    unsigned long long Lt;     // newlines before the tile
-    uint32_t tile;             // global tile id, 0xFFFFFFFF = no more tiles
-    uint32_t agg;              // newlines in the tile's region
-};
-
-template <int TIER>
-__global__ void __launch_bounds__(512, 1) match_fastq_ws_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t TEAM = 64;
-    const uint32_t grp = threadIdx.x >> 7, tid = threadIdx.x & 127u;
-    const bool is_scanner = tid < TEAM;
-    const uint32_t rtid = tid & (TEAM - 1u), lane = rtid & 31u, rwarp = rtid >> 5;
-    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1u + 2u * grp + (is_scanner ? 0u : 1u)), "n"(TEAM) : "memory"); };
-
-    uint8_t* s_tab = smem;
-    uint8_t* s_cls = smem + table_smem_bytes;
-    uint8_t* s_grp = s_cls + 256 + (size_t)grp * kWsGroupBytes;
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_grp);            // [2] bulk-copy completion
-    uint64_t* s_ready = s_full + 2;                                   // [2] scanner -> matcher
-    uint64_t* s_empty = s_full + 4;                                   // [2] matcher -> scanner
-    TileMeta* s_meta = reinterpret_cast<TileMeta*>(s_full + 6);       // [2]
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_meta + 2);       // scanner warp sums [2], [8] = tile id
-    uint8_t* s_buf0 = s_grp + 256;
-
-    stage_automaton<TIER>(dfa, s_tab, s_cls);
-    if (tid == 0)
-        for (int i = 0; i < 6; i++) mbar_init(smem_addr(s_full + i), 1);
-    mbar_fence_init();
-    __syncthreads();
-
-    const uint64_t stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
-    if (is_scanner) {
-        for (uint32_t it = 0;; it++) {
-            const uint32_t b = it & 1u, use = it >> 1;
-            uint8_t* buf = s_buf0 + (size_t)b * kBufBytes;
-            const uint32_t tile_sa = smem_addr(buf);
-            uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(buf + kLoad + 32);
-            uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);
-            if (rtid == 0) {
-                if (use) mbar_wait(smem_addr(s_empty + b), (use - 1u) & 1u);     // the matchers are done with this buffer
-                s_misc[8] = atomicAdd(a.tile_counter, 1u);                       // take a tile only once there is room for it
-            }
-            team_sync();
-            const uint32_t tl = s_misc[8];
-            if (tl >= a.tile_count) {
-                if (rtid == 0) { s_meta[b].tile = 0xFFFFFFFFu; mbar_arrive(smem_addr(s_ready + b)); }
-                break;
-            }
-            const TileGeom g = tile_geom(a, a.tile_first + tl, stream_len);
-            if (rtid == 0) {
-                const uint32_t fbar = smem_addr(s_full + b);
-                if (g.real_avail) {
-                    const uint32_t bytes = (g.real_avail + 15u) & ~15u;
-                    mbar_arrive_expect_tx(fbar, bytes);
-                    bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, fbar);
-                } else mbar_arrive(fbar);
-                mbar_wait(fbar, use & 1u);
-            }
-            team_sync();
-            build_bitmap(tile_sa, s_bitmap, g, rtid, TEAM);
-            team_sync();
-            prefix_counts<TEAM>(s_bitmap, s_pre, s_misc, rtid, team_sync);
-            const uint32_t agg = region_newlines(s_bitmap, s_pre, g.region);
-            if (rwarp == 0) {
-                const unsigned long long excl = lookback(a, g.t, agg, lane);
-                if (lane == 0) {
-                    s_meta[b].Lt = excl;
-                    s_meta[b].tile = g.t;
-                    s_meta[b].agg = agg;
-                    if (g.T0 + g.region == stream_len) *a.lines_out = excl + agg;
-                }
-            }
-            team_sync();                                                        // bitmap, prefix counts and meta are written
-            if (rtid == 0) mbar_arrive(smem_addr(s_ready + b));
-        }
-    } else {
-        const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
-        unsigned long long local_count = 0;
-        for (uint32_t it = 0;; it++) {
-            const uint32_t b = it & 1u, use = it >> 1;
-            uint8_t* buf = s_buf0 + (size_t)b * kBufBytes;
-            const uint32_t* s_bitmap = reinterpret_cast<const uint32_t*>(buf + kLoad + 32);
-            const uint16_t* s_pre = reinterpret_cast<const uint16_t*>(s_bitmap + kGroups + 2);
-            if (rtid == 0) {
-                mbar_wait(smem_addr(s_ready + b), use & 1u);
-                if (s_meta[b].tile != 0xFFFFFFFFu) mbar_wait(smem_addr(s_full + b), use & 1u);   // (already complete) observe the bulk copy too
-            }
-            team_sync();
-            const TileMeta meta = s_meta[b];
-            if (meta.tile == 0xFFFFFFFFu) break;
-            const TileGeom g = tile_geom(a, meta.tile, stream_len);
-            local_count += match_records<TIER>(a, ev, smem_addr(buf), s_bitmap, s_pre, g, meta.Lt, meta.agg, stream_len, rwarp, lane, TEAM);
-            team_sync();                                                        // every matcher lane is done with the buffer
-            if (rtid == 0) mbar_arrive(smem_addr(s_empty + b));
-        }
-        if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
-    }
-}
-
 // pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747).
 // Record counts are still on the device (written by the streams' last tiles), so they are read here.
 __global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
@@ -608,26 +502,6 @@ template <int TIER>
 cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
-    static const int use_ws = [] { const char* e = std::getenv("FQG_FASTQ_WS"); return e ? std::atoi(e) : 0; }();
-    if (use_ws) {
-        uint32_t groups = (budget - table_smem - 256u - 128u) / kWsGroupBytes;
-        if (groups > 4u) groups = 4u;
-        if (groups >= 1u) {
-            if (a.tile_count < (uint32_t)sm_count * groups) {
-                groups = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
-                if (groups < 1u) groups = 1u;
-            }
-            const uint32_t smem = table_smem + 256u + groups * kWsGroupBytes + 128u;
-            auto kern = match_fastq_ws_kernel<TIER>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            uint32_t grid = (a.tile_count + groups - 1u) / groups;
-            if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-            if (grid == 0) return cudaSuccess;
-            kern<<<grid, groups * 128u, smem, stream>>>(a, dfa, table_smem);
-            return cudaGetLastError();
-        }
-    }
     constexpr int THREADS = 128;
     uint32_t groups = (budget - table_smem - 256u - 128u) / kGroupBytes;
     if (groups > 8u) groups = 8u;
