@@ -7,3 +7,4 @@ from .matcher import (BITMASK, BITMASK_SET, FIXED, FIXED_SET, INTERLEAVED, NAMES
                       MatcherFactory, MatcherOpts, context, expand_iupac, expand_iupac_fixed_pattern, expand_iupac_regex, is_fastq_path, is_gzip_path, read_input,
                       validate_fixed_pattern,
                       write_selected)
+from .driver import Opts, fqgrep, fqgrep_from_opts, read_patterns, read_query_names  # noqa: E402,F401
