@@ -239,3 +239,34 @@ def test_device_resident_entry_with_pair_or_mask():
     got = np.unpackbits(mask2.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
     assert (got == (f1 | f2)).all()
     assert int(count.item()) == int((f1 | f2).sum())
+
+
+def test_fuzz_random_pattern_sets_on_ragged_mixed_alphabet_reads():
+    """Random regex / literal / bit-mask sets against reads with N, lowercase, protein letters and ragged lengths:
+    exercises the 4-base and 2-base table paths, their exact non-ACGT fallback, the tails and the class-indexed tiers."""
+    rng = random.Random(77)
+    seqs = []
+    for i in range(12000):
+        L = rng.choice([0, 1, 3, 4, 5, 8, 16, 31, 32, 33, 75, 150, 151, 152, 153, 301])
+        alpha = "ACGT" if i % 3 else rng.choice(["ACGTN", "ACGTacgt", "ACGTNRYKM", "ARNDCEQGHILKMFPSTWYV"])
+        seqs.append("".join(rng.choice(alpha) for _ in range(L)))
+    bases, offs = soa(seqs)
+    atoms = ["A", "C", "G", "T", "N", ".", "[AC]", "[^G]", "[ACGT]", "(A|T)", "(CG|GC)", "a", "[Nn]"]
+    quants = ["", "", "", "", "*", "+", "?", "{2}", "{1,3}"]
+    for trial in range(40):
+        kind = rng.choice([F.REGEX_SET, F.REGEX_SET, F.FIXED_SET, F.BITMASK_SET])
+        if kind == F.REGEX_SET:
+            pats = []
+            for _ in range(rng.randint(1, 12)):
+                body = "".join(rng.choice(atoms) + rng.choice(quants) for _ in range(rng.randint(2, 9)))
+                pats.append(rng.choice(["", "^", ""]) + body + rng.choice(["", "$", ""]))
+        elif kind == F.FIXED_SET:
+            pats = ["".join(rng.choice("ACGTN") for _ in range(rng.randint(1, 14))) for _ in range(rng.randint(1, 40))]
+        else:
+            pats = ["".join(rng.choice("ACGTRYKMSWN") for _ in range(rng.randint(2, 10))) for _ in range(rng.randint(2, 6))]
+        inv, rc = rng.random() < 0.3, rng.random() < 0.5
+        try:
+            O.Matcher(kind, pats, inv, rc)
+        except O.OracleError:
+            continue
+        check(kind, pats, inv, rc, bases, offs)
