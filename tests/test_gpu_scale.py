@@ -96,3 +96,38 @@ def test_four_million_pairs_three_paths_and_oracle_agree():
     il = np.frombuffer(sel, dtype=np.uint8)
     again = m.grep_fastq(il, mode=F.INTERLEAVED)
     assert again["count"] == again["units"] == int(exp[:200_000].sum())
+
+
+def test_host_soa_entry_chunks_above_one_gib():
+    """fqg_match_bases_host splits batches above 1 GiB of bases into several launches; masks must line up."""
+    import torch
+    n = 7_400_000                                   # 1.11 GB of bases -> two chunks
+    m = F.Matcher(F.FIXED, ["GACGAGATTA"], F.MatcherOpts(False, True))
+    tb = _gen(torch, n, 1, 99, 0)
+    offs32 = (torch.arange(n + 1, dtype=torch.int64, device=tb.device) * RL).to(torch.int32)
+    words = (n + 31) // 32 + 1
+    dmask = torch.zeros(words, dtype=torch.int32, device=tb.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=tb.device)
+    rc = _ffi.lib().fqg_match_bases_device(F.context(0), m._h, tb.data_ptr(), offs32.data_ptr(), offs32.data_ptr() + 4, n, dmask.data_ptr(), None,
+                                           cnt.data_ptr(), RL, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, _ffi.last_error()
+    torch.cuda.synchronize()
+    host = tb[: n * RL].cpu().numpy()
+    bits, count = m.match_bases(host, np.arange(n + 1, dtype=np.uint64) * RL)
+    exp = np.unpackbits(dmask.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert count == int(cnt.item()) and (bits == exp).all() and count > 0
+
+
+def test_paired_files_with_different_read_lengths_stream_in_step():
+    """R1 and R2 with the same record count but different byte sizes: the chunked host pipeline interleaves the two
+    copies without the mates drifting apart (PairedFastqReader's job, src/lib/seq_io.rs:149-198)."""
+    from tests import synth
+    n = 260_000
+    m1, m2 = synth.bases(n, 150, seed=1), synth.bases(n, 90, seed=2)
+    synth.plant(m1, PATS, rate=0.01, seed=99)
+    synth.plant(m2, PATS, rate=0.02, seed=98)
+    f1, f2 = synth.fastq(m1), synth.fastq(m2)      # 82 MB and 51 MB: different numbers of 64 MB copy chunks
+    m = F.MatcherFactory.new_matcher(None, False, PATS, None, F.MatcherOpts(True, True))
+    g = m.grep_fastq(f1, f2, mode=F.PAIRED)
+    e = O.Matcher(O.REGEX_SET, PATS, True, True).grep(f1, f2, mode=O.PAIRED, threads=16)
+    assert g["count"] == e["count"] and (g["mask"] == (e["flags"] != 0)).all()
