@@ -10,7 +10,7 @@ SYMBOLS = [
     "fqg_last_error", "fqg_version", "fqg_matcher_new", "fqg_matcher_free", "fqg_validate_fixed_pattern",
     "fqg_matcher_dfa_info", "fqg_matcher_dfa_export", "fqg_ctx_create", "fqg_ctx_destroy", "fqg_device_count",
     "fqg_alloc_pinned", "fqg_free_pinned", "fqg_match_bases_device", "fqg_match_bases_host",
-    "fqg_grep_fastq_host", "fqg_grep_fastq_device", "fqg_write_selected", "fqg_kernel_launches", "fqg_synth_reads_device", "fqg_fastq_split", "fqg_iupac_expand", "fqg_read_input", "fqg_free_input", "fqg_is_gzip_path", "fqg_is_fastq_path",
+    "fqg_grep_fastq_host", "fqg_grep_fastq_device", "fqg_write_selected", "fqg_kernel_launches", "fqg_synth_reads_device", "fqg_fastq_split", "fqg_iupac_expand", "fqg_read_input", "fqg_free_input", "fqg_index_fastq_device", "fqg_compact_bases_device", "fqg_is_gzip_path", "fqg_is_fastq_path",
 ]
 
 
@@ -55,6 +55,8 @@ def lib():
     L.fqg_write_selected.argtypes = [C.c_int, vp, sz, vp, sz, vp, vp, C.POINTER(sz), vp, C.POINTER(sz)]
     L.fqg_synth_reads_device.argtypes = [vp, vp, u64, u64, u32, C.c_int, u64, C.c_char_p, vp, u32, C.c_double, u64, vp]
     L.fqg_fastq_split.argtypes = [vp, sz, u32, vp]
+    L.fqg_index_fastq_device.argtypes = [vp, vp, sz, vp, vp, u64, C.POINTER(u64), vp]
+    L.fqg_compact_bases_device.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp]
     L.fqg_read_input.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.fqg_free_input.argtypes = [vp, C.c_int]
     L.fqg_is_gzip_path.argtypes = [C.c_char_p]

@@ -256,18 +256,25 @@ const char* fastq_err_name(unsigned code) {
     return "unknown";
 }
 
+struct IndexOut {                    // K0: optional per-record index of stream 1 (device arrays owned by the caller)
+    unsigned long long* seq_start = nullptr;
+    uint32_t* seq_len = nullptr;
+    uint64_t cap = 0;
+};
+
+// m == nullptr: index only (parse, validate, index; no matching)
 int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, bool on_device,
                     uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res, cudaStream_t user_stream, unsigned min_record_bytes,
-                    bool* capacity_hit) {
+                    bool* capacity_hit, const IndexOut* idx = nullptr) {
     std::memset(res, 0, sizeof *res);
     *capacity_hit = false;
     if (mode != FQG_SINGLE && mode != FQG_INTERLEAVED && mode != FQG_PAIRED) return fail(FQG_E_INVALID_ARG, "unknown mode");
     if ((n1 && !r1) || (mode == FQG_PAIRED && n2 && !r2)) return fail(FQG_E_INVALID_ARG, "NULL input");
     CU_TRY(cudaSetDevice(c->device));
     DeviceDfa dd;
-    int rc = get_device_dfa(c, m, &dd);
+    int rc = m ? get_device_dfa(c, m, &dd) : 0;
     if (rc) return rc;
-    const bool names = m->kind == FQG_NAMES;
+    const bool names = m && m->kind == FQG_NAMES;
     NamesView nv;
     if (names) {
         std::lock_guard<std::mutex> lock(const_cast<fqg_matcher*>(m)->mu);
@@ -348,9 +355,10 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
         a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
         a.count = mode == FQG_SINGLE ? ctl + 1 : nullptr;
         a.err = ctl + 0;
-        a.invert = (m->opts & FQG_INVERT_MATCH) ? 1u : 0u;
+        a.invert = (m && (m->opts & FQG_INVERT_MATCH)) ? 1u : 0u;
         a.names = nv;
-        CU_TRY(launch_match_fastq(dd, names, a, c->sm_count, cs));
+        if (idx && i == 0) { a.seq_start = idx->seq_start; a.seq_len = idx->seq_len; a.span_cap = idx->cap; }
+        CU_TRY(launch_match_fastq(dd, names, m == nullptr, a, c->sm_count, cs));
         g_launches++;
         s.launches++;
         s.tiles_done = tile_end;
@@ -781,6 +789,36 @@ int fqg_read_input(const char* path, int decompress, int pinned, uint8_t** out, 
 void fqg_free_input(uint8_t* p, int pinned) { free_input(p, pinned); }
 int fqg_is_gzip_path(const char* path) { return path && is_gzip_path(path) ? 1 : 0; }
 int fqg_is_fastq_path(const char* path) { return path && is_fastq_path(path) ? 1 : 0; }
+
+int fqg_index_fastq_device(fqg_ctx* c, const uint8_t* d_fastq, size_t n, uint64_t* d_seq_start, uint32_t* d_seq_len, uint64_t capacity,
+                           uint64_t* n_records, void* stream) {
+    if (!c || !d_seq_start || !d_seq_len || !n_records || (n && !d_fastq)) return fail(FQG_E_INVALID_ARG, "NULL argument");
+    IndexOut idx;
+    idx.seq_start = reinterpret_cast<unsigned long long*>(d_seq_start);
+    idx.seq_len = d_seq_len;
+    idx.cap = capacity;
+    fqg_result res;
+    bool hit = false;
+    int rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, 32, &hit, &idx);
+    if (rc && hit) rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, 8, &hit, &idx);
+    if (rc) return rc;
+    *n_records = res.n_records;
+    if (res.n_records > capacity) return fail(FQG_E_INVALID_ARG, "index arrays too small: " + std::to_string(res.n_records) + " records");
+    return FQG_OK;
+}
+
+int fqg_compact_bases_device(fqg_ctx* c, const uint8_t* d_fastq, const uint64_t* d_seq_start, const uint32_t* d_seq_len, uint64_t n_records,
+                             uint8_t* d_bases_out, uint32_t* d_offsets_out, void* stream) {
+    if (!c || !d_bases_out || !d_offsets_out || (n_records && (!d_fastq || !d_seq_start || !d_seq_len))) return fail(FQG_E_INVALID_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    void* scratch;
+    int rc = ensure_dev(c, 6, compact_scratch_words(n_records) * 4, &scratch);
+    if (rc) return rc;
+    CU_TRY(launch_compact_bases(d_fastq, reinterpret_cast<const unsigned long long*>(d_seq_start), d_seq_len, n_records, d_bases_out, d_offsets_out,
+                                (uint32_t*)scratch, (cudaStream_t)stream));
+    g_launches += n_records ? 4 : 0;
+    return FQG_OK;
+}
 
 int fqg_fastq_split(const uint8_t* buf, size_t n, uint32_t parts, uint64_t* cuts) {
     if (!cuts || parts == 0 || (n && !buf)) return fail(FQG_E_INVALID_ARG, "bad argument");

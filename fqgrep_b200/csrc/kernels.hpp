@@ -77,10 +77,18 @@ struct FastqArgs {
     unsigned long long* err;       // min over (position << 4 | code), initialised to ~0
     uint32_t invert;
     NamesView names;
+    unsigned long long* seq_start;  // optional record index (K0): stream offset of every record's sequence line ...
+    uint32_t* seq_len;              // ... and its length without line terminator
+    uint64_t span_cap;
 };
 uint32_t fastq_tile_bytes();
 uint32_t fastq_overlap_bytes();
-cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs& a, int sm_count, cudaStream_t stream);
+// names: read-name lookup instead of an automaton; index_only: no matching at all, only parse / validate / index (K0)
+cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only, const FastqArgs& a, int sm_count, cudaStream_t stream);
+// K0 part 2: gather the indexed sequence lines into one contiguous SoA buffer with u32 offsets[n+1]
+cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n_records,
+                                 uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream);
+uint64_t compact_scratch_words(uint64_t n_records);
 cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
                                  uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
                                  unsigned long long* id_mismatch, cudaStream_t stream);

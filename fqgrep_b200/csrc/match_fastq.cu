@@ -92,10 +92,10 @@ struct NamesProbe {
     }
 };
 
-// TIER 0..2: DFA tiers (see kernels.hpp); TIER 3: read-name lookup.
+// TIER 0,1,2,4: DFA tiers (see kernels.hpp); TIER 3: read-name lookup; TIER 5: index only (no matching).
 template <int TIER>
 struct RecordEval {
-    DfaView<(TIER != 3 ? TIER : 0)> view;
+    DfaView<((TIER != 3 && TIER != 5) ? TIER : 0)> view;
     NamesProbe names;
     uint32_t start, accept_from;
     bool invert;
@@ -131,7 +131,8 @@ struct RecordEval {
             if (want_idh) *idh = h ^ (h >> 15);
         }
         bool found;
-        if (TIER == 3) found = names.contains_shared(tile + s + 1, id_len);
+        if (TIER == 5) found = false;
+        else if (TIER == 3) found = names.contains_shared(tile + s + 1, id_len);
         else found = walk_shared(view, tile + p0 + 1, seq_len, start) >= accept_from;
         return found != invert;
     }
@@ -149,7 +150,8 @@ struct RecordEval {
             *idh = h ^ (h >> 15);
         }
         bool found;
-        if (TIER == 3) found = names.contains_global(head, id_len);
+        if (TIER == 5) found = false;
+        else if (TIER == 3) found = names.contains_global(head, id_len);
         else found = walk_global(view, seq, seq_len, start) >= accept_from;
         return found != invert;
     }
@@ -295,7 +297,8 @@ __device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, 
         const uint32_t k = k0 + lane;
         const bool valid = k < n_list;
         bool sel = false;
-        uint32_t idh = 0;
+        uint32_t idh = 0, seq_n = 0;
+        unsigned long long seq_pos = 0;
         if (valid) {
             const uint32_t s = k < extra ? 0u : newline_of_rank(j0 + 4u * (k - extra)) + 1u;
             const uint32_t p0 = next_nl(s);
@@ -309,6 +312,8 @@ __device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, 
                 if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
                 else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
                 else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
+                seq_pos = T0 + p0 + 1u;
+                seq_n = seq_len;
                 sel = ev.eval_shared(tile_sa, s, p0, p1, seq_len, &idh, want_idh);
             } else {
                 // record runs past tile+overlap (or the stream is truncated): walk it in global memory
@@ -328,6 +333,8 @@ __device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, 
                     if (base[gs] != '@') report(a, gs, kErrInvalidStart);
                     else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
                     else if (seq_len != qual_len) report(a, gs, kErrUnequal);
+                    seq_pos = q[0] + 1;
+                    seq_n = (uint32_t)seq_len;
                     sel = ev.eval_global(base + gs + 1, (uint32_t)(q[0] - gs - 1 - cr0), base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
                 }
             }
@@ -336,6 +343,7 @@ __device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, 
         if (valid) {
             if (R_base + k >= a.mask_bits || (want_idh && R_base + k >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
             else if (want_idh) a.id_hash[R_base + k] = idh;
+            if (a.seq_start && R_base + k < a.span_cap) { a.seq_start[R_base + k] = seq_pos; a.seq_len[R_base + k] = seq_n; }
         }
         const uint32_t m = __ballot_sync(kFullMask, sel);
         if (lane == 0 && m) {
@@ -367,7 +375,7 @@ __device__ __forceinline__ void stage_automaton(const DeviceDfa& dfa, uint8_t* s
     if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
     if (TIER == 2)
         for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
-    if (TIER != 3)
+    if (TIER != 3 && TIER != 5)
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
 }
 
@@ -526,7 +534,8 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_coun
 uint32_t fastq_tile_bytes() { return kTile; }
 uint32_t fastq_overlap_bytes() { return kOverlap; }
 
-cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only, const FastqArgs& a, int sm_count, cudaStream_t stream) {
+    if (index_only) return launch_fastq_t<5>(dfa, a, sm_count, stream);
     if (names) return launch_fastq_t<3>(dfa, a, sm_count, stream);
     switch (dfa.tier) {
         case 0: return launch_fastq_t<0>(dfa, a, sm_count, stream);
@@ -535,6 +544,88 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, const FastqArgs
         // tier 3 (q-gram filter) is an SoA-kernel path; the fused FASTQ kernel walks its exact tier-2 table
         default: return launch_fastq_t<2>(dfa, a, sm_count, stream);
     }
+}
+
+// ---- K0 part 2: compaction of the indexed sequence lines into SoA (bases back to back + u32 offsets) -------------------
+namespace {
+constexpr uint32_t kScanBlock = 256, kScanItems = 8, kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_w, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= (uint32_t)d) incl += u;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (uint32_t w = 0; w < kScanBlock / 32; w++) { if (w < warp) base += s_w[w]; tot += s_w[w]; }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+__global__ void scan_block_sums_kernel(const uint32_t* len, uint64_t n, uint32_t* block_sums) {
+    __shared__ uint32_t s_w[kScanBlock / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < kScanItems; i++) if (base + i < n) v += len[base + i];
+    uint32_t tot;
+    block_exclusive_scan(v, s_w, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks) {     // one block; block_sums -> exclusive prefix, total appended
+    __shared__ uint32_t s_w[kScanBlock / 32];
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += kScanBlock) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan(v, s_w, &tot);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) block_sums[n_blocks] = carry;
+}
+__global__ void scan_offsets_kernel(const uint32_t* len, uint64_t n, const uint32_t* block_sums, uint32_t* offsets) {
+    __shared__ uint32_t s_w[kScanBlock / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t item[kScanItems], v = 0;
+    for (uint32_t i = 0; i < kScanItems; i++) { item[i] = base + i < n ? len[base + i] : 0u; v += item[i]; }
+    uint32_t tot;
+    uint32_t run = block_sums[blockIdx.x] + block_exclusive_scan(v, s_w, &tot);
+    for (uint32_t i = 0; i < kScanItems; i++) {
+        if (base + i < n) offsets[base + i] = run;
+        run += item[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanBlock - 1) offsets[n] = block_sums[gridDim.x];
+}
+// one warp per record: contiguous byte copy of its sequence line
+__global__ void gather_bases_kernel(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n,
+                                    const uint32_t* offsets, uint8_t* out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n; r += warps) {
+        const uint8_t* src = fastq + seq_start[r];
+        uint8_t* dst = out + offsets[r];
+        const uint32_t L = seq_len[r];
+        for (uint32_t i = lane; i < L; i += 32u) dst[i] = src[i];
+    }
+}
+}  // namespace
+
+uint64_t compact_scratch_words(uint64_t n_records) { return (n_records + kScanTile - 1) / kScanTile + 2; }
+
+cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n_records,
+                                 uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream) {
+    if (n_records == 0) return cudaMemsetAsync(offsets_out, 0, 4, stream);
+    const uint32_t n_blocks = (uint32_t)((n_records + kScanTile - 1) / kScanTile);
+    scan_block_sums_kernel<<<n_blocks, kScanBlock, 0, stream>>>(seq_len, n_records, block_sums);
+    scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(block_sums, n_blocks);
+    scan_offsets_kernel<<<n_blocks, kScanBlock, 0, stream>>>(seq_len, n_records, block_sums, offsets_out);
+    gather_bases_kernel<<<148 * 8, 256, 0, stream>>>(fastq, seq_start, seq_len, n_records, offsets_out, bases_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,

@@ -145,6 +145,19 @@ int fqg_grep_fastq_host(fqg_ctx* ctx, const fqg_matcher* m, int mode, const uint
 int fqg_grep_fastq_device(fqg_ctx* ctx, const fqg_matcher* m, int mode, const uint8_t* d_r1, size_t n1, const uint8_t* d_r2, size_t n2,
                           uint32_t* d_unit_mask_out, size_t unit_mask_words, fqg_result* res, void* stream);
 
+/* K0, for callers that parse once and match many times (the batcher of north_star: "finds record and line boundaries ...
+ * and compacts the sequence lines into an SoA bases buffer with per-read offsets").  Replaces the reader thread's record
+ * splitting (seq_io 0.3.4 RecordSet, driven from src/lib/seq_io.rs:60-80, 149-198) without matching anything.
+ *   fqg_index_fastq_device   d_seq_start[r] = stream offset of record r's sequence line, d_seq_len[r] = its length (CR
+ *                            stripped); same validation and errors as fqg_grep_fastq_*.  Arrays hold `capacity` records.
+ *   fqg_compact_bases_device gathers those lines back to back into d_bases_out (sum of lengths + 16 bytes) and writes
+ *                            d_offsets_out[n_records+1] (u32: at most 4 GiB of bases per call), ready for
+ *                            fqg_match_bases_device(d_bases_out, d_offsets_out, d_offsets_out + 1, ...).                */
+int fqg_index_fastq_device(fqg_ctx* ctx, const uint8_t* d_fastq, size_t n, uint64_t* d_seq_start, uint32_t* d_seq_len, uint64_t capacity,
+                           uint64_t* n_records, void* stream);
+int fqg_compact_bases_device(fqg_ctx* ctx, const uint8_t* d_fastq, const uint64_t* d_seq_start, const uint32_t* d_seq_len, uint64_t n_records,
+                             uint8_t* d_bases_out, uint32_t* d_offsets_out, void* stream);
+
 /* Selected-record write-back (src/main.rs:641-657 and write_paired_record :682-727 via seq_io write_to):
  * emits "@head\nseq\n+\nqual\n" for every selected unit in input order (pairs: R1 then R2), normalising CRLF
  * and "+name" lines like the reference.  out/out2 must be at least n1(+n2) bytes; out2 non-NULL splits R2

@@ -247,3 +247,56 @@ def test_device_resident_fastq_entry():
     assert res.n_selected == e["count"] and res.n_units == n
     got = np.unpackbits(mask.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
     assert (got == (e["flags"] != 0)).all()
+
+
+def test_k0_index_and_compaction_then_soa_match():
+    """Parse once, match many: fqg_index_fastq_device + fqg_compact_bases_device give the SoA layout of the same reads;
+    the SoA kernel over it must select exactly what the fused kernel selects."""
+    import ctypes as C
+    import torch
+    from fqgrep_b200 import _ffi
+    L = _ffi.lib()
+    ctx = F.context(0)
+    dev = torch.device("cuda:0")
+    rng = random.Random(3)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(rng.choice([0, 1, 50, 150, 151, 300, 5000]))) for _ in range(20_000)]
+    seqs[5] = "GACGAGATTA" + seqs[5]
+    data = np.frombuffer(fastq(seqs, crlf=True, plus_name=True, final_newline=False), dtype=np.uint8)
+    tb = torch.zeros(data.size + 64, dtype=torch.uint8, device=dev)
+    tb[: data.size] = torch.from_numpy(data.copy()).to(dev)
+    cap = len(seqs) + 10
+    d_start = torch.zeros(cap, dtype=torch.int64, device=dev)
+    d_len = torch.zeros(cap, dtype=torch.int32, device=dev)
+    n_rec = C.c_uint64(0)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.fqg_index_fastq_device(ctx, tb.data_ptr(), data.size, d_start.data_ptr(), d_len.data_ptr(), cap, C.byref(n_rec), sp)
+    assert rc == 0, _ffi.last_error()
+    assert n_rec.value == len(seqs)
+    starts, lens = d_start.cpu().numpy()[: len(seqs)], d_len.cpu().numpy()[: len(seqs)]
+    assert [int(x) for x in lens] == [len(s) for s in seqs]
+    for i in (0, 5, 777, len(seqs) - 1):
+        assert bytes(data[starts[i]: starts[i] + lens[i]]).decode() == seqs[i]
+    total = int(lens.sum())
+    d_bases = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+    d_offs = torch.zeros(len(seqs) + 1, dtype=torch.int32, device=dev)
+    rc = L.fqg_compact_bases_device(ctx, tb.data_ptr(), d_start.data_ptr(), d_len.data_ptr(), len(seqs), d_bases.data_ptr(), d_offs.data_ptr(), sp)
+    assert rc == 0, _ffi.last_error()
+    torch.cuda.synchronize()
+    offs = d_offs.cpu().numpy().astype(np.int64)
+    assert offs[0] == 0 and offs[-1] == total and (np.diff(offs) == lens).all()
+    assert d_bases[:total].cpu().numpy().tobytes() == "".join(seqs).encode()
+    pats = ["GACGAGATTA", "^ACG", "TT$"]
+    m = F.Matcher(F.REGEX_SET, pats, opts(False, True))
+    words = len(seqs) // 32 + 2
+    mask = torch.zeros(words, dtype=torch.int32, device=dev)
+    rc = L.fqg_match_bases_device(ctx, m._h, d_bases.data_ptr(), d_offs.data_ptr(), d_offs.data_ptr() + 4, len(seqs), mask.data_ptr(), None, None, 0, sp)
+    assert rc == 0, _ffi.last_error()
+    torch.cuda.synchronize()
+    fused = m.grep_fastq(data)
+    got = np.unpackbits(mask.cpu().numpy().view(np.uint8), bitorder="little")[: len(seqs)].astype(bool)
+    assert (got == fused["mask"]).all() and fused["count"] > 0
+    # malformed input is reported by the indexer too
+    bad = np.frombuffer(b"@a\nACGT\n+\nXXX\n", dtype=np.uint8)
+    tb2 = torch.zeros(bad.size + 64, dtype=torch.uint8, device=dev)
+    tb2[: bad.size] = torch.from_numpy(bad.copy()).to(dev)
+    assert L.fqg_index_fastq_device(ctx, tb2.data_ptr(), bad.size, d_start.data_ptr(), d_len.data_ptr(), cap, C.byref(n_rec), sp) == -4
