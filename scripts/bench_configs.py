@@ -117,6 +117,28 @@ def run_names(out, n=20_000_000, n_names=1_000_000):
 ONLY = sys.argv[2] if len(sys.argv) > 2 else ""
 
 
+def run_index_only(out, n=20_000_000):
+    """K0 alone: parse + validate + index, no matching: the parse floor of the fused kernel."""
+    tb = gen(n, 1, [], 0.0, 0, fastq=1)
+    nbytes = n * (2 * RL + 17)
+    d_start = torch.zeros(n + 8, dtype=torch.int64, device=dev)
+    d_len = torch.zeros(n + 8, dtype=torch.int32, device=dev)
+    nrec = C.c_uint64(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(5):
+        if it == 2:
+            torch.cuda.synchronize()
+            e0.record()
+        rc = L.fqg_index_fastq_device(ctx, tb.data_ptr(), nbytes, d_start.data_ptr(), d_len.data_ptr(), n + 8, C.byref(nrec), sp)
+        assert rc == 0, _ffi.last_error()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["k0_index_only_fastq"] = {"reads": n, "ms_incl_host_sync": ms, "greads_s": n / (ms / 1e3) / 1e9,
+                                  "raw_fastq_roofline_frac": (2 * RL + 17 + 12) * n / (ms / 1e3) / 1e9 / PEAK, "records": int(nrec.value)}
+    print("k0_index_only", json.dumps(out["k0_index_only_fastq"]), flush=True)
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     out = {"peak_gbs": PEAK}
@@ -138,6 +160,8 @@ def main():
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
     if not ONLY or ONLY in "cfg5b_names":
         run_names(out)
+    if not ONLY or ONLY in "k0_index_only":
+        run_index_only(out)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_%s.json" % tag), "w"), indent=1)
 
