@@ -35,7 +35,7 @@ struct DeviceTables {
     void* table = nullptr;
     uint8_t* byte_class = nullptr;
     // q-gram filter
-    uint32_t *g_bitmap = nullptr, *g_kv = nullptr, *g_pat_off = nullptr;
+    uint32_t *g_bitmap = nullptr, *g_kv = nullptr;
     uint8_t* g_pool = nullptr;
     // names
     uint64_t* slots = nullptr;
@@ -172,8 +172,7 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
                     return cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
                 };
                 CU_TRY(up(&t.g_bitmap, g.bitmap));
-                CU_TRY(up(&t.g_kv, g.slot_kv));
-                CU_TRY(up(&t.g_pat_off, g.pat_off));
+                CU_TRY(up(&t.g_kv, g.slots));
                 CU_TRY(up(&t.g_pool, g.pool));
             }
         }
@@ -188,8 +187,8 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
             const GramFilter& g = m->gram;
             DeviceGram& d = out->gram;
             d.bitmap = it->second.g_bitmap; d.bitmap_bytes = (uint32_t)g.bitmap.size() * 4; d.bitmap_shift = 32 - (g.bitmap_bits_log2 - 5);     // hash -> WORD index
-            d.slot_kv = it->second.g_kv; d.slot_shift = 32 - g.slots_log2; d.slot_mask = (1u << g.slots_log2) - 1;
-            d.pool = it->second.g_pool; d.pat_off = it->second.g_pat_off;
+            d.slots = reinterpret_cast<const uint4*>(it->second.g_kv); d.slot_shift = 32 - g.slots_log2; d.slot_mask = (1u << g.slots_log2) - 1;
+            d.pool = it->second.g_pool;
             d.q = g.q; d.s = g.s; d.min_len = g.min_len; d.qmask = g.qmask;
         }
         out->row = m->row;
@@ -572,7 +571,7 @@ void fqg_matcher_free(fqg_matcher* m) {
         cudaFree(kv.second.slots);
         cudaFree(kv.second.slot_off);
         cudaFree(kv.second.pool);
-        cudaFree(kv.second.g_bitmap); cudaFree(kv.second.g_kv); cudaFree(kv.second.g_pat_off); cudaFree(kv.second.g_pool);
+        cudaFree(kv.second.g_bitmap); cudaFree(kv.second.g_kv); cudaFree(kv.second.g_pool);
         cudaSetDevice(prev);
     }
     delete m;

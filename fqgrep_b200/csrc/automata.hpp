@@ -60,9 +60,8 @@ struct GramFilter {
     uint32_t q = 0, s = 0, min_len = 0, qmask = 0;
     uint32_t bitmap_bits_log2 = 0, slots_log2 = 0;
     std::vector<uint32_t> bitmap;      // shared-memory resident on the device
-    std::vector<uint32_t> slot_kv;     // pairs {gram code, pattern id << 5 | offset in the pattern}; value 0xFFFFFFFF = empty
-    std::vector<uint8_t> pool;         // patterns back to back (+ reverse complements)
-    std::vector<uint32_t> pat_off;     // n_patterns + 1
+    std::vector<uint32_t> slots;       // 4 words per slot {gram key, pool offset, pattern length << 5 | offset in the pattern, -}; all ones = empty
+    std::vector<uint8_t> pool;         // patterns (+ reverse complements), each starting on a 16-byte boundary
 };
 uint32_t gram_code(const uint8_t* p, uint32_t q);
 bool build_gram_filter(const std::vector<std::string>& patterns, bool with_revcomp, GramFilter* out);

@@ -29,6 +29,10 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                  "r"(bar)
                  : "memory");
 }
+// warm L2 with a span that a later bulk copy will read (same alignment rules); no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {

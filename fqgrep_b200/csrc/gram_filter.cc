@@ -9,7 +9,8 @@
 // lands on a window that starts at pattern offset 0..s-1.  The device therefore keeps
 //   * a blocked Bloom filter (shared memory, 3 bits per gram inside one 32-bit word) of the grams at offsets 0..s-1
 //     of every pattern: exact negative filter;
-//   * an open-addressing table gram -> (pattern id, offset) in L2 for the rare positives, verified byte by byte.
+//   * an open-addressing table gram -> (offset in the pattern, pattern bytes) in L2 for the rare positives: one 16-byte
+//     slot read decides a false positive; a real gram is verified against the pattern 16 bytes at a time.
 // Grams are built from 2-bit codes (byte >> 1) & 3 of ANY byte (not only ACGT): text and patterns use the same map, so
 // aliasing (N ~ G ...) can only add candidates, never lose a match.
 #include "automata.hpp"
@@ -22,6 +23,18 @@ namespace fqg {
 uint32_t gram_code(const uint8_t* p, uint32_t q) {
     uint32_t g = 0;
     for (uint32_t i = 0; i < q; i++) g = (g << 2) | ((p[i] >> 1) & 3u);
+    return g;
+}
+
+// Key of the q bases p[0..q) when the device samples grams that end on a 4-byte boundary of its staging buffer
+// (stride a multiple of 4).  The device packs every aligned 32-bit word of text into one byte with a single multiply
+// -- (w & 0x06060606) * 0x00820820 >> 24: byte k of the word lands in bits 2k..2k+1 -- and shifts those bytes
+// through a register, newest word in the low byte; the key is that register masked to the last q bases.
+// Base p[q-1-i] therefore sits in byte i/4 at bits 2*(3 - i%4).
+static uint32_t gram_bit_offset(uint32_t i) { return 8u * (i / 4u) + 2u * (3u - (i % 4u)); }
+uint32_t gram_key_aligned(const uint8_t* p, uint32_t q) {
+    uint32_t g = 0;
+    for (uint32_t i = 0; i < q; i++) g |= (uint32_t)((p[q - 1 - i] >> 1) & 3u) << gram_bit_offset(i);
     return g;
 }
 
@@ -38,23 +51,31 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     if (pats.empty()) return false;
     size_t min_len = SIZE_MAX, total = 0;
     for (auto& p : pats) { min_len = std::min(min_len, p.size()); total += p.size(); }
-    if (min_len < 8 || pats.size() >= (1u << 26) || total >= (1ull << 31)) return false;
+    if (min_len < 8 || pats.size() >= (1u << 26) || total + 16 * pats.size() >= (1ull << 31)) return false;
     uint32_t q = (uint32_t)std::min<size_t>(16, std::max<size_t>(8, min_len / 2 + 2));
     uint32_t s = (uint32_t)min_len - q + 1;
     if (s > 32) { s = 32; }            // payload keeps the offset in 5 bits; a smaller stride is always valid
-    if (s >= 4) {                      // word-aligned sampling (one probe every s/4 input words, no sub-word shifts);
-        s &= ~3u;                      // the slack goes back into a longer, more selective gram
-        q = (uint32_t)std::min<size_t>(16, min_len - s + 1);
+    const bool aligned = s >= 4;
+    if (aligned) {                     // aligned sampling: one probe per s bytes of staged text, read with aligned
+        s = s >= 8 ? (s & ~7u) : 4u;   // 8-byte (or 4-byte) shared loads and no sub-word shifts; the slack goes back
+        q = (uint32_t)std::min<size_t>(16, min_len - s + 1);      // into a longer, more selective gram
     }
     out->q = q;
     out->s = s;
     out->min_len = (uint32_t)min_len;
     out->qmask = q == 16 ? 0xFFFFFFFFu : ((1u << (2 * q)) - 1u);
+    if (aligned) {
+        out->qmask = 0;
+        for (uint32_t i = 0; i < q; i++) out->qmask |= 3u << gram_bit_offset(i);
+    }
     const uint64_t n_grams = (uint64_t)pats.size() * s;
-    if (n_grams > (1ull << 24)) return false;
-    // blocked 3-bit Bloom filter in shared memory: one hash picks a 32-bit word, a second one three bits inside it.
-    // ~40 bits per gram keeps the false-positive rate near 0.2 %; capped at 128 KB (2^20 bits), floor 8 KB.
-    uint32_t bits_log2 = 16, cap_log2 = 20;
+    if (n_grams > (1ull << 22)) return false;
+    // blocked 3-bit Bloom filter in shared memory: the top bits of one multiplicative hash pick a 32-bit word, bits 2..16
+    // three bits inside it.  ~40 bits per gram keeps the false-positive rate near 0.2 %; floor 8 KB, cap 128 KB (2^20
+    // bits).  The filter shares the SM's 227 KB with the staging slots, i.e. with the number of resident warps, so the
+    // last doubling (64 -> 128 KB) is only taken when 64 KB would leave less than ~6 bits per gram (measured on B200,
+    // 10 k 20-mers: 80 k grams run 5 % faster with 64 KB and more warps, 160 k grams 28 % faster with 128 KB).
+    uint32_t bits_log2 = 16, cap_log2 = n_grams * 6 <= (1ull << 19) ? 19 : 20;
     if (const char* e = std::getenv("FQG_GRAM_BITS_LOG2_MAX")) {      // tuning knob for experiments
         int v = std::atoi(e);
         if (v >= 16 && v <= 20) cap_log2 = (uint32_t)v;
@@ -65,23 +86,24 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     uint32_t slots_log2 = 4;
     while ((1ull << slots_log2) < n_grams * 4 + 2) slots_log2++;        // load <= 0.25: a miss ends after ~1.2 slots
     out->slots_log2 = slots_log2;
-    out->slot_kv.assign((size_t)2 << slots_log2, 0xFFFFFFFFu);
+    out->slots.assign((size_t)4 << slots_log2, 0xFFFFFFFFu);      // {gram, pool offset, length << 5 | j, -}; all ones = empty
     out->pool.clear();
-    out->pat_off.assign(1, 0);
     for (size_t id = 0; id < pats.size(); id++) {
         const std::string& p = pats[id];
+        const uint32_t pool_off = (uint32_t)out->pool.size();      // 16-byte aligned: the device compares uint4 chunks
         for (uint32_t j = 0; j < s; j++) {
-            const uint32_t g = gram_code((const uint8_t*)p.data() + j, q);
-            const uint32_t word = (g * 0x9E3779B1u) >> (32 - (bits_log2 - 5));
-            const uint32_t h2 = (g * 0xC2B2AE35u) >> 17;
-            out->bitmap[word] |= (1u << (h2 & 31u)) | (1u << ((h2 >> 5) & 31u)) | (1u << (h2 >> 10));
+            const uint32_t g = aligned ? gram_key_aligned((const uint8_t*)p.data() + j, q) : gram_code((const uint8_t*)p.data() + j, q);
+            const uint32_t h = g * 0x9E3779B1u;
+            const uint32_t word = h >> (32 - (bits_log2 - 5));
+            out->bitmap[word] |= (1u << ((h >> 2) & 31u)) | (1u << ((h >> 7) & 31u)) | (1u << ((h >> 12) & 31u));
             uint32_t i = (g * 0x85EBCA6Bu) >> (32 - slots_log2);
-            while (out->slot_kv[2 * (size_t)i + 1] != 0xFFFFFFFFu) i = (i + 1) & ((1u << slots_log2) - 1);
-            out->slot_kv[2 * (size_t)i] = g;
-            out->slot_kv[2 * (size_t)i + 1] = (uint32_t)(id << 5) | j;
+            while (out->slots[4 * (size_t)i + 2] != 0xFFFFFFFFu) i = (i + 1) & ((1u << slots_log2) - 1);
+            out->slots[4 * (size_t)i] = g;
+            out->slots[4 * (size_t)i + 1] = pool_off;
+            out->slots[4 * (size_t)i + 2] = (uint32_t)(p.size() << 5) | j;
         }
         out->pool.insert(out->pool.end(), p.begin(), p.end());
-        out->pat_off.push_back((uint32_t)out->pool.size());
+        out->pool.resize((out->pool.size() + 15) & ~(size_t)15, 0);
     }
     out->pool.resize(out->pool.size() + 16, 0);
     out->usable = true;

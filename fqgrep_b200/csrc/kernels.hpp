@@ -17,11 +17,10 @@ namespace fqg {
 // Device view of the q-gram filter (tier 3); see gram_filter.cc / match_soa.cu.
 struct DeviceGram {
     const uint32_t* bitmap = nullptr;    // device copy, staged into shared memory by the kernel
-    uint32_t bitmap_bytes = 0, bitmap_shift = 0;   // word index = (gram * 0x9E3779B1) >> bitmap_shift; 2 bits from a second hash
-    const uint32_t* slot_kv = nullptr;     // pairs {gram, pattern id << 5 | offset}; value 0xFFFFFFFF = empty
+    uint32_t bitmap_bytes = 0, bitmap_shift = 0;   // h = gram * 0x9E3779B1: word index = h >> bitmap_shift, bit positions (h>>2, h>>7, h>>12) & 31
+    const uint4* slots = nullptr;          // {gram key, pool offset, pattern length << 5 | offset in the pattern, -}; .z all ones = empty
     uint32_t slot_shift = 0, slot_mask = 0;
-    const uint8_t* pool = nullptr;
-    const uint32_t* pat_off = nullptr;
+    const uint8_t* pool = nullptr;         // patterns, each on a 16-byte boundary
     uint32_t q = 0, s = 0, min_len = 0, qmask = 0;
 };
 

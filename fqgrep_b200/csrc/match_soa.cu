@@ -33,38 +33,57 @@ struct GramView {
     uint32_t cls;             // shared address of the byte -> class LUT
     uint32_t dfa_start, dfa_accept;
 };
+// Exact check of one filter hit: is the gram that ends at base e of the read at shared address p (len bases) a gram of
+// some pattern, and does that pattern occur around it?  A false positive costs one 16-byte L2 read (an empty slot).
 __device__ __forceinline__ bool gram_verify(const GramView& v, uint32_t p, uint32_t len, uint32_t gram, uint32_t e) {
     uint32_t i = (gram * 0x85EBCA6Bu) >> v.g.slot_shift;
     for (;;) {
-        const uint2 kv = __ldg(reinterpret_cast<const uint2*>(v.g.slot_kv) + i);      // {gram, pattern id << 5 | offset}
-        if (kv.y == 0xFFFFFFFFu) return false;
-        if (kv.x == gram) {
-            const uint32_t id = kv.y >> 5, j = kv.y & 31u;
-            const uint32_t o0 = __ldg(v.g.pat_off + id), plen = __ldg(v.g.pat_off + id + 1) - o0;
+        const uint4 slot = __ldg(v.g.slots + i);      // {gram key, pool offset, pattern length << 5 | offset, -}
+        if (slot.z == 0xFFFFFFFFu) return false;
+        if (slot.x == gram) {
+            const uint32_t plen = slot.z >> 5, j = slot.z & 31u;
             const int32_t start = (int32_t)e - (int32_t)(v.g.q - 1u) - (int32_t)j;     // where the pattern would begin in the read
             if (start >= 0 && (uint32_t)start + plen <= len) {
-                uint32_t k = 0;
-                while (k < plen && lds_u8(p + (uint32_t)start + k) == __ldg(v.g.pool + o0 + k)) k++;
-                if (k == plen) return true;
+                // 16 pattern bytes per L2 read against the (unaligned) text words in shared memory
+                const uint4* pat = reinterpret_cast<const uint4*>(v.g.pool + slot.y);
+                const uint32_t a = p + (uint32_t)start, sh = (a & 3u) * 8u;
+                uint32_t wp = a & ~3u, w0 = lds_u32_volatile(wp), diff = 0;
+                for (uint32_t k = 0; k < plen && !diff; k += 16u) {
+                    const uint4 c = __ldg(pat + (k >> 4));
+                    const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t rem = plen - k > 4u * t ? plen - k - 4u * t : 0u;      // pattern bytes left in this word
+                        const uint32_t w1 = rem ? lds_u32_volatile(wp + 4u) : 0u;
+                        wp += 4u;
+                        const uint32_t text = __funnelshift_r(w0, w1, sh);
+                        w0 = w1;
+                        const uint32_t keep = rem >= 4u ? 0xFFFFFFFFu : rem ? (1u << (8u * rem)) - 1u : 0u;
+                        diff |= (text ^ cw[t]) & keep;
+                    }
+                }
+                if (!diff) return true;
             }
         }
         i = (i + 1u) & v.g.slot_mask;
     }
 }
 
-// 2-bit codes of the q bases ending at base index e of the read at shared address p (only for the rare filter hits)
-__device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q, uint32_t qmask) {
-    if ((e & 3u) == 3u && e >= 15u) {          // word-aligned sampling: re-pack the four words that end at base e
-        const uint32_t a = p + e - 15u, sh = (a & 3u) * 8u;
-        uint32_t wp = a & ~3u, w0 = lds_u32_volatile(wp), g = 0;
+// aligned sampling: 2-bit codes of one aligned text word -> one byte (byte k of the word in bits 2k..2k+1), shifted
+// into the rolling register `lo` (newest word in the low byte).  gram_filter.cc builds the keys the same way.
+__device__ __forceinline__ uint32_t pack_word(uint32_t w, uint32_t lo) {
+    return __byte_perm((w & 0x06060606u) * 0x00820820u, lo, 0x6543);
+}
+__device__ __forceinline__ uint2 lds_u64_volatile(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q, uint32_t qmask, bool aligned) {
+    if (aligned) {          // aligned sampling: re-pack the four staged words that end at base e (see pack_word)
+        uint32_t wp = p + e - 15u, g = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            wp += 4u;
-            const uint32_t w1 = lds_u32_volatile(wp);
-            const uint32_t x = (__funnelshift_r(w0, w1, sh) >> 1) & 0x03030303u;
-            w0 = w1;
-            g = (g << 8) | ((x * 0x40100401u) >> 24);
-        }
+        for (int k = 0; k < 4; k++) g = pack_word(lds_u32_volatile(wp + 4u * k), g);
         return g & qmask;
     }
     uint32_t g = 0;
@@ -72,7 +91,8 @@ __device__ __forceinline__ uint32_t gram_at(uint32_t p, uint32_t e, uint32_t q, 
     return g;
 }
 
-// true iff some pattern of the set occurs in the read at shared address p
+// true iff some pattern of the set occurs in the read at shared address p.  Must be called by all 32 lanes of the warp
+// together (lanes without a read pass len = 0): the filter hits of the whole batch are verified cooperatively.
 __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_t len) {
     // pinned into registers (asm volatile cannot be rematerialised) so the probe does not re-derive them per gram
     uint32_t bitmap, bshift, qmask;
@@ -81,79 +101,84 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
     asm volatile("mov.u32 %0, %1;" : "=r"(qmask) : "r"(v.g.qmask));
     const uint32_t q = v.g.q, stride = v.g.s;
     bool found = false, exact_walk = false;
+    const bool aligned = (stride & 3u) == 0;
+    uint32_t hits0 = 0, hits1 = 0, probes_done = 0, e0 = 0;
     if (len >= v.g.min_len) {
         // Filter hits are recorded branch-free as one bit per probe (probe i ends at base e0 + i*stride); the gram of a
         // hit is re-read from shared memory later.  64 probes cover reads up to ~64*stride bases; longer reads take
         // the exact automaton walk.
         // hits0 takes probes 0..31 (first probe ends up in the highest used bit), hits1 probes 32..63.
-        uint32_t hits0 = 0, hits1 = 0;
         auto probe_into = [&](uint32_t gram, uint32_t& acc) {
-            const uint32_t wi = (gram * 0x9E3779B1u) >> bshift;              // word of the blocked Bloom filter
-            const uint32_t h2 = (gram * 0xC2B2AE35u) >> 17;                  // three bit positions inside it
-            const uint32_t need = (1u << (h2 & 31u)) | (1u << ((h2 >> 5) & 31u)) | (1u << (h2 >> 10));
+            const uint32_t h = gram * 0x9E3779B1u;
+            const uint32_t wi = h >> bshift;                                 // word of the blocked Bloom filter (top bits)
+            // three bit positions inside it from bits 2..16 of the same product (funnel shifts wrap the amount mod 32)
+            const uint32_t need = __funnelshift_l(0u, 1u, h >> 2) | __funnelshift_l(0u, 1u, h >> 7) | __funnelshift_l(0u, 1u, h >> 12);
             uint32_t word;
             asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bitmap + (wi << 2)));
             acc = (acc << 1) | (uint32_t)((word & need) == need);
         };
-        uint32_t probes_done = 0;
         auto probe = [&](uint32_t gram, uint32_t) {
             if (probes_done < 32u) probe_into(gram, hits0); else probe_into(gram, hits1);
             probes_done++;
         };
-        const uint32_t sh0 = (p & 3u) * 8u;
-        uint32_t wp = p & ~3u;
-        uint32_t w0 = lds_u32_volatile(wp);
-        uint32_t lo = 0, hi = 0;              // 2-bit codes of the last 32 bases, newest in the low bits
-        const uint32_t nw = len >> 2;
-        uint32_t e0, n_probes = 0;
-        if ((stride & 3u) == 0) {
-            // word-aligned sampling: grams end on the last base of a word, one probe every stride/4 words.
-            // (the <4-base tail never ends a sampled gram, and every occurrence still covers >= stride gram ends)
-            const uint32_t every = stride >> 2, k0 = (q - 1u) >> 2;
-            e0 = 4u * k0 + 3u;
-            n_probes = nw > k0 ? (nw - 1u - k0) / every + 1u : 0u;
+        uint32_t lo = 0, hi = 0;              // 2-bit codes of the last 16 (+16) bases, newest in the low bits
+        uint32_t n_probes = 0;
+        if (aligned) {
+            // Aligned sampling: the sampled grams end on the last byte of an aligned 8-byte unit (4-byte when
+            // stride == 4) of the STAGING BUFFER, whatever the read's own alignment: aligned LDS.64, no funnel shifts,
+            // one multiply packs a word.  Sampled ends are e0, e0 + stride, ... <= len - 1 with e0 in [q-1, q-1+7]:
+            // every run of `stride` consecutive gram ends inside the read still contains one of them.
+            const uint32_t unit = (stride & 7u) ? 3u : 7u;
+            const uint32_t end0 = (p + q - 1u) | unit;          // shared address of the first sampled end
+            e0 = end0 - p;
+            n_probes = len > e0 ? (len - 1u - e0) / stride + 1u : 0u;
             if (n_probes > 64u) exact_walk = true;
             else if (n_probes) {
-                auto append = [&]() {
-                    wp += 4;
-                    const uint32_t w1 = lds_u32_volatile(wp);
-                    const uint32_t w = __funnelshift_r(w0, w1, sh0);
-                    w0 = w1;
-                    const uint32_t x = (w >> 1) & 0x03030303u;
-                    lo = (lo << 8) | ((x * 0x40100401u) >> 24);      // first base of the word in the high bits
-                };
-                for (uint32_t k = 0; k <= k0; k++) append();
+                uint32_t wp = end0 - 15u;
+#pragma unroll
+                for (int k = 0; k < 4; k++) lo = pack_word(lds_u32_volatile(wp + 4u * k), lo);
+                wp += 16u;
                 probe_into(lo & qmask, hits0);
-                // one probe per `every` words, no per-word branch: the common strides are unrolled
                 const uint32_t n_first = n_probes < 32u ? n_probes : 32u;
-                auto groups = [&](auto every_c) {
-                    constexpr uint32_t E = decltype(every_c)::value;
+                auto groups = [&](auto units_c) {       // units_c 8-byte units per probe
+                    constexpr uint32_t E = decltype(units_c)::value;
                     for (uint32_t g = 1; g < n_first; g++) {
 #pragma unroll
-                        for (uint32_t j = 0; j < E; j++) append();
+                        for (uint32_t j = 0; j < E; j++) {
+                            const uint2 w = lds_u64_volatile(wp + 8u * j);
+                            lo = pack_word(w.y, pack_word(w.x, lo));
+                        }
+                        wp += 8u * E;
                         probe_into(lo & qmask, hits0);
                     }
                     for (uint32_t g = 32; g < n_probes; g++) {
 #pragma unroll
-                        for (uint32_t j = 0; j < E; j++) append();
+                        for (uint32_t j = 0; j < E; j++) {
+                            const uint2 w = lds_u64_volatile(wp + 8u * j);
+                            lo = pack_word(w.y, pack_word(w.x, lo));
+                        }
+                        wp += 8u * E;
                         probe_into(lo & qmask, hits1);
                     }
-                    probes_done = n_probes;
                 };
-                switch (every) {
-                    case 1: groups(std::integral_constant<uint32_t, 1>{}); break;
-                    case 2: groups(std::integral_constant<uint32_t, 2>{}); break;
-                    case 3: groups(std::integral_constant<uint32_t, 3>{}); break;
-                    case 4: groups(std::integral_constant<uint32_t, 4>{}); break;
-                    default:
-                        probes_done = 1;
+                switch (stride) {
+                    case 8: groups(std::integral_constant<uint32_t, 1>{}); break;
+                    case 16: groups(std::integral_constant<uint32_t, 2>{}); break;
+                    case 24: groups(std::integral_constant<uint32_t, 3>{}); break;
+                    case 32: groups(std::integral_constant<uint32_t, 4>{}); break;
+                    default:          // stride 4: one aligned word per probe
                         for (uint32_t g = 1; g < n_probes; g++) {
-                            for (uint32_t j = 0; j < every; j++) append();
-                            probe(lo & qmask, g);
+                            lo = pack_word(lds_u32_volatile(wp), lo);
+                            wp += 4u;
+                            if (g < 32u) probe_into(lo & qmask, hits0); else probe_into(lo & qmask, hits1);
                         }
                 }
+                probes_done = n_probes;
             }
         } else {
+            const uint32_t sh0 = (p & 3u) * 8u, nw = len >> 2;
+            uint32_t wp = p & ~3u;
+            uint32_t w0 = lds_u32_volatile(wp);
             e0 = q - 1u;
             if ((len - q) / stride + 1u > 64u) exact_walk = true;
             else {
@@ -185,22 +210,52 @@ __device__ __forceinline__ bool gram_walk(const GramView& v, uint32_t p, uint32_
                 }
             }
         }
-        // exact verification of the few hits; lanes run the loop side by side so their L2 latencies overlap
-        // (plain per-lane loop, no warp collective: lanes of ragged batches leave this function at different points)
-        // bit b of hits0 is probe (n0 - 1 - b), bit b of hits1 is probe (32 + n1 - 1 - b)
-        const uint32_t n0 = probes_done < 32u ? probes_done : 32u, n1 = probes_done - n0;
-        while (hits0 && !found) {
-            const uint32_t b = (uint32_t)__ffs((int)hits0) - 1u;
-            hits0 &= hits0 - 1u;
-            const uint32_t e = e0 + (n0 - 1u - b) * stride;
-            found = gram_verify(v, p, len, gram_at(p, e, q, qmask), e);
+    }
+    // Exact verification, shared by the warp.  Hits are rare but unevenly spread (a lane-private loop makes the warp
+    // wait for its unluckiest lane, one L2 round trip per hit), so they are numbered across the batch and dealt out one
+    // per lane: task t belongs to the lane `owner` whose running hit count first exceeds t; the verifying lane fetches
+    // the owner's read (shared address, length, hit bits) by shuffle.  Warp-uniform control flow around every collective.
+    {
+        const uint32_t mine = (uint32_t)__popc(hits0) + (uint32_t)__popc(hits1);
+        uint32_t inc = mine;                       // inclusive prefix sum of the per-lane hit counts
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+            if ((threadIdx.x & 31u) >= d) inc += t;
         }
-        while (hits1 && !found) {
-            const uint32_t b = (uint32_t)__ffs((int)hits1) - 1u;
-            hits1 &= hits1 - 1u;
-            const uint32_t e = e0 + (32u + n1 - 1u - b) * stride;
-            found = gram_verify(v, p, len, gram_at(p, e, q, qmask), e);
+        const uint32_t total = __shfl_sync(kFullMask, inc, 31);
+        uint32_t found_lanes = 0;
+        for (uint32_t first = 0; first < total; first += 32u) {
+            const uint32_t task = first + (threadIdx.x & 31u);
+            uint32_t owner = 0;                    // number of lanes whose inclusive count is <= task
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) {
+                const uint32_t t = __shfl_sync(kFullMask, inc, owner + step - 1u);
+                if (t <= task) owner += step;
+            }
+            owner &= 31u;                          // idle lanes (task >= total) read lane 0..31 harmlessly
+            const uint32_t o_inc = __shfl_sync(kFullMask, inc, owner), o_mine = __shfl_sync(kFullMask, mine, owner);
+            const uint32_t o_h0 = __shfl_sync(kFullMask, hits0, owner), o_h1 = __shfl_sync(kFullMask, hits1, owner);
+            const uint32_t o_p = __shfl_sync(kFullMask, p, owner), o_len = __shfl_sync(kFullMask, len, owner);
+            const uint32_t o_e0 = __shfl_sync(kFullMask, e0, owner), o_n = __shfl_sync(kFullMask, probes_done, owner);
+            bool ok = false;
+            if (task < total) {
+                uint32_t k = task - (o_inc - o_mine);          // which of the owner's hits, lowest bit of hits0 first
+                const uint32_t c0 = (uint32_t)__popc(o_h0);
+                const bool in0 = k < c0;
+                uint32_t h = in0 ? o_h0 : o_h1;
+                if (!in0) k -= c0;
+                for (; k; k--) h &= h - 1u;
+                const uint32_t bit = (uint32_t)__ffs((int)h) - 1u;
+                // bit b of hits0 is probe (n0 - 1 - b), bit b of hits1 is probe (32 + n1 - 1 - b)
+                const uint32_t n0 = o_n < 32u ? o_n : 32u, n1 = o_n - n0;
+                const uint32_t probe_idx = in0 ? n0 - 1u - bit : 32u + n1 - 1u - bit;
+                const uint32_t e = o_e0 + probe_idx * stride;
+                ok = gram_verify(v, o_p, o_len, gram_at(o_p, e, q, qmask, aligned), e);
+            }
+            found_lanes |= __reduce_or_sync(kFullMask, ok ? 1u << owner : 0u);
         }
+        found = (found_lanes >> (threadIdx.x & 31u)) & 1u;
     }
     if (exact_walk) {          // very long read: exact automaton walk through L2
         uint32_t st = v.dfa_start;
@@ -254,12 +309,22 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     const uint32_t stride = gridDim.x * nwarps;
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
 
-    auto load_desc = [&](uint32_t batch) -> BatchDesc {
-        BatchDesc d;
+    // A batch descriptor is fetched in two steps so the offset loads (streamed from HBM) have a whole batch of work to
+    // land: load_raw only issues them, finalize (one iteration later) consumes them.
+    struct RawDesc { uint32_t s, e; bool valid; };
+    auto load_raw = [&](uint32_t batch) -> RawDesc {
+        RawDesc d;
         const uint32_t r = batch * 32u + lane;
-        const bool valid = batch < n_batches && r < b.n_reads;
-        d.s = valid ? __ldg(b.start + r) : 0u;
-        d.e = valid ? __ldg(b.end + r) : 0u;
+        d.valid = batch < n_batches && r < b.n_reads;
+        d.s = d.valid ? __ldg(b.start + r) : 0u;
+        d.e = d.valid ? __ldg(b.end + r) : 0u;
+        return d;
+    };
+    auto finalize = [&](const RawDesc& raw) -> BatchDesc {
+        BatchDesc d;
+        const bool valid = raw.valid;
+        d.s = raw.s;
+        d.e = raw.e;
         if (d.e < d.s) d.e = d.s;
         const uint32_t lo = __reduce_min_sync(kFullMask, valid ? d.s : 0xFFFFFFFFu);
         const uint32_t hi = __reduce_max_sync(kFullMask, valid ? d.e : 0u);
@@ -286,16 +351,20 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     uint32_t phase_bits = 0, stage = 0;
     unsigned long long local_count = 0;
 
-    BatchDesc cur = load_desc(batch);
+    BatchDesc cur = finalize(load_raw(batch));
     issue(cur, 0);
-    BatchDesc nxt = load_desc(batch + stride);
+    // nxt: the batch after cur.  STAGES == 2 copies it into the other slot while cur is walked; STAGES == 1 has no slot
+    // for it and instead pulls its bytes into L2 (126 MB), so the copy issued when the slot frees only pays L2 latency
+    // and the HBM requests in flight are not capped by the staging memory.  ahead: offsets in flight for the batch after nxt.
+    auto prefetch = [&](const BatchDesc& d) {
+        if (STAGES == 1 && d.fits && d.bytes && lane == 0) bulk_prefetch_l2(reinterpret_cast<const void*>(d.src), d.bytes);
+    };
+    BatchDesc nxt = finalize(load_raw(batch + stride));
+    prefetch(nxt);
+    RawDesc ahead = load_raw(batch + 2u * stride);
 
     for (; batch < n_batches; batch += stride) {
-        BatchDesc nn;
-        if (STAGES == 2) {
-            issue(nxt, stage ^ 1u);                 // descriptors were fetched one iteration ago
-            nn = load_desc(batch + 2u * stride);    // consumed next iteration
-        }
+        if (STAGES == 2) issue(nxt, stage ^ 1u);
         uint32_t st = st_start;
         const uint32_t len = cur.e - cur.s;
         if (cur.fits) {
@@ -319,13 +388,11 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
             local_count += __popc(m);
         }
         __syncwarp();   // every lane is done reading the slot before it is refilled
-        if (STAGES == 2) {
-            cur = nxt; nxt = nn; stage ^= 1u;
-        } else {
-            cur = nxt;
-            issue(cur, 0);
-            nxt = load_desc(batch + 2u * stride);
-        }
+        cur = nxt;
+        if (STAGES == 2) stage ^= 1u; else issue(cur, 0);
+        nxt = finalize(ahead);
+        prefetch(nxt);
+        ahead = load_raw(batch + 3u * stride);
     }
     if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
 }

@@ -158,6 +158,7 @@ def main():
     run_soa("extra_tier1_regexset_60_25M", F.REGEX_SET, r60, False, False, 25_000_000, p10k[:20], out)
     run_soa("cfg5a_1000_fixed_25M", F.FIXED_SET, p1k, False, False, 25_000_000, p1k[:50], out)
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
+    run_soa("extra_cfg3_10k_20mers_revcomp_25M", F.FIXED_SET, p10k, False, True, 25_000_000, p10k[:200], out)
     if not ONLY or ONLY in "cfg5b_names":
         run_names(out)
     if not ONLY or ONLY in "k0_index_only":
