@@ -278,7 +278,7 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
     if (names) {
         std::lock_guard<std::mutex> lock(const_cast<fqg_matcher*>(m)->mu);
         const DeviceTables& t = const_cast<fqg_matcher*>(m)->dev[c->device];
-        nv.slots = t.slots; nv.slot_off = t.slot_off; nv.pool = t.pool; nv.mask = m->names.n_slots - 1;
+        nv.slots = t.slots; nv.slot_off = t.slot_off; nv.pool = t.pool; nv.mask = m->names.n_slots / 4 - 1;
     }
     const int n_streams = mode == FQG_PAIRED ? 2 : 1;
     const bool check_ids = mode != FQG_SINGLE;
@@ -652,13 +652,25 @@ int fqg_match_bases_device(fqg_ctx* c, const fqg_matcher* m, const uint8_t* d_ba
                            uint64_t n_reads, uint32_t* d_mask_out, const uint32_t* d_or_mask, uint64_t* d_count, uint32_t avg_read_len,
                            void* stream) {
     if (!c || !m || !d_mask_out || (n_reads && (!d_bases || !d_start || !d_end))) return fail(FQG_E_INVALID_ARG, "NULL argument");
-    if (m->kind == FQG_NAMES) return fail(FQG_E_INVALID_ARG, "read-name matchers need headers: use the FASTQ entry points");
     if (n_reads >= (1ull << 32)) return fail(FQG_E_TOO_LARGE, "more than 2^32-1 reads in one call; split the batch");
     if (n_reads == 0) return FQG_OK;
     CU_TRY(cudaSetDevice(c->device));
     DeviceDfa dd;
     int rc = get_device_dfa(c, m, &dd);
     if (rc) return rc;
+    if (m->kind == FQG_NAMES) {      // the spans are header lines (without '@'), not sequences
+        NamesView nv;
+        {
+            std::lock_guard<std::mutex> lock(const_cast<fqg_matcher*>(m)->mu);
+            const DeviceTables& t = const_cast<fqg_matcher*>(m)->dev[c->device];
+            nv.slots = t.slots; nv.slot_off = t.slot_off; nv.pool = t.pool; nv.mask = m->names.n_slots / 4 - 1;
+        }
+        SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
+                   (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr};
+        CU_TRY(launch_match_names_soa(nv, b, c->sm_count, (cudaStream_t)stream));
+        g_launches++;
+        return FQG_OK;
+    }
     if (m->split_lit) {
         // pass 1: literal members -> "found" bits in d_mask_out; pass 2: regex members, OR those bits in before invert
         DeviceDfa d1, d2;

@@ -58,7 +58,7 @@ struct NamesView {
     const uint64_t* slots = nullptr;
     const uint32_t* slot_off = nullptr;
     const uint8_t* pool = nullptr;
-    uint32_t mask = 0;     // n_slots - 1
+    uint32_t mask = 0;     // n_buckets - 1 (a bucket = four consecutive slots = 32 bytes)
 };
 struct FastqArgs {
     const uint8_t* buf;            // device, readable 16 bytes past nbytes
@@ -80,6 +80,8 @@ struct FastqArgs {
     uint32_t* seq_len;              // ... and its length without line terminator
     uint64_t span_cap;
 };
+// -N over SoA headers: spans are header lines without '@'; the id ends at the first space (matcher.rs:631-638)
+cudaError_t launch_match_names_soa(const NamesView& nv, const SoaBatch& b, int sm_count, cudaStream_t stream);
 uint32_t fastq_tile_bytes();
 uint32_t fastq_overlap_bytes();
 // names: read-name lookup instead of an automaton; index_only: no matching at all, only parse / validate / index (K0)

@@ -18,7 +18,7 @@
 // inside tile+overlap (reads longer than ~1 kb) fall back to a global-memory walk.
 #include "dfa_device.cuh"
 #include "kernels.hpp"
-#include "names_hash.h"
+#include "names_device.cuh"
 
 namespace fqg {
 namespace {
@@ -55,40 +55,12 @@ __device__ __forceinline__ uint32_t newline_nibble(uint32_t w) {
 
 struct NamesProbe {
     NamesView nv;
-    // exact membership of id bytes [p, p+len) (shared memory) in the name set
+    // exact membership of id bytes [p, p+len) in the name set; p is a shared-window address / a global pointer
     __device__ bool contains_shared(uint32_t p, uint32_t len) const {
-        uint64_t h = 0x9E3779B97F4A7C15ull ^ len;
-        for (uint32_t i = 0; i < len; i++) h = (h ^ lds_u8_volatile(p + i)) * 0x100000001B3ull;
-        h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
-        const uint64_t want = fqg_slot_word(h, len);
-        uint32_t i = (uint32_t)(h >> 32) & nv.mask;
-        for (;;) {
-            const uint64_t s = __ldg(nv.slots + i);
-            if (s == 0) return false;
-            if (s == want) {
-                const uint8_t* q = nv.pool + __ldg(nv.slot_off + i);
-                uint32_t k = 0;
-                while (k < len && __ldg(q + k) == lds_u8_volatile(p + k)) k++;
-                if (k == len) return true;
-            }
-            i = (i + 1) & nv.mask;
-        }
+        return names_contains(nv, p, len, [](uint32_t a) { return lds_u32_volatile(a); });
     }
     __device__ bool contains_global(const uint8_t* p, uint32_t len) const {
-        uint64_t h = fqg_name_hash(p, len);
-        const uint64_t want = fqg_slot_word(h, len);
-        uint32_t i = (uint32_t)(h >> 32) & nv.mask;
-        for (;;) {
-            const uint64_t s = __ldg(nv.slots + i);
-            if (s == 0) return false;
-            if (s == want) {
-                const uint8_t* q = nv.pool + __ldg(nv.slot_off + i);
-                uint32_t k = 0;
-                while (k < len && __ldg(q + k) == p[k]) k++;
-                if (k == len) return true;
-            }
-            i = (i + 1) & nv.mask;
-        }
+        return names_contains(nv, reinterpret_cast<uintptr_t>(p), len, [](uintptr_t a) { return __ldg(reinterpret_cast<const uint32_t*>(a)); });
     }
 };
 

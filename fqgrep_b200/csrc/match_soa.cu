@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include "dfa_device.cuh"
+#include "names_device.cuh"
 #include "kernels.hpp"
 
 namespace fqg {
@@ -567,6 +568,65 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
 }
 
 }  // namespace
+
+// ---- read-name lookup over SoA headers (-N) ------------------------------------------------------------------------
+// QueryNameMatcher::read_match (/root/reference/src/lib/matcher.rs:631-638): id = header up to the first space,
+// selected iff (id in set) != invert.  One read per thread, ids read straight from global memory (a warp's 32 headers
+// are contiguous, so its loads share cache lines); the table probe is one random 8-byte L2 read per read.
+// Algorithmic bytes per read: header + 4 (offset) + 8 (one slot) + 1/8 (result).
+namespace {
+__global__ void __launch_bounds__(256) match_names_soa_kernel(SoaBatch b, NamesView nv) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_batches = (b.n_reads + 31u) >> 5;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
+    auto load = [](uintptr_t p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); };
+    unsigned long long local_count = 0;
+    for (uint32_t batch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < n_batches; batch += warps) {
+        const uint32_t r = batch * 32u + lane;
+        bool found = false;
+        if (r < b.n_reads) {
+            const uint32_t s = __ldg(b.start + r), e = __ldg(b.end + r);
+            const uintptr_t a = base + s;
+            const uint32_t n = e > s ? e - s : 0u;
+            // one pass: hash the header word by word until a word holds a space, which ends the id
+            uint64_t h = fqg_name_hash_init();
+            uint32_t id_len = n;
+            for (IdWords<uintptr_t, decltype(load)> it(a, n, load); it.more();) {
+                const uint32_t pos = it.pos, w = it.next(), x = w ^ 0x20202020u;
+                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);      // 0x80 where a byte is ' '
+                if (z) {                                  // (the zero padding past the end is never a space)
+                    const uint32_t k = ((uint32_t)__ffs((int)z) - 1u) >> 3;
+                    id_len = pos + k;
+                    if (k) h = fqg_name_hash_word(h, w & ((1u << (8u * k)) - 1u));
+                    break;
+                }
+                h = fqg_name_hash_word(h, w);
+            }
+            h = fqg_name_hash_finish(h, id_len);
+            found = names_probe(nv, a, id_len, load, h);
+        }
+        const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
+        uint32_t m = __ballot_sync(kFullMask, sel);
+        if (lane == 0) {
+            if (b.or_mask) m |= __ldg(b.or_mask + batch);
+            b.mask_out[batch] = m;
+            local_count += __popc(m);
+        }
+    }
+    if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
+}
+}  // namespace
+
+cudaError_t launch_match_names_soa(const NamesView& nv, const SoaBatch& b, int sm_count, cudaStream_t stream) {
+    const uint32_t n_batches = (b.n_reads + 31u) / 32u;
+    if (!n_batches) return cudaSuccess;
+    uint32_t grid = (n_batches + 7u) / 8u;
+    const uint32_t cap = (uint32_t)sm_count * 8u * 4u;        // 8 resident CTAs of 256 threads per SM, 4 waves' worth of slack
+    if (grid > cap) grid = cap;
+    match_names_soa_kernel<<<grid, 256, 0, stream>>>(b, nv);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
     // Measured on B200 (profiles/README.md): the ring variant matches the double-buffered kernel on the issue-bound

@@ -1,4 +1,4 @@
-// names_hash.h -- the one hash shared by the host table builder and the device probe kernel.
+// names_hash.h -- the one hash shared by the host table builder and the device probe kernels.
 #pragma once
 #include <stdint.h>
 
@@ -8,14 +8,26 @@
 #define FQG_HD inline
 #endif
 
-// 64-bit multiply-xorshift over bytes; cheap in device integer ops, avalanche finish.
+// The id is hashed four bytes at a time: little-endian 32-bit words, the last one zero-padded; the length goes in at
+// the end (ids are found by scanning for the first space, so the length is not known up front).  Multiply-xorshift
+// rounds: cheap in device integer ops, avalanche finish.
+FQG_HD uint64_t fqg_name_hash_init() { return 0x9E3779B97F4A7C15ull; }
+FQG_HD uint64_t fqg_name_hash_word(uint64_t h, uint32_t w) {
+    h = (h ^ w) * 0x9FB21C651E98DF25ull;
+    return h ^ (h >> 32);
+}
+FQG_HD uint64_t fqg_name_hash_finish(uint64_t h, uint32_t n) {
+    h = (h ^ n) * 0xD6E8FEB86659FD93ull;
+    return h ^ (h >> 32);
+}
 FQG_HD uint64_t fqg_name_hash(const uint8_t* p, uint32_t n) {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ n;
-    for (uint32_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001B3ull;
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ull;
-    h ^= h >> 32;
-    return h;
+    uint64_t h = fqg_name_hash_init();
+    for (uint32_t i = 0; i < n; i += 4) {
+        uint32_t w = 0;
+        for (uint32_t k = 0; k < 4 && i + k < n; k++) w |= (uint32_t)p[i + k] << (8 * k);
+        h = fqg_name_hash_word(h, w);
+    }
+    return fqg_name_hash_finish(h, n);
 }
 // names longer than 2^24-1 bytes are rejected at construction
 FQG_HD uint64_t fqg_slot_word(uint64_t h, uint32_t len) { return ((h | (1ull << 63)) & 0xFFFFFFFFFF000000ull) | (len & 0xFFFFFFu); }

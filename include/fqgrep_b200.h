@@ -114,7 +114,9 @@ void fqg_free_pinned(void* p);
  *                      (pair rule `read_match(r1) || read_match(r2)`, src/main.rs:749-755)
  *   d_count            optional device uint64, incremented by the number of set bits written
  *   avg_read_len       hint used to size shared-memory staging (0 = 150)
- *   stream             cudaStream_t as void* (NULL = the legacy default stream, like any CUDA API).  Asynchronous. */
+ *   stream             cudaStream_t as void* (NULL = the legacy default stream, like any CUDA API).  Asynchronous.
+ * With a FQG_NAMES matcher (QueryNameMatcher::read_match, matcher.rs:631-638) the spans are the records' HEADER lines
+ * without the leading '@' instead of their bases; the id ends at the first space, as seq_io's id_bytes() has it. */
 int fqg_match_bases_device(fqg_ctx* ctx, const fqg_matcher* m, const uint8_t* d_bases, const uint32_t* d_start, const uint32_t* d_end,
                            uint64_t n_reads, uint32_t* d_mask_out, const uint32_t* d_or_mask, uint64_t* d_count, uint32_t avg_read_len,
                            void* stream);

@@ -898,7 +898,16 @@ int64_t fqo_grep(const fqo_matcher *m, int mode, const uint8_t *r1, size_t n1, c
 
 /* SoA entry: bases[offs[i]..offs[i+1]) for i<n; mask bit i = read_match. Header-less, so not for NAMES. */
 typedef struct { const fqo_matcher *m; const uint8_t *bases; const uint64_t *offs; size_t lo, hi; uint8_t *flag; } SJob;
-static void *sjob_run(void *arg) { SJob *j = arg; for (size_t i = j->lo; i < j->hi; i++) j->flag[i] = (uint8_t)fqo_read_match(j->m, (const uint8_t *)"", 0, j->bases + j->offs[i], j->offs[i + 1] - j->offs[i]); return NULL; }
+/* SoA spans are sequences, except for a read-name matcher where they are header lines without '@' (matcher.rs:631-638) */
+static void *sjob_run(void *arg) {
+    SJob *j = arg;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        const uint8_t *p = j->bases + j->offs[i];
+        size_t n = j->offs[i + 1] - j->offs[i];
+        j->flag[i] = (uint8_t)(j->m->kind == FQO_NAMES ? fqo_read_match(j->m, p, n, (const uint8_t *)"", 0) : fqo_read_match(j->m, (const uint8_t *)"", 0, p, n));
+    }
+    return NULL;
+}
 int64_t fqo_match_soa(const fqo_matcher *m, const uint8_t *bases, const uint64_t *offs, size_t n, int threads, uint8_t *flags_out) {
     if (threads < 1) threads = 1; if (threads > 256) threads = 256;
     pthread_t th[256]; SJob jobs[256];

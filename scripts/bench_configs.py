@@ -117,6 +117,44 @@ def run_names(out, n=20_000_000, n_names=1_000_000):
 ONLY = sys.argv[2] if len(sys.argv) > 2 else ""
 
 
+def run_names_soa(out, n=50_000_000, n_names=1_000_000):
+    """cfg5b on SoA headers: ids r%010d back to back (11 B each) + u32 offsets; SURVEY 8(d): header + 4 + 8 + 1/8 B per read."""
+    idl = 11
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    hb = torch.empty((n, idl), dtype=torch.uint8, device=dev)
+    hb[:, 0] = ord("r")
+    for k in range(10):
+        hb[:, 10 - k] = ((idx // (10 ** k)) % 10 + 48).to(torch.uint8)
+    del idx
+    offs = (torch.arange(n + 1, device=dev, dtype=torch.int64) * idl).to(torch.int32)
+    rng = np.random.default_rng(5)
+    chosen = rng.choice(n, int(n_names * 0.9), replace=False)
+    names = ["r%010d" % i for i in chosen] + ["r%010d" % (n + i) for i in range(n_names - chosen.size)]
+    m = F.Matcher(F.NAMES, names)
+    words = n // 32 + 2
+    mask = torch.zeros(words, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def once():
+        rc = L.fqg_match_bases_device(ctx, m._h, hb.data_ptr(), offs.data_ptr(), offs.data_ptr() + 4, n, mask.data_ptr(), None, cnt.data_ptr(), idl, sp)
+        assert rc == 0, _ffi.last_error()
+    for _ in range(3):
+        once()
+    cnt.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    sel = int(cnt.item()) // 5
+    out["cfg5b_names_1M_ids_soa"] = {"reads": n, "ms": ms, "greads_s": n / (ms / 1e3) / 1e9, "roofline_frac": (idl + 12.125) * n / (ms / 1e3) / 1e9 / PEAK,
+                                     "selected": sel, "expected_selected": int(chosen.size), "parity_ok": sel == int(chosen.size)}
+    print("cfg5b_soa", json.dumps(out["cfg5b_names_1M_ids_soa"]), flush=True)
+
+
 def run_index_only(out, n=20_000_000):
     """K0 alone: parse + validate + index, no matching: the parse floor of the fused kernel."""
     tb = gen(n, 1, [], 0.0, 0, fastq=1)
@@ -161,6 +199,7 @@ def main():
     run_soa("extra_cfg3_10k_20mers_revcomp_25M", F.FIXED_SET, p10k, False, True, 25_000_000, p10k[:200], out)
     if not ONLY or ONLY in "cfg5b_names":
         run_names(out)
+        run_names_soa(out)
     if not ONLY or ONLY in "k0_index_only":
         run_index_only(out)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -270,3 +270,34 @@ def test_fuzz_random_pattern_sets_on_ragged_mixed_alphabet_reads():
         except O.OracleError:
             continue
         check(kind, pats, inv, rc, bases, offs)
+
+
+def test_names_over_soa_headers():
+    """QueryNameMatcher::read_match (matcher.rs:631-638) through the SoA entry point: the spans are header lines, the id
+    ends at the first space.  Checked against the oracle and against plain Python set membership."""
+    rng = random.Random(11)
+    alphabet = "abcXYZ0189._:/-"
+    ids = ["".join(rng.choice(alphabet) for _ in range(rng.choice((0, 1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 31, 40)))) for _ in range(6000)]
+    ids += ["read1", "read1_extra", "SRR001666.1", "r0000000001", "r0000000002"]
+    chosen = sorted(set(rng.sample(ids, 2500)) | {"read1", "SRR001666.1"})
+    heads = []
+    for i in range(40_037):        # ragged: not a multiple of 32
+        h = rng.choice(ids)
+        k = rng.random()
+        if k < 0.3:
+            h += " " + "".join(rng.choice(alphabet + " ") for _ in range(rng.randrange(0, 20)))      # description after a space
+        elif k < 0.35:
+            h = h[: max(0, len(h) - 1)]          # near miss (a prefix)
+        elif k < 0.4:
+            h += "x"                             # near miss (an extension)
+        heads.append(h.encode())
+    blob = np.frombuffer(b"".join(heads), dtype=np.uint8)
+    offs = np.zeros(len(heads) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(h) for h in heads])
+    want = np.array([h.split(b" ")[0].decode() in set(chosen) for h in heads])
+    for inv in (False, True):
+        m = F.Matcher(F.NAMES, chosen, opts(inv, False))
+        bits, cnt = m.match_bases(blob, offs)
+        ocnt, flags = O.Matcher(F.NAMES, chosen, inv, False).match_soa(blob, offs, threads=4)
+        assert (bits == (want != inv)).all()
+        assert (bits == (flags != 0)).all() and cnt == ocnt == int((want != inv).sum())
