@@ -6,6 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfqgrep_b200.so")
+CLI = os.path.join(HERE, "fqgrep-b200")      # the reference's command line over the device path (csrc/cli.cc)
 SOURCES = ["api.cu", "match_soa.cu", "match_fastq.cu", "synth.cu", "regex_compile.cc", "ac_build.cc", "gram_filter.cc", "names.cc", "fastq_host.cc", "input_host.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -15,7 +16,11 @@ def _stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "fqgrep_b200.h"), __file__]
+    if not os.path.exists(CLI):
+        return True
+    t = min(t, os.path.getmtime(CLI))
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, "fqgrep_b200.h"), os.path.join(inc, "fqgrep_b200.hpp"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -41,6 +46,10 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % src)
     cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz"]
     subprocess.check_call(cmd)
+    # host-only C++ above the C ABI: links the library by relative rpath so the pair travels together
+    cxx = os.environ.get("CXX", "g++")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"), os.path.join(CSRC, "cli.cc"),
+                           "-o", CLI, "-L", HERE, "-lfqgrep_b200", "-Wl,-rpath,$ORIGIN"])
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
