@@ -315,7 +315,8 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
             if ((rc = fq_ensure(c, i, S_BUF, n + 64, &p))) return rc;
             s.d = (const uint8_t*)p;
         } else s.d = s.src;
-        if ((rc = fq_ensure(c, i, S_STATE, (size_t)s.tiles * 8 + 8, &p))) return rc;
+        // look-back state: one word per tile, then one per segment of 32 tiles
+        if ((rc = fq_ensure(c, i, S_STATE, ((size_t)s.tiles + s.tiles / 32 + 2) * 8, &p))) return rc;
         s.state = (unsigned long long*)p;
         if ((rc = fq_ensure(c, i, S_COUNTERS, kMaxLaunches * 4, &p))) return rc;
         s.counters = (uint32_t*)p;
@@ -338,7 +339,7 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
     CU_TRY(cudaEventRecord(c->ev[0], cs));
     CU_TRY(cudaMemcpyAsync(ctl, ctl_init, sizeof ctl_init, cudaMemcpyHostToDevice, cs));
     for (int i = 0; i < n_streams; i++) {
-        CU_TRY(cudaMemsetAsync(sp[i].state, 0, (size_t)sp[i].tiles * 8 + 8, cs));
+        CU_TRY(cudaMemsetAsync(sp[i].state, 0, ((size_t)sp[i].tiles + sp[i].tiles / 32 + 2) * 8, cs));
         CU_TRY(cudaMemsetAsync(sp[i].counters, 0, kMaxLaunches * 4, cs));
         CU_TRY(cudaMemsetAsync(sp[i].mask, 0, sp[i].mask_words * 4, cs));
     }
@@ -350,7 +351,7 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
         FastqArgs a{};
         a.buf = s.d; a.nbytes = s.n; a.virtual_final_nl = 1;
         a.tile_first = s.tiles_done; a.tile_count = tile_end - s.tiles_done;
-        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.lines_out = ctl + 3 + i;
+        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_state = s.state + s.tiles + 1; a.lines_out = ctl + 3 + i;
         a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
         a.count = mode == FQG_SINGLE ? ctl + 1 : nullptr;
         a.err = ctl + 0;

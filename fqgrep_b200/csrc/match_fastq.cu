@@ -201,29 +201,50 @@ __device__ __forceinline__ uint32_t region_newlines(const uint32_t* s_bitmap, co
     return (region & 31u) == 0 ? s_pre[region >> 5] : s_pre[region >> 5] + __popc(s_bitmap[region >> 5]);
 }
 
-// decoupled look-back by one warp: number of newlines before tile t; publishes this tile's aggregate / inclusive prefix
+// Decoupled look-back by one warp: number of newlines before tile t; publishes this tile's aggregate / inclusive prefix.
+// Two levels.  Every resident tile group works on its own tile at about the same time (1184 tiles in flight), so a flat
+// look-back finds nothing but aggregates for a whole wave and needs wave/32 dependent L2 round trips per tile -- measured,
+// that chain WAS the kernel's run time.  Tiles are therefore grouped in segments of 32: the tile that closes a segment
+// publishes the segment's aggregate as soon as it has seen its 31 predecessors' aggregates, and a look-back sums its own
+// segment first (one round), then hops 32 segments (1024 tiles) per round.  State words: flag << 62 | value, flag 1 =
+// aggregate, 2 = inclusive prefix.  Tiles are handed out in order, so every state a tile waits for belongs to a group that
+// is already running and publishes it without waiting for anything later: no circular wait.
 __device__ __forceinline__ unsigned long long lookback(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
+    const unsigned long long kValue = (1ull << 62) - 1;
+    auto poll = [](const unsigned long long* p) {
+        unsigned long long st;
+        do { st = *reinterpret_cast<const volatile unsigned long long*>(p); } while ((st >> 62) == 0);
+        return st;
+    };
+    // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix
+    auto fold = [&](unsigned long long st, bool use, bool& hit_prefix) {
+        const uint32_t has_prefix = __ballot_sync(kFullMask, use && (st >> 62) == 2);
+        const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
+        unsigned long long v = (use && lane <= first) ? (st & kValue) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+        hit_prefix = has_prefix != 0;
+        return v;
+    };
     unsigned long long excl = 0;
+    const uint32_t r = t & 31u;                    // predecessors inside this tile's own segment
     if (t > 0) {
         if (lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
-        int32_t look = (int32_t)t - 1;
-        for (;;) {
-            const int32_t idx = look - (int32_t)lane;
-            unsigned long long st = (2ull << 62);   // before the stream: prefix 0
-            if (idx >= 0) {
-                do { st = *reinterpret_cast<volatile unsigned long long*>(a.tile_state + idx); } while ((st >> 62) == 0);
-            }
-            const uint32_t has_prefix = __ballot_sync(kFullMask, (st >> 62) == 2);
-            const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
-            unsigned long long v = lane <= first ? (st & ((1ull << 62) - 1)) : 0ull;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
-            excl += v;
-            if (has_prefix) break;
-            look -= 32;
+        bool done = false;
+        const bool mine = lane < r;
+        excl = fold(mine ? poll(a.tile_state + (t - 1u - lane)) : 0ull, mine, done);
+        if (r == 31u && !done && lane == 0) atomicExch(a.seg_state + (t >> 5), (1ull << 62) | (excl + agg));
+        int32_t seg = (int32_t)(t >> 5) - 1;       // nearest earlier segment
+        while (!done) {
+            const int32_t idx = seg - (int32_t)lane;
+            excl += fold(idx >= 0 ? poll(a.seg_state + idx) : (2ull << 62), true, done);      // before the stream: prefix 0
+            seg -= 32;
         }
     }
-    if (lane == 0) atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
+    if (lane == 0) {
+        atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
+        if (r == 31u) atomicExch(a.seg_state + (t >> 5), (2ull << 62) | (excl + agg));
+    }
     return excl;
 }
 
@@ -400,6 +421,14 @@ __global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, Devic
                 const uint32_t bytes = (g.real_avail + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
+                // Tiles are handed out in order, so the tile one full wave ahead (one per resident group) is the one some
+                // group will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~24 MB) so that copy
+                // only pays L2 latency.  Each group has a single tile buffer, hence no other way to keep HBM busy.
+                const uint32_t ahead = s_misc[40] + gridDim.x * (blockDim.x / THREADS);
+                if (ahead < a.tile_count) {
+                    const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
+                    if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
+                }
                 // one thread polls the transaction barrier; the rest of the group sleeps on the (hardware) named barrier
                 // instead of spinning on try_wait and stealing issue slots from the other groups of the SM
                 mbar_wait(bar, phase);
