@@ -237,7 +237,7 @@ def main():
         tj = json.load(open(tp))
         if abs(tj.get("reads_per_launch", 0) - reads_per_launch) < 1:
             traffic = tj["dram_bytes_per_launch"]
-    roofline = {"bound": "hbm", "kernel": "match_soa_kernel<tier0,2-stage>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "match_soa_kernel<tier0,1 slot + L2 prefetch>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": traffic,
                 "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ, "reads_per_launch": reads_per_launch, "launch_ms": launch_ms}
 
