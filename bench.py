@@ -217,8 +217,20 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches_timed = L.fqg_kernel_launches() - l0
-    clocks = sampler.stop(t_from, time.perf_counter()) if rank == 0 else None
+    t_to = time.perf_counter()
     selected = int(count.item())
+    # The timed region lasts tens of milliseconds, i.e. one or two nvidia-smi samples.  Keep the identical load running
+    # (untimed) for another ~0.4 s so that the clock / throttle report rests on more than that; both counts are reported.
+    clocks = None
+    if rank == 0:
+        t_probe = time.perf_counter()
+        while time.perf_counter() - t_probe < 0.4:
+            step()
+            torch.cuda.synchronize()
+        in_region = len([1 for t, r in sampler.rows if t_from <= t <= t_to and r and r[0].isdigit()])
+        clocks = sampler.stop(t_from, time.perf_counter())
+        clocks["samples_in_timed_region"] = in_region
+        clocks["note"] = "samples = timed region + 0.4 s of the same steps run untimed right after it"
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -8,4 +8,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $CMD > gpurun_out/prof_plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:match_soa_kernel -s 2 -c 2 -o gpurun_out/prof_soa_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:match_fastq_kernel -s 2 -c 2 -o gpurun_out/prof_fastq_$TAG -f $CMD > gpurun_out/ncu_fullq_$TAG.log 2>&1
-tail -3 gpurun_out/ncu_full_$TAG.log gpurun_out/ncu_fullq_$TAG.log
+tail -n 3 gpurun_out/ncu_full_$TAG.log; tail -n 3 gpurun_out/ncu_fullq_$TAG.log
