@@ -366,6 +366,10 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
 
     for (; batch < n_batches; batch += stride) {
         if (STAGES == 2) issue(nxt, stage ^ 1u);
+        // mate / split-set masks of this batch: requested now, consumed after the walk (an L2/HBM round trip otherwise
+        // sits between the walk and the result store of every batch)
+        const uint32_t or_word = b.or_mask ? __ldg(b.or_mask + batch) : 0u;
+        const uint32_t pre_word = b.pre_or_mask ? __ldg(b.pre_or_mask + batch) : 0u;
         uint32_t st = st_start;
         const uint32_t len = cur.e - cur.s;
         if (cur.fits) {
@@ -380,11 +384,11 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
         }
         const uint32_t r = batch * 32u + lane;
         bool found = st >= st_accept;
-        if (b.pre_or_mask) found |= ((__ldg(b.pre_or_mask + batch) >> lane) & 1u) != 0;     // split pattern sets, see api.cu
+        found |= ((pre_word >> lane) & 1u) != 0;      // split pattern sets, see api.cu
         const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
         uint32_t m = __ballot_sync(kFullMask, sel);
         if (lane == 0) {
-            if (b.or_mask) m |= __ldg(b.or_mask + batch);
+            m |= or_word;
             b.mask_out[batch] = m;
             local_count += __popc(m);
         }
@@ -481,6 +485,8 @@ match_soa_ring_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t t
         if (slot2 >= n_slots) { slot2 -= n_slots; use2++; }
         const uint32_t batch2 = gbatch(k + nwarps);
         const BatchDesc nxt = load_desc(batch2);
+        const uint32_t or_word = b.or_mask ? __ldg(b.or_mask + batch) : 0u;            // consumed after the walk
+        const uint32_t pre_word = b.pre_or_mask ? __ldg(b.pre_or_mask + batch) : 0u;
 
         mbar_wait(full_sa + slot * 8u, use & 1u);
         uint32_t st = st_start;
@@ -498,11 +504,11 @@ match_soa_ring_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t t
 
         const uint32_t r = batch * 32u + lane;
         bool found = st >= st_accept;
-        if (b.pre_or_mask) found |= ((__ldg(b.pre_or_mask + batch) >> lane) & 1u) != 0;     // split pattern sets, see api.cu
+        found |= ((pre_word >> lane) & 1u) != 0;        // split pattern sets, see api.cu
         const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
         uint32_t m = __ballot_sync(kFullMask, sel);
         if (lane == 0) {
-            if (b.or_mask) m |= __ldg(b.or_mask + batch);
+            m |= or_word;
             b.mask_out[batch] = m;
             local_count += __popc(m);
         }
