@@ -12,11 +12,13 @@
 //   * a warp owns a batch of 32 consecutive reads.  Their bytes are contiguous in HBM, so ONE bulk async copy
 //     (cp.async.bulk global->shared, the TMA engine, completion on an mbarrier) brings the 16 B-aligned span
 //     into the warp's private smem slot -- fully coalesced DRAM traffic, no register staging;
-//   * double-buffered per warp: the copy of batch k+1 is in flight while the 32 lanes walk batch k, one read
-//     per lane, out of shared memory (aligned 32-bit LDS + funnel shift, 4 bases per load);
+//   * ONE slot per warp (32 resident warps for 150-base reads): while the 32 lanes walk batch k, one read per lane,
+//     out of shared memory (aligned 32-bit LDS + funnel shift, 4 bases per load), batch k+1 is pulled into L2 with
+//     cp.async.bulk.prefetch.L2, so the copy issued when the slot frees only pays L2 latency; the offsets of a batch
+//     are requested two batches ahead.  (A second slot per warp, or a CTA-wide ring of slots, leaves room for
+//     fewer warps and measured slower on every tier.)
 //   * epilogue: ballot -> one mask word per batch (optionally OR-ed with the mate's mask: the pair rule of
 //     src/main.rs:749-755), popcount accumulated per warp and added to the global count once.
-#include <cstdlib>
 #include <type_traits>
 
 #include "dfa_device.cuh"
@@ -402,150 +404,6 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
 }
 
-// ---- ring variant (tiers 0-2): W warps share S > W staging slots ----------------------------------------------------
-// The double-buffered kernel above keeps two private slots per warp, one of which only holds prefetched bytes, so
-// shared memory (not registers) caps the SM at 22 warps for 150-base reads.  Here the slots form a CTA-wide ring: batch
-// k of the CTA uses slot k % S and is walked by warp k % W.  A warp issues the bulk copy of its NEXT batch only when
-// it is ~60 % through the current one, so a slot sits idle for ~0.4 batch times instead of a whole one and S ~ 1.45 W
-// slots feed W warps: more resident warps per SM for the same shared memory.  full[s] (transaction barrier) says
-// "slot s holds batch data", empty[s] says "its reader is done"; both advance one phase per use of the slot.
-template <int TIER>
-__global__ void __launch_bounds__(1024, 1)
-match_soa_ring_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_smem_bytes, uint32_t n_slots, uint32_t split) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem);
-    uint8_t* s_cls = smem + table_smem_bytes;
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_cls + 256);
-    uint64_t* s_empty = s_full + 64;
-    uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_empty + 64);
-    s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
-
-    if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
-    if (TIER == 2)
-        for (uint32_t i = threadIdx.x; i < dfa.hot_entries; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tab)[i] = __ldg(reinterpret_cast<const uint32_t*>(dfa.table) + i);
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
-    if (threadIdx.x < n_slots) {
-        mbar_init(smem_addr(&s_full[threadIdx.x]), 1);
-        mbar_init(smem_addr(&s_empty[threadIdx.x]), 1);
-    }
-    mbar_fence_init();
-    __syncthreads();
-
-    DfaView<TIER> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), TIER == 2 ? dfa.hot_entries : 0u};
-    const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;
-    const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
-    const uint32_t n_batches = (b.n_reads + 31u) >> 5;
-    const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
-    const uint32_t slots_sa = smem_addr(s_slots), full_sa = smem_addr(s_full), empty_sa = smem_addr(s_empty);
-
-    auto load_desc = [&](uint32_t batch) -> BatchDesc {
-        BatchDesc d;
-        const uint32_t r = batch * 32u + lane;
-        const bool valid = batch < n_batches && r < b.n_reads;
-        d.s = valid ? __ldg(b.start + r) : 0u;
-        d.e = valid ? __ldg(b.end + r) : 0u;
-        if (d.e < d.s) d.e = d.s;
-        const uint32_t lo = __reduce_min_sync(kFullMask, valid ? d.s : 0xFFFFFFFFu);
-        const uint32_t hi = __reduce_max_sync(kFullMask, valid ? d.e : 0u);
-        if (hi > lo) {
-            const uintptr_t a_lo = (base + lo) & ~uintptr_t(15), a_hi = (base + hi + 15) & ~uintptr_t(15);
-            d.src = a_lo;
-            d.off = (uint32_t)(base + d.s - a_lo);
-            d.fits = (a_hi - a_lo) <= (uintptr_t)(slot_bytes - 16u);
-            d.bytes = d.fits ? (uint32_t)(a_hi - a_lo) : 0u;
-        } else {
-            d.src = base; d.off = 0; d.bytes = 0; d.fits = true;
-        }
-        return d;
-    };
-    // every batch is one "use" of its slot, with or without bytes, so barrier phases stay in step with the batch index
-    auto fill = [&](const BatchDesc& d, uint32_t slot) {
-        if (lane == 0) {
-            const uint32_t bar = full_sa + slot * 8u;
-            if (d.fits && d.bytes) {
-                mbar_arrive_expect_tx(bar, d.bytes);
-                bulk_copy_g2s(slots_sa + slot * slot_bytes, reinterpret_cast<const void*>(d.src), d.bytes, bar);
-            } else mbar_arrive(bar);
-        }
-    };
-    auto gbatch = [&](uint32_t k) -> uint32_t {
-        const uint64_t g = (uint64_t)blockIdx.x + (uint64_t)k * gridDim.x;
-        return g < n_batches ? (uint32_t)g : n_batches;      // n_batches = "none"
-    };
-
-    unsigned long long local_count = 0;
-    uint32_t k = warp, slot = warp, use = 0;                  // warp < n_slots always (host guarantees nwarps <= n_slots)
-    BatchDesc cur = load_desc(gbatch(k));
-    if (gbatch(k) < n_batches) fill(cur, slot);
-    while (gbatch(k) < n_batches) {
-        const uint32_t batch = gbatch(k);
-        // the batch this warp walks next: its slot and use number follow from k + nwarps
-        uint32_t slot2 = slot + nwarps, use2 = use;
-        if (slot2 >= n_slots) { slot2 -= n_slots; use2++; }
-        const uint32_t batch2 = gbatch(k + nwarps);
-        const BatchDesc nxt = load_desc(batch2);
-        const uint32_t or_word = b.or_mask ? __ldg(b.or_mask + batch) : 0u;            // consumed after the walk
-        const uint32_t pre_word = b.pre_or_mask ? __ldg(b.pre_or_mask + batch) : 0u;
-
-        mbar_wait(full_sa + slot * 8u, use & 1u);
-        uint32_t st = st_start;
-        const uint32_t len = cur.e - cur.s, rd = slots_sa + slot * slot_bytes + cur.off;
-        const uint32_t len_a = cur.fits ? (len < split ? len : split) : 0u;
-        if (len_a) st = walk_shared(view, rd, len_a, st);
-
-        if (batch2 < n_batches) {                       // ~60 % through this batch: start the copy of the next one
-            if (use2) mbar_wait(empty_sa + slot2 * 8u, (use2 - 1u) & 1u);
-            fill(nxt, slot2);
-        }
-
-        if (cur.fits) { if (len > len_a) st = walk_shared(view, rd + len_a, len - len_a, st); }
-        else if (len) st = walk_global(view, b.bases + cur.s, len, st_start);
-
-        const uint32_t r = batch * 32u + lane;
-        bool found = st >= st_accept;
-        found |= ((pre_word >> lane) & 1u) != 0;        // split pattern sets, see api.cu
-        const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
-        uint32_t m = __ballot_sync(kFullMask, sel);
-        if (lane == 0) {
-            m |= or_word;
-            b.mask_out[batch] = m;
-            local_count += __popc(m);
-        }
-        __syncwarp();                                   // every lane is done reading the slot
-        if (lane == 0) mbar_arrive(empty_sa + slot * 8u);
-        k += nwarps; slot = slot2; use = use2; cur = nxt;
-    }
-    if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
-}
-
-template <int TIER>
-cudaError_t launch_ring_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
-    const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
-    uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
-    slot = (slot + 127u) & ~127u;
-    const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
-    const uint32_t fixed = table_smem + 256u + 128u * 8u + 128u;
-    const uint32_t budget = 227u * 1024u;
-    if (fixed + 3u * slot > budget) return cudaErrorInvalidConfiguration;      // caller falls back to the double-buffered kernel
-    uint32_t n_slots = (budget - fixed) / slot;
-    if (n_slots > 64u) n_slots = 64u;
-    uint32_t warps = (n_slots * 16u) / 23u;             // S ~ 1.44 W
-    if (warps > 32u) warps = 32u;
-    if (warps < 1u) warps = 1u;
-    const uint32_t smem = fixed + n_slots * slot;
-    auto kern = match_soa_ring_kernel<TIER>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const uint32_t n_batches = (b.n_reads + 31u) / 32u;
-    uint32_t grid = (n_batches + warps - 1u) / warps;
-    if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-    if (grid == 0) return cudaSuccess;
-    const uint32_t split = ((avg * 5u) / 8u) & ~3u;
-    kern<<<grid, warps * 32u, smem, stream>>>(b, dfa, slot, table_smem, n_slots, split);
-    return cudaGetLastError();
-}
-
 template <int TIER, int STAGES>
 cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
     const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
@@ -635,12 +493,6 @@ cudaError_t launch_match_names_soa(const NamesView& nv, const SoaBatch& b, int s
 }
 
 cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
-    // Measured on B200 (profiles/README.md): the ring variant matches the double-buffered kernel on the issue-bound
-    // shared-memory tiers (0.81 vs 0.81) and wins 25 % on the latency-bound L2 tier, so only tier 2 takes it.
-    if (dfa.tier == 2) {
-        cudaError_t e = launch_ring_t<2>(dfa, b, sm_count, stream);
-        if (e != cudaErrorInvalidConfiguration) return e;
-    }
     // One staging slot per warp + the next batch pulled into L2 (cp.async.bulk.prefetch.L2) instead of a second slot:
     // measured on B200 with 150-base reads, 32 resident warps with one slot each beat 22 warps with two
     // (tier 0: 0.83 -> 0.90 of the HBM roofline), because the walk is a dependent chain per lane and more warps hide it.
