@@ -276,7 +276,7 @@ struct BatchDesc {
     bool fits;            // warp-uniform: span fits the slot
 };
 
-template <int TIER, int STAGES>
+template <int TIER>
 __global__ void __launch_bounds__(1024, 1)
 match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -286,7 +286,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem);
     uint8_t* s_cls = smem + table_smem_bytes;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cls + 256);
-    uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_bar + 32 * STAGES);
+    uint8_t* s_slots = reinterpret_cast<uint8_t*>(s_bar + 32);
     s_slots = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_slots) + 127) & ~uintptr_t(127));
 
     if (kSmemTable<TIER>) stage_table(dfa.table, dfa.table_bytes, s_tab, threadIdx.x, blockDim.x);
@@ -299,7 +299,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
     if (lane == 0)
-        for (int s = 0; s < STAGES; s++) mbar_init(smem_addr(&s_bar[warp * STAGES + s]), 1);
+        mbar_init(smem_addr(&s_bar[warp]), 1);
     mbar_fence_init();
     __syncthreads();
 
@@ -307,7 +307,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     GramView gview{smem_addr(s_tab), dfa.gram, reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), dfa.start, dfa.accept_from};
     const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
     const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;
-    uint8_t* my_slots = s_slots + (size_t)warp * STAGES * slot_bytes;
+    uint8_t* my_slot = s_slots + (size_t)warp * slot_bytes;      // this warp's one staging slot
     const uint32_t n_batches = (b.n_reads + 31u) >> 5;
     const uint32_t stride = gridDim.x * nwarps;
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
@@ -342,32 +342,31 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
         }
         return d;
     };
-    auto issue = [&](const BatchDesc& d, uint32_t stage) {
+    auto issue = [&](const BatchDesc& d) {
         if (d.fits && d.bytes && lane == 0) {
-            const uint32_t bar = smem_addr(&s_bar[warp * STAGES + stage]);
+            const uint32_t bar = smem_addr(&s_bar[warp]);
             mbar_arrive_expect_tx(bar, d.bytes);
-            bulk_copy_g2s(smem_addr(my_slots + (size_t)stage * slot_bytes), reinterpret_cast<const void*>(d.src), d.bytes, bar);
+            bulk_copy_g2s(smem_addr(my_slot), reinterpret_cast<const void*>(d.src), d.bytes, bar);
         }
     };
 
     uint32_t batch = blockIdx.x * nwarps + warp;
-    uint32_t phase_bits = 0, stage = 0;
+    uint32_t phase = 0;
     unsigned long long local_count = 0;
 
     BatchDesc cur = finalize(load_raw(batch));
-    issue(cur, 0);
-    // nxt: the batch after cur.  STAGES == 2 copies it into the other slot while cur is walked; STAGES == 1 has no slot
-    // for it and instead pulls its bytes into L2 (126 MB), so the copy issued when the slot frees only pays L2 latency
-    // and the HBM requests in flight are not capped by the staging memory.  ahead: offsets in flight for the batch after nxt.
+    issue(cur);
+    // nxt: the batch after cur.  The warp has no second slot for it; its bytes are pulled into L2 (126 MB) instead, so
+    // the copy issued when the slot frees only pays L2 latency and the HBM requests in flight are not capped by the
+    // staging memory.  ahead: offsets in flight for the batch after nxt.
     auto prefetch = [&](const BatchDesc& d) {
-        if (STAGES == 1 && d.fits && d.bytes && lane == 0) bulk_prefetch_l2(reinterpret_cast<const void*>(d.src), d.bytes);
+        if (d.fits && d.bytes && lane == 0) bulk_prefetch_l2(reinterpret_cast<const void*>(d.src), d.bytes);
     };
     BatchDesc nxt = finalize(load_raw(batch + stride));
     prefetch(nxt);
     RawDesc ahead = load_raw(batch + 2u * stride);
 
     for (; batch < n_batches; batch += stride) {
-        if (STAGES == 2) issue(nxt, stage ^ 1u);
         // mate / split-set masks of this batch: requested now, consumed after the walk (an L2/HBM round trip otherwise
         // sits between the walk and the result store of every batch)
         const uint32_t or_word = b.or_mask ? __ldg(b.or_mask + batch) : 0u;
@@ -376,11 +375,11 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
         const uint32_t len = cur.e - cur.s;
         if (cur.fits) {
             if (cur.bytes) {
-                mbar_wait(smem_addr(&s_bar[warp * STAGES + stage]), (phase_bits >> stage) & 1u);
-                phase_bits ^= 1u << stage;
+                mbar_wait(smem_addr(&s_bar[warp]), phase);
+                phase ^= 1u;
             }
-            if (TIER == 3) st = gram_walk(gview, smem_addr(my_slots) + stage * slot_bytes + cur.off, len) ? st_accept : 0u;
-            else if (len) st = walk_shared(view, smem_addr(my_slots) + stage * slot_bytes + cur.off, len, st);
+            if (TIER == 3) st = gram_walk(gview, smem_addr(my_slot) + cur.off, len) ? st_accept : 0u;
+            else if (len) st = walk_shared(view, smem_addr(my_slot) + cur.off, len, st);
         } else if (len) {
             st = walk_global(view, b.bases + cur.s, len, st);
         }
@@ -396,7 +395,7 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
         }
         __syncwarp();   // every lane is done reading the slot before it is refilled
         cur = nxt;
-        if (STAGES == 2) stage ^= 1u; else issue(cur, 0);
+        issue(cur);
         nxt = finalize(ahead);
         prefetch(nxt);
         ahead = load_raw(batch + 3u * stride);
@@ -404,23 +403,23 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
 }
 
-template <int TIER, int STAGES>
+template <int TIER>
 cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cudaStream_t stream) {
     const uint32_t avg = b.avg_read_len ? b.avg_read_len : 150u;
     uint32_t slot = ((32u * avg + 64u + 15u) & ~15u) + 16u;
     slot = (slot + 127u) & ~127u;
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 3 ? ((dfa.gram.bitmap_bytes + 127u) & ~127u) : ((dfa.hot_entries * 4u + 127u) & ~127u);
-    const uint32_t fixed = table_smem + 256u + 32u * STAGES * 8u + 128u;
+    const uint32_t fixed = table_smem + 256u + 32u * 8u + 128u;
     const uint32_t budget = 227u * 1024u;
-    if (fixed + STAGES * slot > budget) {
+    if (fixed + slot > budget) {
         // slot too large for even one warp: shrink it; oversized batches take the global-memory path
-        slot = ((budget - fixed) / STAGES) & ~127u;
+        slot = (budget - fixed) & ~127u;
     }
-    uint32_t warps = (budget - fixed) / (STAGES * slot);
+    uint32_t warps = (budget - fixed) / slot;
     if (warps > 32u) warps = 32u;
     if (warps < 1u) warps = 1u;
-    const uint32_t smem = fixed + warps * STAGES * slot;
-    auto kern = match_soa_kernel<TIER, STAGES>;
+    const uint32_t smem = fixed + warps * slot;
+    auto kern = match_soa_kernel<TIER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t n_batches = (b.n_reads + 31u) / 32u;
@@ -497,11 +496,11 @@ cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_cou
     // measured on B200 with 150-base reads, 32 resident warps with one slot each beat 22 warps with two
     // (tier 0: 0.83 -> 0.90 of the HBM roofline), because the walk is a dependent chain per lane and more warps hide it.
     switch (dfa.tier) {
-        case 0: return launch_t<0, 1>(dfa, b, sm_count, stream);
-        case 1: return launch_t<1, 1>(dfa, b, sm_count, stream);
-        case 4: return launch_t<4, 1>(dfa, b, sm_count, stream);
-        case 3: return launch_t<3, 1>(dfa, b, sm_count, stream);     // the filter bitmap takes 64-128 KB of the shared memory
-        default: return launch_t<2, 1>(dfa, b, sm_count, stream);
+        case 0: return launch_t<0>(dfa, b, sm_count, stream);
+        case 1: return launch_t<1>(dfa, b, sm_count, stream);
+        case 4: return launch_t<4>(dfa, b, sm_count, stream);
+        case 3: return launch_t<3>(dfa, b, sm_count, stream);     // the filter bitmap takes 64-128 KB of the shared memory
+        default: return launch_t<2>(dfa, b, sm_count, stream);
     }
 }
 
