@@ -169,7 +169,8 @@ int fqg_write_selected(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2
 
 /* Input plumbing, host side: replaces spawn_reader (src/main.rs:61-87).  Reads `path` ("-" = stdin) completely into one
  * buffer (pinned=1: cudaHostAlloc, the fast path for fqg_grep_fastq_host; pinned=0: malloc, no CUDA needed).  The input is
- * gunzipped (multi-member gzip / BGZF, like flate2's MultiGzDecoder) when the extension is .gz/.bgz, or when `decompress`
+ * gunzipped (multi-member gzip / BGZF, like flate2's MultiGzDecoder; pure BGZF files are inflated member-parallel on all
+ * host threads) when the extension is .gz/.bgz, or when `decompress`
  * (-Z) is set and the extension is not .fq/.fastq (src/main.rs:77, src/lib/mod.rs:157-183).  Free with fqg_free_input. */
 int fqg_read_input(const char* path, int decompress, int pinned, uint8_t** out, size_t* n_out);
 void fqg_free_input(uint8_t* p, int pinned);

@@ -63,3 +63,42 @@ def test_count_is_the_same_for_fq_fastq_gz_bgz(tmp_path, kat):
         _write(p, data, mode)
         buf = F.read_input(p, pinned=True)
         assert m.grep_fastq(buf)["count"] == exp == 100
+
+
+def bgzf(data, block=900, eof=True):
+    """What bgzip writes: independent gzip members with a 'BC' extra field holding the member size - 1."""
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof else [])
+    for ch in chunks:
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        payload = c.compress(ch) + c.flush()
+        bsize = 12 + 6 + len(payload) + 8
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += payload + struct.pack("<II", zlib.crc32(ch) & 0xFFFFFFFF, len(ch))
+    return bytes(out)
+
+
+def test_bgzf_members_are_inflated_in_parallel_and_checked(tmp_path):
+    """BGZF input takes the parallel path (members located through their BC fields); the bytes are those Python's gzip
+    reads, damage is an error like in the serial decoder, and anything that is not pure BGZF falls back to it."""
+    data = fastq(["ACGT" * 40, "TTTTGGGGCCCC" * 12, "N" * 7] * 3000)
+    z = bgzf(data)
+    assert gzip.decompress(z) == data and z.count(b"BC\x02\x00") > 500
+    p = str(tmp_path / "r.fq.gz")
+    open(p, "wb").write(z)
+    assert F.read_input(p).tobytes() == data
+    assert F.read_input(p, pinned=False).tobytes() == data
+    # one flipped payload byte: CRC or stream error
+    bad = bytearray(z)
+    bad[len(z) // 2] ^= 0x55
+    open(str(tmp_path / "bad.fq.gz"), "wb").write(bytes(bad))
+    with pytest.raises(F.FqgrepError):
+        F.read_input(str(tmp_path / "bad.fq.gz"))
+    # BGZF followed by a plain gzip member: not pure BGZF, the serial multi-member decoder takes it
+    open(str(tmp_path / "mixed.fq.gz"), "wb").write(bgzf(data[:5000], eof=False) + gzip.compress(data[5000:9000]))
+    assert F.read_input(str(tmp_path / "mixed.fq.gz")).tobytes() == data[:9000]
+    # empty BGZF file (only the EOF marker)
+    open(str(tmp_path / "empty.fq.bgz"), "wb").write(bgzf(b""))
+    assert F.read_input(str(tmp_path / "empty.fq.bgz")).size == 0
