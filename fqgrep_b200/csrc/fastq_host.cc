@@ -6,7 +6,14 @@
 // This is host I/O glue driven by the device bitmask; no matching happens here.
 #include "fastq_host.hpp"
 
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
+
 #include <cuda_runtime.h>
 
 #include "../../include/fqgrep_b200.h"
@@ -93,11 +100,157 @@ inline uint8_t* emit(uint8_t* o, const HostRecord& r) {
     *o++ = '\n';
     return o;
 }
+
+// ---- parallel write-back ---------------------------------------------------------------------------------------------
+// The serial walk above parses every record to find the selected ones: ~memchr speed on one core, i.e. seconds for
+// the tens of gigabytes the device matches in one.  The parallel form cuts each input into shards at record starts
+// (find_record_start), walks every shard once noting where its records start (pass 1, 4 bytes per record), and with the
+// record number of each shard's first record known re-reads and emits only the selected records (pass 2).  It is only trusted when it provably equals the
+// serial parse: every shard's walk must end EXACTLY on the next shard's first byte and no walk may hit a malformed
+// record; otherwise -- and for small inputs -- the serial walk runs and reports whatever it finds.
+struct Span { uint64_t unit; size_t off, len; };
+struct ShardOut {
+    std::vector<uint8_t> bytes;     // selected records of the shard, write_to form
+    std::vector<Span> spans;        // one per selected record: its unit and where it sits in `bytes`
+};
+
+size_t write_shard_bytes() {
+    if (const char* e = std::getenv("FQG_WRITE_SHARD_BYTES")) {      // test hook: exercise the parallel form on small inputs
+        const long v = std::atol(e);
+        if (v > 0) return (size_t)v;
+    }
+    return (size_t)8 << 20;
+}
+
+// Parses one stream in parallel.  unit_of(record) maps a record number to its unit; on success fills `shards` (in input
+// order) and *n_records.  Returns false when the parallel parse cannot be trusted.
+bool parallel_select(const uint8_t* buf, size_t n, const uint32_t* mask, bool interleaved, std::vector<ShardOut>* shards, uint64_t* n_records) {
+    const size_t shard_bytes = write_shard_bytes();
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 4;
+    if (nt > 32) nt = 32;
+    if (n < 2 * shard_bytes || nt < 2) return false;
+    size_t n_shards = n / shard_bytes;
+    if (n_shards > (size_t)nt * 8) n_shards = (size_t)nt * 8;
+    if (n_shards < (n >> 31) + 1) n_shards = (n >> 31) + 1;      // record starts are kept as 32-bit offsets into their shard
+    std::vector<size_t> cut(n_shards + 1);
+    cut[0] = 0;
+    for (size_t i = 1; i < n_shards; i++) {
+        cut[i] = find_record_start(buf, n, (size_t)((unsigned __int128)n * i / n_shards));
+        if (cut[i] < cut[i - 1]) cut[i] = cut[i - 1];
+    }
+    cut[n_shards] = n;
+    const bool trace = std::getenv("FQG_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) std::fprintf(stderr, "[fqg] write_selected %s: %.1f ms since start (%zu shards, %u threads)\n", what,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), n_shards, nt);
+    };
+    std::vector<std::vector<uint32_t>> starts(n_shards);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> ok{true};
+    auto run = [&](auto&& body) {
+        next = 0;
+        std::vector<std::thread> pool;
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n_shards || !ok) break;
+                body(i);
+            }
+        };
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    };
+    // pass 1: record starts of every shard; every walk must land exactly on the next cut (the last one on a clean end of input)
+    run([&](size_t i) {
+        if (cut[i + 1] - cut[i] > 0xFFFFFFFFull) { ok = false; return; }
+        size_t pos = cut[i];
+        HostRecord r;
+        std::string err;
+        std::vector<uint32_t> st;      // local: the headers of starts[] share cache lines between threads
+        st.reserve((cut[i + 1] - cut[i]) / 256 + 16);
+        while (pos < cut[i + 1]) {
+            const size_t at = pos;
+            const int rc = next_host_record(buf, n, &pos, &r, &err);
+            if (rc < 0) { ok = false; return; }
+            if (rc == 0) { pos = n; break; }          // only blank lines left
+            st.push_back((uint32_t)(at - cut[i]));
+        }
+        if (pos != cut[i + 1] && !(i + 1 == n_shards && pos >= n)) { ok = false; return; }
+        starts[i] = std::move(st);
+    });
+    if (!ok) return false;
+    lap("pass 1");
+    std::vector<uint64_t> first(n_shards + 1, 0);
+    for (size_t i = 0; i < n_shards; i++) first[i + 1] = first[i] + starts[i].size();
+    if (interleaved && (first[n_shards] & 1)) return false;      // odd record count: the serial walk reports it
+    shards->assign(n_shards, ShardOut());
+    // pass 2: re-read and emit only the selected records of every shard
+    run([&](size_t i) {
+        ShardOut so;                   // local for the same reason
+        HostRecord r;
+        std::string err;
+        for (uint64_t rec = first[i]; rec < first[i + 1]; rec++) {
+            const uint64_t unit = interleaved ? rec >> 1 : rec;
+            if (!((mask[unit >> 5] >> (unit & 31)) & 1u)) continue;
+            size_t pos = cut[i] + starts[i][rec - first[i]];
+            if (next_host_record(buf, n, &pos, &r, &err) != 1) { ok = false; return; }
+            const size_t len = r.head_len + r.seq_len + r.qual_len + 6;
+            const size_t off = so.bytes.size();
+            so.bytes.resize(off + len);
+            emit(so.bytes.data() + off, r);
+            so.spans.push_back(Span{unit, off, len});
+        }
+        (*shards)[i] = std::move(so);
+    });
+    if (!ok) return false;
+    lap("pass 2");
+    *n_records = first[n_shards];
+    return true;
+}
+
+bool write_selected_parallel(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* mask, uint8_t* out, size_t* out_len,
+                             uint8_t* out2, size_t* out2_len) {
+    std::vector<ShardOut> s1, s2;
+    uint64_t c1 = 0, c2 = 0;
+    if (!parallel_select(r1, n1, mask, mode == FQG_INTERLEAVED, &s1, &c1)) return false;
+    if (mode != FQG_PAIRED) {
+        uint8_t* o = out;
+        for (auto& so : s1) { if (!so.bytes.empty()) memcpy(o, so.bytes.data(), so.bytes.size()); o += so.bytes.size(); }
+        *out_len = (size_t)(o - out);
+        if (out2_len) *out2_len = 0;
+        return true;
+    }
+    if (!parallel_select(r2, n2, mask, false, &s2, &c2) || c2 < c1) return false;      // fewer R2 records: serial walk reports it
+    // R2 may hold MORE records than R1 (the serial walk stops with R1): units >= c1 never count
+    uint8_t *o = out, *o2 = out2;
+    size_t j = 0, k = 0;      // cursor into s2
+    for (auto& so : s1)
+        for (auto& sp : so.spans) {
+            memcpy(o, so.bytes.data() + sp.off, sp.len); o += sp.len;
+            while (j < s2.size() && k >= s2[j].spans.size()) { j++; k = 0; }
+            if (j >= s2.size() || s2[j].spans[k].unit != sp.unit) return false;      // cannot happen: same mask, same units
+            const Span& b = s2[j].spans[k++];
+            if (o2) { memcpy(o2, s2[j].bytes.data() + b.off, b.len); o2 += b.len; }
+            else { memcpy(o, s2[j].bytes.data() + b.off, b.len); o += b.len; }
+        }
+    *out_len = (size_t)(o - out);
+    if (out2_len) *out2_len = out2 ? (size_t)(o2 - out2) : 0;
+    return true;
+}
 }  // namespace
 
 int write_selected_host(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* mask, uint8_t* out, size_t* out_len,
                         uint8_t* out2, size_t* out2_len, std::string* err) {
     if (!out || !out_len || (!mask)) { *err = "NULL argument"; return FQG_E_INVALID_ARG; }
+    const bool trace = std::getenv("FQG_TRACE") != nullptr;
+    if (write_selected_parallel(mode, r1, n1, r2, n2, mask, out, out_len, out2, out2_len)) {
+        if (trace) std::fprintf(stderr, "[fqg] write_selected: parallel walk\n");
+        return 0;
+    }
+    if (trace) std::fprintf(stderr, "[fqg] write_selected: serial walk\n");
     uint8_t *o = out, *o2 = out2;
     size_t p1 = 0, p2 = 0;
     uint64_t unit = 0;

@@ -245,3 +245,57 @@ def test_write_selected_is_host_glue_and_matches_oracle_output():
     assert F.write_selected(mask2, r1, r2, mode=F.PAIRED) == e3["out"]
     with pytest.raises(F.FqgrepError):
         F.write_selected(mask, b"@a\nACGT\n+\nXX\n")
+
+
+def test_parallel_write_back_equals_the_serial_walk(monkeypatch, capfd):
+    """fqg_write_selected cuts big inputs into shards and walks them on all host threads; it must equal the serial walk
+    (= the oracle's output) byte for byte, and step aside for it whenever the input is not clean FASTQ.  The shard size
+    is shrunk through the test hook so that a few hundred kilobytes already run the parallel form."""
+    import random
+    from tests.fq_util import fastq
+    rng = random.Random(3)
+    seqs = ["".join(rng.choice("ACGTN") for _ in range(rng.choice((1, 7, 36, 150, 151, 400)))) for _ in range(3000)]
+    quals = None
+    def words(flags):
+        b = np.packbits(flags.astype(bool), bitorder="little").tobytes()
+        return np.frombuffer(b + b"\0" * (8 - len(b) % 4), dtype=np.uint32)
+    o = O.Matcher(O.REGEX_SET, ["ACG", "T{3}"])
+    monkeypatch.setenv("FQG_TRACE", "1")
+    for crlf, plus_name, final_nl in ((False, False, True), (True, True, False)):
+        r1 = fastq(seqs, crlf=crlf, plus_name=plus_name, final_newline=final_nl)
+        r2 = fastq([s[::-1] for s in seqs], crlf=not crlf)
+        want1 = o.grep(r1, want_output=True)
+        wantp = o.grep(r1, r2, mode=O.PAIRED, want_output=True)
+        wants = o.grep(r1, r2, mode=O.PAIRED, want_output=True, split=True)
+        ri = fastq(seqs, heads=["p%d" % (i // 2) for i in range(len(seqs))], crlf=crlf, plus_name=plus_name, final_newline=final_nl)
+        wanti = o.grep(ri, mode=O.INTERLEAVED, want_output=True)
+        for shard in ("1000", "4096", "100000"):
+            monkeypatch.setenv("FQG_WRITE_SHARD_BYTES", shard)
+            assert F.write_selected(words(want1["flags"]), r1) == want1["out"]
+            assert F.write_selected(words(wantp["flags"]), r1, r2, mode=F.PAIRED) == wantp["out"]
+            a, b = F.write_selected(words(wants["flags"]), r1, r2, mode=F.PAIRED, split=True)
+            assert a == wants["out"] and b == wants["out2"]
+            assert F.write_selected(words(wanti["flags"]), ri, mode=F.INTERLEAVED) == wanti["out"]
+            err = capfd.readouterr().err
+            assert err.count("parallel walk") == 4 and "serial walk" not in err, (shard, err)
+    # quality lines that start with '@' (a shard cut must not take them for headers)
+    monkeypatch.setenv("FQG_WRITE_SHARD_BYTES", "600")
+    tricky = b"".join(b"@r%d\n%s\n+\n@%s\n" % (i, b"ACGT" * 10, b"I" * 39) for i in range(400))
+    e = O.Matcher(O.FIXED, ["ACGT"]).grep(tricky, want_output=True)
+    assert F.write_selected(words(e["flags"]), tricky) == e["out"] == tricky
+    assert "parallel walk" in capfd.readouterr().err
+    # malformed input inside a later shard: same error as the serial walk
+    bad = tricky + b"@x\nACGT\n+\nII\n" + tricky
+    with pytest.raises(F.FqgrepError):
+        F.write_selected(words(np.ones(900)), bad)
+    assert "serial walk" in capfd.readouterr().err
+    # R2 longer than R1 is tolerated by the serial walk (it stops with R1), shorter is an error
+    r1 = fastq(seqs[:500])
+    r2 = fastq([s[::-1] for s in seqs[:520]])
+    sel = np.zeros(500); sel[::7] = 1
+    monkeypatch.delenv("FQG_WRITE_SHARD_BYTES")
+    serial = F.write_selected(words(sel), r1, r2, mode=F.PAIRED)
+    monkeypatch.setenv("FQG_WRITE_SHARD_BYTES", "2000")
+    assert F.write_selected(words(sel), r1, r2, mode=F.PAIRED) == serial
+    with pytest.raises(F.FqgrepError):
+        F.write_selected(words(sel), r2, r1, mode=F.PAIRED)
