@@ -264,9 +264,10 @@ struct IndexOut {                    // K0: optional per-record index of stream 
 // m == nullptr: index only (parse, validate, index; no matching)
 int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, bool on_device,
                     uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res, cudaStream_t user_stream, unsigned min_record_bytes,
-                    bool* capacity_hit, const IndexOut* idx = nullptr) {
+                    bool* capacity_hit, const IndexOut* idx = nullptr, unsigned keep_newline_mask = 0, unsigned* stripped_mask = nullptr) {
     std::memset(res, 0, sizeof *res);
     *capacity_hit = false;
+    if (stripped_mask) *stripped_mask = 0;
     if (mode != FQG_SINGLE && mode != FQG_INTERLEAVED && mode != FQG_PAIRED) return fail(FQG_E_INVALID_ARG, "unknown mode");
     if ((n1 && !r1) || (mode == FQG_PAIRED && n2 && !r2)) return fail(FQG_E_INVALID_ARG, "NULL input");
     CU_TRY(cudaSetDevice(c->device));
@@ -302,6 +303,21 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
             while (j && (tail[j - 1] == '\n' || tail[j - 1] == '\r')) j--;
             n -= k - j;
             if (j) break;
+        }
+        if (n < s.n) {
+            // Trailing line terminators were dropped.  That is right unless the last record's quality line is EMPTY: then
+            // one of them ended its '+' line (seq_io accepts "...+\n<EOF>" as a record with empty quality).  Which case
+            // this is depends on the line count of the whole stream, so the caller finds out by trying: a parse that
+            // fails with the terminators dropped is repeated with one of them kept.
+            uint8_t first2[2] = {0, 0};
+            const size_t k = s.n - n < 2 ? s.n - n : 2;
+            if (on_device) CU_TRY(cudaMemcpy(first2, s.src + n, k, cudaMemcpyDeviceToHost));
+            else std::memcpy(first2, s.src + n, k);
+            const size_t term = (first2[0] == '\r' && k == 2 && first2[1] == '\n') ? 2 : 1;
+            if (first2[0] == '\n' || term == 2) {
+                if (stripped_mask) *stripped_mask |= 1u << i;
+                if ((keep_newline_mask >> i) & 1u) n += term;
+            }
         }
         s.n = n;
         const uint64_t stream_len = n ? n + 1 : 0;
@@ -463,8 +479,22 @@ int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r
 int grep_fastq(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, bool on_device,
                uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res, cudaStream_t user_stream) {
     bool hit = false;
-    int rc = grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, res, user_stream, 32, &hit);
-    if (rc && hit) rc = grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, res, user_stream, 8, &hit);
+    unsigned stripped = 0, min_rec = 32;
+    int rc = grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, res, user_stream, min_rec, &hit, nullptr, 0, &stripped);
+    if (rc && hit) rc = grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, res, user_stream, min_rec = 8, &hit, nullptr, 0, &stripped);
+    if ((rc == FQG_E_FASTQ || rc == FQG_E_PAIR_MISMATCH) && stripped) {
+        // a last record with an empty quality line, in either stream? (see where the trailing terminators are dropped)
+        const std::string first_error = fqg_last_error();
+        for (unsigned keep = 1; keep <= 3; keep++) {
+            if ((keep & stripped) != keep) continue;
+            fqg_result again;
+            if (grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, &again, user_stream, min_rec, &hit, nullptr, keep) == FQG_OK) {
+                *res = again;
+                return FQG_OK;
+            }
+        }
+        return fail(rc, first_error);
+    }
     return rc;
 }
 
@@ -811,8 +841,15 @@ int fqg_index_fastq_device(fqg_ctx* c, const uint8_t* d_fastq, size_t n, uint64_
     idx.cap = capacity;
     fqg_result res;
     bool hit = false;
-    int rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, 32, &hit, &idx);
-    if (rc && hit) rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, 8, &hit, &idx);
+    unsigned stripped = 0, min_rec = 32;
+    int rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, min_rec, &hit, &idx, 0, &stripped);
+    if (rc && hit) rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, min_rec = 8, &hit, &idx, 0, &stripped);
+    if (rc == FQG_E_FASTQ && stripped) {      // last record with an empty quality line, see grep_fastq
+        const std::string first_error = fqg_last_error();
+        if (grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, min_rec, &hit, &idx, 1) != FQG_OK)
+            return fail(rc, first_error);
+        rc = FQG_OK;
+    }
     if (rc) return rc;
     *n_records = res.n_records;
     if (res.n_records > capacity) return fail(FQG_E_INVALID_ARG, "index arrays too small: " + std::to_string(res.n_records) + " records");

@@ -174,6 +174,15 @@ def test_format_edge_cases():
                     both(F.REGEX_SET, pats, False, True, data)
                 both(F.NAMES, ["@0", "@3"], False, False, data)
     both(F.REGEX, ["A"], False, False, fastq(seqs) + b"\n\n\r\n")       # trailing blank lines
+    # a LAST record with empty sequence and quality: the newline that ends its '+' line must survive the trimming of
+    # trailing terminators (seq_io accepts "...+\n<EOF>"), in one stream or in both
+    for tail in (b"@e\n\n+\n", b"@e\n\n+\n\n", b"@e\r\n\r\n+\r\n", b"@e\n\n+\n\n\n\n"):
+        both(F.REGEX_SET, ["^$", "A"], False, False, fastq(seqs) + tail)
+        both(F.REGEX_SET, ["^$", "A"], False, False, fastq(seqs, heads=["p%d" % i for i in range(5)]) + tail,
+             fastq(seqs, heads=["p%d" % i for i in range(5)]) + b"@e\nAC\n+\nII\n", mode=F.PAIRED)
+        both(F.REGEX_SET, ["^$", "A"], False, False, fastq(seqs) + tail, fastq(seqs) + tail, mode=F.PAIRED)
+    with pytest.raises(F.FqgrepError):
+        F.Matcher(F.REGEX, ["A"]).grep_fastq(fastq(seqs) + b"@e\n\n+")         # no newline after '+': truncated
     assert F.Matcher(F.REGEX, ["A"]).grep_fastq(b"")["count"] == 0
     # ids end at the first space only (a tab belongs to the id)
     both(F.NAMES, ["a\tb"], False, False, fastq(["ACGT"], heads=["a\tb c"]))
@@ -300,3 +309,83 @@ def test_k0_index_and_compaction_then_soa_match():
     tb2 = torch.zeros(bad.size + 64, dtype=torch.uint8, device=dev)
     tb2[: bad.size] = torch.from_numpy(bad.copy()).to(dev)
     assert L.fqg_index_fastq_device(ctx, tb2.data_ptr(), bad.size, d_start.data_ptr(), d_len.data_ptr(), cap, C.byref(n_rec), sp) == -4
+
+
+def _random_fastq(rng, n_records, pair_heads=None):
+    """A valid FASTQ file with everything the format allows mixed in: empty and long lines, CRLF (whole file), '+name'
+    separators, quality lines that start with '@' or '+', headers with spaces and tabs, optional final newline."""
+    nl = b"\r\n" if rng.random() < 0.3 else b"\n"
+    recs, heads = [], []
+    for i in range(n_records):
+        L = rng.choice((0, 1, 2, 3, 4, 7, 33, 64, 150, 150, 150, 151, 299, 2000)) if rng.random() < 0.97 else rng.randrange(15000, 25000)
+        seq = bytes(rng.choice(b"ACGTNacgt") for _ in range(L))
+        qual = bytes(rng.choice(b"@+I#5?") for _ in range(L))
+        if pair_heads is not None:
+            head = pair_heads[i]
+        else:
+            head = ("r%d" % i + rng.choice(("", " 1:N:0", "\tx", " a b", "/1"))).encode()
+        heads.append(head)
+        plus = b"+" + (head if rng.random() < 0.2 else b"")
+        recs.append(b"@" + head + nl + seq + nl + plus + nl + qual + nl)
+    data = b"".join(recs)
+    if rng.random() < 0.4 and data:
+        data = data[:-len(nl)]
+    return data, heads
+
+
+def test_fuzz_valid_and_damaged_fastq_against_the_oracle():
+    """Randomised files through the fused kernel: valid ones must give the oracle's units / count / mask / output bytes in
+    all three pairing modes; damaged ones (a byte range cut out, a line dropped, a quality line shortened, truncation)
+    must be an error exactly when the oracle says so, and agree with it otherwise."""
+    import os
+    rng = random.Random(int(os.environ.get("FQG_FUZZ_SEED", "20240611")))       # longer campaigns: FQG_FUZZ_ITERS / FQG_FUZZ_SEED
+    iters = int(os.environ.get("FQG_FUZZ_ITERS", "40"))
+    matchers = [(F.REGEX_SET, ["ACG", "T{3,}", "^N", "G$"], False, True), (F.FIXED, ["acgt"], True, False), (F.NAMES, ["r1", "r7", "r64", "r501"], False, False)]
+    n_err = n_ok = 0
+    for it in range(iters):
+        n = rng.choice((1, 2, 3, 17, 64, 200, 900))
+        data, heads = _random_fastq(rng, n)
+        kind, pats, inv, rc = matchers[it % len(matchers)]
+        both(kind, pats, inv, rc, data)
+        if n % 2 == 0:
+            ids = [heads[i // 2 * 2].split(b" ")[0] for i in range(n)]
+            inter, _ = _random_fastq(rng, n, pair_heads=[ids[i] + rng.choice((b"", b" x")) for i in range(n)])
+            both(kind, pats, inv, rc, inter, mode=F.INTERLEAVED)
+        mate, _ = _random_fastq(rng, n, pair_heads=[h.split(b" ")[0] + b" 2" for h in heads])
+        both(kind, pats, inv, rc, data, mate, mode=F.PAIRED)
+        # damage
+        for _ in range(4):
+            bad = bytearray(data)
+            how = rng.randrange(6)
+            if how == 0 and len(bad) > 2:
+                a = rng.randrange(len(bad) - 1); del bad[a:a + rng.randrange(1, min(40, len(bad) - a))]
+            elif how == 1 and bad.count(b"\n") > 1:
+                lines = bytes(bad).split(b"\n"); del lines[rng.randrange(len(lines) - 1)]; bad = bytearray(b"\n".join(lines))
+            elif how == 2 and len(bad) > 1:
+                bad = bad[:rng.randrange(1, len(bad))]
+            elif how == 4:      # harmless: another letter inside some line, blank lines at the end
+                spots = [k for k in range(len(bad)) if bad[k] in b"ACGTNacgtI#5?"]
+                if spots:
+                    bad[rng.choice(spots)] = ord("A")
+                bad += b"\n" * rng.randrange(0, 3)
+            elif how == 5:
+                bad += rng.choice((b"\n", b"\r\n", b"\n\n\n"))
+            else:
+                a = rng.randrange(len(bad) + 1); bad[a:a] = rng.choice((b"\n", b"@", b"+\n", b"\r", b"X"))
+            bad = bytes(bad)
+            m = F.Matcher(kind, pats, opts(inv, rc))
+            o = O.Matcher(kind, pats, inv, rc)
+            try:
+                e = o.grep(bad)
+            except O.OracleError:
+                e = None
+            if e is None:
+                with pytest.raises(F.FqgrepError) as ex:
+                    m.grep_fastq(bad)
+                assert ex.value.exit_code == 101
+                n_err += 1
+            else:
+                g = m.grep_fastq(bad)
+                assert g["units"] == e["units"] and g["count"] == e["count"] and (g["mask"] == (e["flags"] != 0)).all()
+                n_ok += 1
+    assert n_err > 20 and n_ok > 20     # the damage produced both kinds
