@@ -78,7 +78,8 @@ struct RecordEval {
         if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
         uint32_t id_len = 0;
         if (TIER == 3 || want_idh) {      // id = header up to the first space; scanned and hashed four bytes at a time
-            const uint32_t a0 = tile + s + 1u, n = head_end - (s + 1u), sh = (a0 & 3u) * 8u;
+            // (a malformed record may "start" on an empty line: p0 == s, no header bytes at all)
+            const uint32_t a0 = tile + s + 1u, n = head_end > s + 1u ? head_end - (s + 1u) : 0u, sh = (a0 & 3u) * 8u;
             uint32_t wp = a0 & ~3u, w0 = lds_u32_volatile(wp), h = 0x811C9DC5u;
             id_len = n;
             for (uint32_t i = 0; i < n; i += 4u) {
@@ -328,7 +329,7 @@ __device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, 
                     else if (seq_len != qual_len) report(a, gs, kErrUnequal);
                     seq_pos = q[0] + 1;
                     seq_n = (uint32_t)seq_len;
-                    sel = ev.eval_global(base + gs + 1, (uint32_t)(q[0] - gs - 1 - cr0), base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
+                    sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
                 }
             }
         }

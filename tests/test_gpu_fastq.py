@@ -333,6 +333,16 @@ def _random_fastq(rng, n_records, pair_heads=None):
     return data, heads
 
 
+def _dump_failing_input(tag, *blobs):
+    """Keeps the inputs of a failing fuzz case where a gpurun call brings them back (gpurun_out/)."""
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        for k, b in enumerate(blobs):
+            if b is not None:
+                open(os.path.join(d, "fuzz_fail_%s_%d.bin" % (tag, k)), "wb").write(bytes(b))
+
+
 def test_fuzz_valid_and_damaged_fastq_against_the_oracle():
     """Randomised files through the fused kernel: valid ones must give the oracle's units / count / mask / output bytes in
     all three pairing modes; damaged ones (a byte range cut out, a line dropped, a quality line shortened, truncation)
@@ -346,13 +356,25 @@ def test_fuzz_valid_and_damaged_fastq_against_the_oracle():
         n = rng.choice((1, 2, 3, 17, 64, 200, 900))
         data, heads = _random_fastq(rng, n)
         kind, pats, inv, rc = matchers[it % len(matchers)]
-        both(kind, pats, inv, rc, data)
+        try:
+            both(kind, pats, inv, rc, data)
+        except Exception:
+            _dump_failing_input("single_it%d" % it, data)
+            raise
         if n % 2 == 0:
             ids = [heads[i // 2 * 2].split(b" ")[0] for i in range(n)]
             inter, _ = _random_fastq(rng, n, pair_heads=[ids[i] + rng.choice((b"", b" x")) for i in range(n)])
-            both(kind, pats, inv, rc, inter, mode=F.INTERLEAVED)
+            try:
+                both(kind, pats, inv, rc, inter, mode=F.INTERLEAVED)
+            except Exception:
+                _dump_failing_input("inter_it%d" % it, inter)
+                raise
         mate, _ = _random_fastq(rng, n, pair_heads=[h.split(b" ")[0] + b" 2" for h in heads])
-        both(kind, pats, inv, rc, data, mate, mode=F.PAIRED)
+        try:
+            both(kind, pats, inv, rc, data, mate, mode=F.PAIRED)
+        except Exception:
+            _dump_failing_input("paired_it%d" % it, data, mate)
+            raise
         # damage
         for _ in range(4):
             bad = bytearray(data)
@@ -379,13 +401,17 @@ def test_fuzz_valid_and_damaged_fastq_against_the_oracle():
                 e = o.grep(bad)
             except O.OracleError:
                 e = None
-            if e is None:
-                with pytest.raises(F.FqgrepError) as ex:
-                    m.grep_fastq(bad)
-                assert ex.value.exit_code == 101
-                n_err += 1
-            else:
-                g = m.grep_fastq(bad)
-                assert g["units"] == e["units"] and g["count"] == e["count"] and (g["mask"] == (e["flags"] != 0)).all()
-                n_ok += 1
+            try:
+                if e is None:
+                    with pytest.raises(F.FqgrepError) as ex:
+                        m.grep_fastq(bad)
+                    assert ex.value.exit_code == 101
+                    n_err += 1
+                else:
+                    g = m.grep_fastq(bad)
+                    assert g["units"] == e["units"] and g["count"] == e["count"] and (g["mask"] == (e["flags"] != 0)).all()
+                    n_ok += 1
+            except BaseException:
+                _dump_failing_input("damaged_it%d_%s" % (it, "oracle_err" if e is None else "oracle_ok"), bad)
+                raise
     assert n_err > 20 and n_ok > 20     # the damage produced both kinds
