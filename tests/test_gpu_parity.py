@@ -244,7 +244,8 @@ def test_device_resident_entry_with_pair_or_mask():
 def test_fuzz_random_pattern_sets_on_ragged_mixed_alphabet_reads():
     """Random regex / literal / bit-mask sets against reads with N, lowercase, protein letters and ragged lengths:
     exercises the 4-base and 2-base table paths, their exact non-ACGT fallback, the tails and the class-indexed tiers."""
-    rng = random.Random(77)
+    import os
+    rng = random.Random(int(os.environ.get("FQG_FUZZ_SEED", "77")))      # longer campaigns: FQG_FUZZ_SEED / FQG_FUZZ_ITERS
     seqs = []
     for i in range(12000):
         L = rng.choice([0, 1, 3, 4, 5, 8, 16, 31, 32, 33, 75, 150, 151, 152, 153, 301])
@@ -253,7 +254,7 @@ def test_fuzz_random_pattern_sets_on_ragged_mixed_alphabet_reads():
     bases, offs = soa(seqs)
     atoms = ["A", "C", "G", "T", "N", ".", "[AC]", "[^G]", "[ACGT]", "(A|T)", "(CG|GC)", "a", "[Nn]"]
     quants = ["", "", "", "", "*", "+", "?", "{2}", "{1,3}"]
-    for trial in range(40):
+    for trial in range(int(os.environ.get("FQG_FUZZ_ITERS", "40"))):
         kind = rng.choice([F.REGEX_SET, F.REGEX_SET, F.FIXED_SET, F.BITMASK_SET])
         if kind == F.REGEX_SET:
             pats = []
@@ -261,7 +262,8 @@ def test_fuzz_random_pattern_sets_on_ragged_mixed_alphabet_reads():
                 body = "".join(rng.choice(atoms) + rng.choice(quants) for _ in range(rng.randint(2, 9)))
                 pats.append(rng.choice(["", "^", ""]) + body + rng.choice(["", "$", ""]))
         elif kind == F.FIXED_SET:
-            pats = ["".join(rng.choice("ACGTN") for _ in range(rng.randint(1, 14))) for _ in range(rng.randint(1, 40))]
+            lo, hi, cnt = rng.choice(((1, 14, 40), (8, 20, 400), (12, 24, 3000), (5, 9, 600)))      # small / q-gram filter / 2-base rows
+            pats = ["".join(rng.choice("ACGTN") for _ in range(rng.randint(lo, hi))) for _ in range(rng.randint(1, cnt))]
         else:
             pats = ["".join(rng.choice("ACGTRYKMSWN") for _ in range(rng.randint(2, 10))) for _ in range(rng.randint(2, 6))]
         inv, rc = rng.random() < 0.3, rng.random() < 0.5
