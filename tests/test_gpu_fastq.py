@@ -411,7 +411,20 @@ def test_fuzz_valid_and_damaged_fastq_against_the_oracle():
                     g = m.grep_fastq(bad)
                     assert g["units"] == e["units"] and g["count"] == e["count"] and (g["mask"] == (e["flags"] != 0)).all()
                     n_ok += 1
+                # the same damaged file as one mate of a pair and as an interleaved file: error or not, like the oracle
+                for mode, second in ((F.PAIRED, mate), (F.INTERLEAVED, None)):
+                    try:
+                        ep = o.grep(bad, second, mode=mode)
+                    except O.OracleError:
+                        ep = None
+                    if ep is None:
+                        with pytest.raises(F.FqgrepError) as ex:
+                            m.grep_fastq(bad, second, mode=mode)
+                        assert ex.value.exit_code == 101
+                    else:
+                        gp = m.grep_fastq(bad, second, mode=mode)
+                        assert gp["units"] == ep["units"] and gp["count"] == ep["count"] and (gp["mask"] == (ep["flags"] != 0)).all()
             except BaseException:
-                _dump_failing_input("damaged_it%d_%s" % (it, "oracle_err" if e is None else "oracle_ok"), bad)
+                _dump_failing_input("damaged_it%d_%s" % (it, "oracle_err" if e is None else "oracle_ok"), bad, mate)
                 raise
     assert n_err > 20 and n_ok > 20     # the damage produced both kinds
