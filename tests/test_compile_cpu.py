@@ -299,3 +299,45 @@ def test_parallel_write_back_equals_the_serial_walk(monkeypatch, capfd):
     assert F.write_selected(words(sel), r1, r2, mode=F.PAIRED) == serial
     with pytest.raises(F.FqgrepError):
         F.write_selected(words(sel), r2, r1, mode=F.PAIRED)
+
+
+def test_parallel_write_back_fuzz_against_the_serial_walk(monkeypatch):
+    """Random valid and damaged files, random masks: the shard-parallel write-back returns exactly what the serial walk
+    returns -- the same bytes, or an error when the serial walk reports one."""
+    import random
+    rng = random.Random(5)
+
+    def rand_file(n):
+        nl = b"\r\n" if rng.random() < 0.3 else b"\n"
+        recs = []
+        for i in range(n):
+            L = rng.choice((0, 1, 4, 33, 150, 151, 400))
+            seq = bytes(rng.choice(b"ACGTN") for _ in range(L))
+            qual = bytes(rng.choice(b"@+I#") for _ in range(L))
+            recs.append(b"@r%d x" % i + nl + seq + nl + b"+" + (b"r%d" % i if rng.random() < 0.2 else b"") + nl + qual + nl)
+        data = b"".join(recs)
+        return data[:-len(nl)] if rng.random() < 0.4 else data
+
+    def run(mask, r1, r2, mode, split):
+        try:
+            return F.write_selected(mask, r1, r2, mode=mode, split=split)
+        except F.FqgrepError as e:
+            return ("error", e.code)
+
+    for it in range(60):
+        n = rng.choice((2, 50, 400, 1500))
+        r1, r2 = rand_file(n), rand_file(n)
+        if rng.random() < 0.5:            # damage one of them
+            bad = bytearray(r1)
+            a = rng.randrange(len(bad))
+            if rng.random() < 0.5:
+                del bad[a:a + rng.randrange(1, 30)]
+            else:
+                bad[a:a] = rng.choice((b"\n", b"@", b"+\n", b"\r"))
+            r1 = bytes(bad)
+        mask = np.frombuffer(bytes(rng.getrandbits(8) for _ in range((n // 32 + 3) * 4)), dtype=np.uint32)
+        for mode, second, split in ((F.SINGLE, None, False), (F.INTERLEAVED, None, False), (F.PAIRED, r2, False), (F.PAIRED, r2, True)):
+            monkeypatch.setenv("FQG_WRITE_SHARD_BYTES", str(1 << 40))
+            serial = run(mask, r1, second, mode, split)
+            monkeypatch.setenv("FQG_WRITE_SHARD_BYTES", rng.choice(("700", "5000", "60000")))
+            assert run(mask, r1, second, mode, split) == serial, (it, mode, split)
