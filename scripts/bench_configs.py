@@ -189,17 +189,18 @@ def main():
     run_soa("cfg2_two_regex_rc_25M", F.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], False, True, 25_000_000, lit, out)
     run_soa("cfg4_class_regex_invert_25M", F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, False, 25_000_000, lit, out)
     p200 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 12)) for _ in range(200)]
-    run_soa("extra_tier1_200x12mers_25M", F.FIXED_SET, p200, False, True, 25_000_000, p200[:20], out)
+    run_soa("extra_200x12mers_rc_25M", F.FIXED_SET, p200, False, True, 25_000_000, p200[:20], out)
     mixed = p10k[:300] + ["AC.G[AT]C"]
-    run_soa("extra_tier2_regexset_301_25M", F.REGEX_SET, mixed, False, True, 25_000_000, p10k[:20], out)
+    run_soa("extra_mixed_300lit_1regex_25M", F.REGEX_SET, mixed, False, True, 25_000_000, p10k[:20], out)
     r60 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 8)) + "[AC]" + "".join("ACGT"[i] for i in rng.integers(0, 4, 6)) for _ in range(60)]
-    run_soa("extra_tier1_regexset_60_25M", F.REGEX_SET, r60, False, False, 25_000_000, p10k[:20], out)
+    run_soa("extra_regexset_60_25M", F.REGEX_SET, r60, False, False, 25_000_000, p10k[:20], out)
     r400 = []
     for _ in range(1200):
         t = ["ACGT"[i] for i in rng.integers(0, 4, 10)]
         t[int(rng.integers(2, 8))] = "[AC]"
         r400.append("".join(t))
-    run_soa("extra_tier2_regexset_1200_25M", F.REGEX_SET, r400, False, False, 25_000_000, p10k[:20], out)
+    run_soa("extra_regexset_400_25M", F.REGEX_SET, r400[:400], False, False, 25_000_000, p10k[:20], out)      # class-indexed smem table (tier 1)
+    run_soa("extra_regexset_1200_25M", F.REGEX_SET, r400, False, False, 25_000_000, p10k[:20], out)           # table through L2 (tier 2)
     run_soa("cfg5a_1000_fixed_25M", F.FIXED_SET, p1k, False, False, 25_000_000, p1k[:50], out)
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
     run_soa("extra_cfg3_10k_20mers_revcomp_25M", F.FIXED_SET, p10k, False, True, 25_000_000, p10k[:200], out)
