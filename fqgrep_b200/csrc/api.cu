@@ -114,8 +114,10 @@ void build_tables(fqg_matcher* m) {
             for (uint64_t c = 0; c < nc; c++) m->t16[s * row0 + 256 + c] = (uint16_t)(d.next[s * nc + c] * row0 * 2);
         }
         for (int b = 0; b < 256; b++) m->lut[b] = (uint8_t)(d.byte_class[b] * 2);
-    } else if (!m->gram.usable && nc <= 127 && n * (16 + ((nc + 7) / 8) * 8) * 2 <= 60 * 1024) {
-        // tier 4: 16 two-base entries + the one-byte entries per row (literal sets prefer the q-gram filter, tier 3)
+    } else if ((!m->gram.usable || m->gram.s < 8 || m->gram.expected_hits > 0.1) && nc <= 127 && n * (16 + ((nc + 7) / 8) * 8) * 2 <= 60 * 1024) {
+        // tier 4: 16 two-base entries + the one-byte entries per row.  Literal sets prefer the q-gram filter (tier 3) when it
+        // probes once per 8 bases or less often and rarely hits (1000 x 20-mers: 0.82 vs 0.62 here); a filter that has to
+        // probe every 4 bases, or verifies a lot, loses to this table (60 x 15-mer regexes: 0.54 vs 0.62 here)
         const uint64_t row4 = 16 + ((nc + 7) / 8) * 8;
         m->tier = 4;
         m->row = (uint32_t)row4 * 2;
@@ -547,10 +549,23 @@ int fqg_matcher_new(int kind, const uint8_t* blob, const uint64_t* offsets, uint
                 build_gram_filter(lits, rc, &m->gram);
             } else {
                 if (!compile_regex_set(pats, rc, &m->dfa, &err)) return fail(FQG_E_PATTERN, err);
-                std::vector<std::string> lit_members, rest_members;
+                // Members with a small finite language ("AC[GT]{3}TT(A|G)CA": 16 strings) are as good as literals: when
+                // every member is one and the strings are long enough, the q-gram filter serves the whole set (the
+                // automaton above stays the exact fallback and the FASTQ kernel's table); otherwise the long-literal
+                // members can still be split off from the real regexes (tier 5).
+                std::vector<std::string> lit_members, rest_members, all_strings;
+                bool all_finite = true;
                 for (size_t i = 0; i < pats.size(); i++) {
-                    std::string l;
-                    if (regex_as_literal(pats[i], &l) && l.size() >= 8) lit_members.push_back(l); else rest_members.push_back(pats[i]);
+                    std::vector<std::string> ls;
+                    bool fin = regex_as_literals(pats[i], 64, &ls);
+                    bool long_enough = fin;
+                    for (auto& l : ls) if (l.size() < 8) long_enough = false;
+                    if (fin) all_strings.insert(all_strings.end(), ls.begin(), ls.end()); else all_finite = false;
+                    if (long_enough) lit_members.insert(lit_members.end(), ls.begin(), ls.end()); else rest_members.push_back(pats[i]);
+                }
+                if (all_finite && rest_members.empty()) {
+                    build_gram_filter(all_strings, rc, &m->gram);      // usable or not is decided there (lengths, density)
+                    break;
                 }
                 if (lit_members.size() >= 16 && !rest_members.empty()) {
                     auto a = std::make_unique<fqg_matcher>();

@@ -45,6 +45,8 @@ bool expand_iupac_fixed(const std::string& pattern, std::vector<std::string>* ou
 std::string iupac_to_regex(const std::string& pattern);
 
 bool regex_as_literal(const std::string& pattern, std::string* literal);
+// the regex's whole (finite, small, non-empty-string) language, see regex_compile.cc
+bool regex_as_literals(const std::string& pattern, size_t max_strings, std::vector<std::string>* literals);
 
 // Literal set -> Aho-Corasick DFA (replaces aho_corasick::AhoCorasick::new, matcher.rs:297-298, and
 // bstr find, matcher.rs:204).  with_revcomp adds rc(pattern) for every pattern.
@@ -59,6 +61,7 @@ struct GramFilter {
     bool usable = false;
     uint32_t q = 0, s = 0, min_len = 0, qmask = 0;
     uint32_t bitmap_bits_log2 = 0, slots_log2 = 0;
+    double expected_hits = 0;          // real gram hits a 150-base read of random bases sends to verification
     std::vector<uint32_t> bitmap;      // shared-memory resident on the device
     std::vector<uint32_t> slots;       // 4 words per slot {gram key, pool offset, pattern length << 5 | offset in the pattern, -}; all ones = empty
     std::vector<uint8_t> pool;         // patterns (+ reverse complements), each starting on a 16-byte boundary

@@ -70,6 +70,13 @@ bool build_gram_filter(const std::vector<std::string>& patterns_in, bool with_re
     }
     const uint64_t n_grams = (uint64_t)pats.size() * s;
     if (n_grams > (1ull << 22)) return false;
+    // The filter only pays when a random text gram is rarely one of ours: with n_grams of the 4^q possible grams in the
+    // table, a 150-base read has ~(150 / s) * n_grams / 4^q real gram hits to verify.  Short patterns in large numbers
+    // (thousands of 10-mers: q = 8) would send every read to verification several times; those sets keep the automaton
+    // (measured, 1000 x 10-mers: filter 0.17 of roofline, class-indexed table 0.29).  api.cu is stricter (0.1) when the
+    // automaton is small enough for the 2-base-stride table, which beats a busy filter (60 x 15-mer regexes: 0.62 vs 0.54).
+    out->expected_hits = q < 16 ? (double)n_grams / (double)(1ull << (2 * q)) * (150.0 / s) : 0.0;
+    if (out->expected_hits > 0.5 && !std::getenv("FQG_GRAM_NO_DENSITY_GUARD")) return false;      // (knob for measurements)
     // blocked 3-bit Bloom filter in shared memory: the top bits of one multiplicative hash pick a 32-bit word, bits 2..16
     // three bits inside it.  ~40 bits per gram keeps the false-positive rate near 0.2 %; floor 8 KB, cap 128 KB (2^20
     // bits).  The filter shares the SM's 227 KB with the staging slots, i.e. with the number of resident warps, so the

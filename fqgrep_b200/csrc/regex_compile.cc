@@ -918,6 +918,72 @@ bool regex_as_literal(const std::string& pattern, std::string* literal) {
     return true;
 }
 
+// The finite language of a regex, when it has one and it is small: classes of a few bytes, alternation, groups and
+// bounded repetition are multiplied out ("AC[GT]{2}(A|G)" -> 8 strings).  An unanchored search for such a regex is a
+// search for any of its strings, so large sets of them can take the q-gram filter like literal sets do.  False for
+// anything else (assertions, unbounded repetition, big classes, more than `max_strings` strings, the empty string).
+static bool finite_language(const Ast& a, size_t max_strings, std::vector<std::string>* out) {
+    out->clear();
+    switch (a.kind) {
+        case Ast::Empty: out->push_back(std::string()); return true;
+        case Ast::Bytes: {
+            for (int b = 0; b < 256; b++)
+                if (bs_has(a.set, b)) { if (out->size() >= 8 || out->size() >= max_strings) return false; out->push_back(std::string(1, (char)b)); }
+            return !out->empty();
+        }
+        case Ast::Cat: {
+            out->push_back(std::string());
+            std::vector<std::string> kid, next;
+            for (auto& k : a.kids) {
+                if (!finite_language(*k, max_strings, &kid)) return false;
+                if (out->size() * kid.size() > max_strings) return false;
+                next.clear();
+                for (auto& x : *out) for (auto& y : kid) next.push_back(x + y);
+                out->swap(next);
+            }
+            return true;
+        }
+        case Ast::Alt: {
+            std::vector<std::string> kid;
+            for (auto& k : a.kids) {
+                if (!finite_language(*k, max_strings, &kid)) return false;
+                if (out->size() + kid.size() > max_strings) return false;
+                out->insert(out->end(), kid.begin(), kid.end());
+            }
+            return !out->empty();
+        }
+        case Ast::Rep: {
+            if (a.max < 0 || a.kids.size() != 1) return false;
+            std::vector<std::string> kid, power(1, std::string()), next;
+            if (!finite_language(*a.kids[0], max_strings, &kid)) return false;
+            for (int k = 0; k <= a.max; k++) {
+                if (k >= a.min) {
+                    if (out->size() + power.size() > max_strings) return false;
+                    out->insert(out->end(), power.begin(), power.end());
+                }
+                if (k == a.max) break;
+                if (power.size() * kid.size() > max_strings) return false;
+                next.clear();
+                for (auto& x : power) for (auto& y : kid) next.push_back(x + y);
+                power.swap(next);
+            }
+            return !out->empty();
+        }
+        default: return false;
+    }
+}
+bool regex_as_literals(const std::string& pattern, size_t max_strings, std::vector<std::string>* literals) {
+    AstP ast;
+    try {
+        ast = Parser(pattern).parse();
+    } catch (ParseError&) {
+        return false;
+    }
+    if (!finite_language(*ast, max_strings, literals)) return false;
+    for (auto& l : *literals) if (l.empty()) return false;
+    return true;
+}
+
 // --iupac bit-mask (BitMaskMatcher / BitMaskSetMatcher, matcher.rs:307-487): a needle is a fixed-length string of
 // byte classes.  With IUPAC_MASKS m[] (mod.rs:14-53), needle symbol n_i = m[pattern byte]:
 //   needle has an ambiguity code (or a non-IUPAC byte): position i accepts every byte b with (n_i & m[b]) == m[b]

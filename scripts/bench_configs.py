@@ -201,6 +201,7 @@ def main():
         r400.append("".join(t))
     run_soa("extra_regexset_400_25M", F.REGEX_SET, r400[:400], False, False, 25_000_000, p10k[:20], out)      # class-indexed smem table (tier 1)
     run_soa("extra_regexset_1200_25M", F.REGEX_SET, r400, False, False, 25_000_000, p10k[:20], out)           # table through L2 (tier 2)
+    run_soa("extra_1000x10mers_25M", F.FIXED_SET, [p[:10] for p in p1k], False, False, 25_000_000, [p[:10] for p in p1k[:20]], out)
     run_soa("cfg5a_1000_fixed_25M", F.FIXED_SET, p1k, False, False, 25_000_000, p1k[:50], out)
     run_soa("cfg3_10k_20mers_25M", F.FIXED_SET, p10k, False, False, 25_000_000, p10k[:200], out)
     run_soa("extra_cfg3_10k_20mers_revcomp_25M", F.FIXED_SET, p10k, False, True, 25_000_000, p10k[:200], out)

@@ -154,11 +154,16 @@ def test_tier2_l2_automaton_for_large_sets_of_short_patterns():
     assert 0 < cnt < 20_000
 
 
-def test_gram_filter_edge_cases():
-    """Tier 3: variable pattern lengths, reverse complement, N in patterns and reads, candidate overflow, ragged reads."""
+def test_gram_filter_edge_cases(monkeypatch):
+    """Tier 3: variable pattern lengths, reverse complement, N in patterns and reads, candidate overflow, ragged reads.
+    4000 patterns as short as 9 bases make a filter that verifies several grams per read; the library would rather walk
+    the automaton for such a set (density guard in gram_filter.cc), so the guard is lifted here to keep the unaligned
+    stride-2 scan and the many-hits verification rounds under test."""
     rng = np.random.default_rng(21)
     pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, int(L))) for L in rng.integers(9, 40, 4000)]
     pats += ["ACGTNNNNACGTAC", "NNNNNNNNNN", "GATTACAGATTACAGATTACA"]
+    assert F.Matcher(F.FIXED_SET, pats).dfa_info().tier == 2
+    monkeypatch.setenv("FQG_GRAM_NO_DENSITY_GUARD", "1")
     for rc in (False, True):
         m = F.Matcher(F.FIXED_SET, pats, opts(False, rc))
         assert m.dfa_info().tier == 3
@@ -191,6 +196,11 @@ def test_gram_filter_edge_cases():
     for inv, rc in ((False, False), (False, True), (True, True)):
         cnt = check(F.FIXED_SET, pats, inv, rc, bases, offs)
         assert 0 < cnt < len(seqs)
+    # with the guard in place: a set small enough for a stride-2 filter, too big for the 2-base-stride table
+    monkeypatch.delenv("FQG_GRAM_NO_DENSITY_GUARD")
+    few = pats[:120] + ["NNNNNNNNNN"]
+    assert F.Matcher(F.FIXED_SET, few).dfa_info().tier == 3
+    assert check(F.FIXED_SET, few, False, False, bases, offs) > 0
 
 
 def test_protein_alphabet(kat):
