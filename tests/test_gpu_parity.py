@@ -313,3 +313,49 @@ def test_names_over_soa_headers():
         ocnt, flags = O.Matcher(F.NAMES, chosen, inv, False).match_soa(blob, offs, threads=4)
         assert (bits == (want != inv)).all()
         assert (bits == (flags != 0)).all() and cnt == ocnt == int((want != inv).sum())
+
+
+def test_regexes_with_finite_languages_take_the_gram_filter():
+    """Members like `ACGT(A|C)G{1,2}[GT]...` have a small finite language: the set is multiplied out for the q-gram filter
+    (the automaton stays the exact fallback).  Every construct of the expansion is exercised and checked against the
+    oracle's NFA, with reads that carry real occurrences of random members of the languages."""
+    rng = random.Random(31)
+
+    def lit(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+
+    pats, samples = [], []
+    for i in range(400):
+        a, b, c = lit(rng.randint(6, 10)), lit(rng.randint(5, 9)), lit(rng.randint(4, 8))
+        kind = i % 5
+        if kind == 0:
+            pats.append(a + "[AG]" + b + "(C|T)" + c); samples.append(a + "G" + b + "T" + c)
+        elif kind == 1:
+            pats.append(a + "(AC|GT|T)" + b + c); samples.append(a + "GT" + b + c)
+        elif kind == 2:
+            pats.append(a + "N{1,2}" + b + "[CT]" + c); samples.append(a + "NN" + b + "C" + c)
+        elif kind == 3:
+            pats.append(a + b + "(?:A|C){2}" + c); samples.append(a + b + "CA" + c)
+        else:
+            pats.append(a + "G?" + b + c + "[ACGT]"); samples.append(a + b + c + "T")
+    for rc in (False, True):
+        assert F.Matcher(F.REGEX_SET, pats, opts(False, rc)).dfa_info().tier == 3
+    seqs = []
+    for i in range(20000):
+        L = rng.choice([20, 36, 75, 150, 151, 250])
+        s = "".join(rng.choice("ACGT") for _ in range(L))
+        if i % 9 == 0:
+            p = samples[rng.randrange(len(samples))]
+            if i % 18 == 0:
+                p = O.revcomp(p).decode()
+            if len(p) <= L:
+                o = rng.randrange(L - len(p) + 1)
+                s = s[:o] + p + s[o + len(p):]
+        seqs.append(s)
+    bases, offs = soa(seqs)
+    for inv, rc in ((False, False), (False, True), (True, True)):
+        cnt = check(F.REGEX_SET, pats, inv, rc, bases, offs)
+        assert 0 < cnt < len(seqs)
+    # a member without a finite language (or with the empty string in it) keeps the whole set on the automaton / split path
+    assert F.Matcher(F.REGEX_SET, pats + ["ACGTACGTAC.*TTTTGGGGCC"]).dfa_info().tier in (2, 5)
+    assert F.Matcher(F.REGEX_SET, pats[:3] + ["A*"]).dfa_info().tier in (0, 1, 2, 4)
