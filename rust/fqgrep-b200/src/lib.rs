@@ -12,7 +12,7 @@ pub struct MatcherOpts {
 
 #[repr(i32)]
 #[derive(Copy, Clone, Debug)]
-pub enum Kind { Fixed = 0, FixedSet = 1, Regex = 2, RegexSet = 3, Names = 4 }
+pub enum Kind { Fixed = 0, FixedSet = 1, Regex = 2, RegexSet = 3, Names = 4, BitMask = 5, BitMaskSet = 6 }
 
 #[repr(i32)]
 #[derive(Copy, Clone, Debug)]
@@ -40,6 +40,39 @@ extern "C" {
                            unit_mask_out: *mut u32, unit_mask_words: usize, res: *mut FqgResult) -> c_int;
     fn fqg_write_selected(mode: c_int, r1: *const u8, n1: usize, r2: *const u8, n2: usize, unit_mask: *const u32,
                           out: *mut u8, out_len: *mut usize, out2: *mut u8, out2_len: *mut usize) -> c_int;
+    // The rest of include/fqgrep_b200.h, declared so the whole C ABI is reachable from Rust (used by callers that keep
+    // their reads resident on the device, read inputs through the library, or shard across GPUs).
+    pub fn fqg_version() -> *const c_char;
+    pub fn fqg_device_count() -> c_int;
+    pub fn fqg_kernel_launches() -> u64;
+    pub fn fqg_iupac_expand(pattern: *const c_char, to_regex: c_int, out: *mut c_char, cap: usize, out_len: *mut usize) -> c_int;
+    pub fn fqg_matcher_dfa_info(m: *const c_void, out: *mut FqgDfaInfo) -> c_int;
+    pub fn fqg_matcher_dfa_export(m: *const c_void, byte_class: *mut u8, next: *mut u32) -> c_int;
+    pub fn fqg_alloc_pinned(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn fqg_free_pinned(p: *mut c_void);
+    pub fn fqg_match_bases_device(ctx: *mut c_void, m: *const c_void, d_bases: *const u8, d_start: *const u32, d_end: *const u32, n_reads: u64,
+                                  d_mask_out: *mut u32, d_or_mask: *const u32, d_count: *mut u64, avg_read_len: u32, stream: *mut c_void) -> c_int;
+    pub fn fqg_grep_fastq_device(ctx: *mut c_void, m: *const c_void, mode: c_int, d_r1: *const u8, n1: usize, d_r2: *const u8, n2: usize,
+                                 d_unit_mask_out: *mut u32, unit_mask_words: usize, res: *mut FqgResult, stream: *mut c_void) -> c_int;
+    pub fn fqg_index_fastq_device(ctx: *mut c_void, d_fastq: *const u8, n: usize, d_seq_start: *mut u64, d_seq_len: *mut u32, capacity: u64,
+                                  n_records: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn fqg_compact_bases_device(ctx: *mut c_void, d_fastq: *const u8, d_seq_start: *const u64, d_seq_len: *const u32, n_records: u64,
+                                    d_bases_out: *mut u8, d_offsets_out: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn fqg_read_input(path: *const c_char, decompress: c_int, pinned: c_int, out: *mut *mut u8, n_out: *mut usize) -> c_int;
+    pub fn fqg_free_input(p: *mut u8, pinned: c_int);
+    pub fn fqg_is_gzip_path(path: *const c_char) -> c_int;
+    pub fn fqg_is_fastq_path(path: *const c_char) -> c_int;
+    pub fn fqg_fastq_split(buf: *const u8, n: usize, parts: u32, cuts: *mut u64) -> c_int;
+    pub fn fqg_synth_reads_device(ctx: *mut c_void, d_out: *mut u8, n_reads: u64, first_index: u64, read_len: u32, fastq: c_int, seed: u64,
+                                  plant_blob: *const u8, plant_offsets: *const u32, n_plant: u32, plant_rate: f64, plant_seed: u64,
+                                  stream: *mut c_void) -> c_int;
+}
+
+/// fqg_dfa_info of the C header (compiled-automaton introspection).
+#[repr(C)]
+#[derive(Default, Debug)]
+pub struct FqgDfaInfo {
+    pub n_states: u32, pub n_classes: u32, pub start: u32, pub accept_from: u32, pub tier: u32, pub table_bytes: u32,
 }
 
 fn last_error() -> String {
