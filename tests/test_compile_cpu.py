@@ -27,6 +27,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert declared == set(_ffi.SYMBOLS)
     assert b"sm_100a" in L.fqg_version()
+    # the reference-side bindings shown in INTEGRATION.md (Rust shim, source only) and the C++ host header name them all too
+    root = os.path.join(os.path.dirname(__file__), "..")
+    rust = open(os.path.join(root, "rust", "fqgrep-b200", "src", "lib.rs")).read()
+    assert not [n for n in declared if n not in rust]
+    hpp = open(os.path.join(root, "include", "fqgrep_b200.hpp")).read()
+    for n in ("fqg_matcher_new", "fqg_grep_fastq_host", "fqg_match_bases_host", "fqg_write_selected", "fqg_read_input", "fqg_iupac_expand"):
+        assert n in hpp
 
 
 def test_kat_fixed(kat):
