@@ -56,6 +56,8 @@ struct fqg_matcher {
     std::vector<uint16_t> t16;
     std::vector<uint32_t> t32;
     uint8_t lut[256] = {0};   // byte -> class in the form the tier's kernel wants
+    uint32_t settled[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // states that only lead to themselves (see DeviceDfa), found in build_tables
+    uint32_t settle = 0;
     std::mutex mu;
     std::map<int, DeviceTables> dev;
     // Mixed -e/-f sets (many plain literals + a few real regexes) determinise into automata far too large for shared
@@ -97,6 +99,16 @@ int ensure_dev(fqg_ctx* c, int slot, size_t bytes, void** out) {
 void build_tables(fqg_matcher* m) {
     const Dfa& d = m->dfa;
     const uint64_t n = d.n_states, nc = d.n_classes;
+    {   // states that only lead to themselves: at most a dead one and an all-accepting one in a minimal automaton
+        int k = 0;
+        for (uint32_t s = 0; s < d.n_states && k < 2; s++) {
+            bool self = true;
+            for (uint32_t c = 0; c < d.n_classes && self; c++) self = d.next[(size_t)s * d.n_classes + c] == s;
+            if (!self) continue;
+            m->settled[k++] = s;
+            if (s < d.accept_from) m->settle = 1;      // a dead state: every read is decided after a few bases
+        }
+    }
     std::memcpy(m->lut, d.byte_class, 256);
     const uint64_t row0 = 256 + ((nc + 7) / 8) * 8;      // tier-0 row: 256 four-base entries + the one-byte entries
     if (nc <= 127 && n * row0 * 2 <= 40 * 1024) {
@@ -197,6 +209,9 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
         out->start = m->dfa.start * m->row;
         out->accept_from = m->dfa.accept_from * m->row;
         out->n_states = m->dfa.n_states;
+        out->settled[0] = m->settled[0] == 0xFFFFFFFFu ? 0xFFFFFFFFu : m->settled[0] * out->row;
+        out->settled[1] = m->settled[1] == 0xFFFFFFFFu ? 0xFFFFFFFFu : m->settled[1] * out->row;
+        out->settle = m->settle;
         if (m->tier == 2 || m->tier == 3) {     // rows of the first (shallowest, BFS order) states that fit 60 KB of shared memory
             uint64_t rows = (60ull * 1024) / (m->dfa.n_classes * 4ull);
             if (rows > m->dfa.n_states) rows = m->dfa.n_states;

@@ -49,6 +49,9 @@ struct DfaView {
     const uint32_t* t32;   // global (tier 2)
     uint32_t cls;          // smem address of the byte -> class LUT (tier 0,1: class*2; tier 2: class)
     uint32_t hot_limit;    // tier 2: states (entry indices) below this have their rows cached in shared memory at `tab`
+    // tiers 1, 2, 4: when the automaton has a dead state (^-anchored sets), a read is decided once its state is the dead
+    // or the all-accepting one, usually after a few bases; settle != 0 makes the walk stop there (kernels.hpp)
+    uint32_t settled_a = 0xFFFFFFFFu, settled_b = 0xFFFFFFFFu, settle = 0;
 
     __device__ __forceinline__ uint32_t step1(uint32_t st, uint32_t byte) const {
         if (TIER == 0) return lds_u16(st + 512u + lds_u8(cls + byte));
@@ -129,6 +132,8 @@ __device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t
             st = d.step1(st, (w >> 16) & 0xFFu);
             st = d.step1(st, w >> 24);
         }
+        // decided for good (not in tier 0, whose loop has no room for a branch); `bad` words were still seen in full
+        if (TIER != 0 && d.settle && !bad && (st == d.settled_a || st == d.settled_b)) return st;
     }
     if (kPackedCodes<TIER> && bad) return walk_shared_bytes(d, p, len, st0);
     const uint32_t rem = len & 3u;

@@ -35,6 +35,11 @@ struct DeviceDfa {
     uint32_t accept_from = 0;        // premultiplied
     uint32_t n_states = 0;
     uint32_t hot_entries = 0;        // tiers 2/3: leading table entries (whole rows of the shallowest states) cached in smem
+    // States every transition of which leads back to themselves (premultiplied like `start`, 0xFFFFFFFF = none): the dead
+    // state of a set of ^-anchored patterns and the all-accepting state of patterns without `$`.  `settle` is set when a
+    // dead state exists, i.e. when every read is decided after a few bases; the slower tiers then stop walking there.
+    uint32_t settled[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    uint32_t settle = 0;
 };
 
 struct SoaBatch {

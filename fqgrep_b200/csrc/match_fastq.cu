@@ -357,6 +357,12 @@ __device__ __forceinline__ RecordEval<TIER> make_eval(const FastqArgs& a, const 
     ev.view.t32 = reinterpret_cast<const uint32_t*>(dfa.table);
     ev.view.cls = smem_addr(s_cls);
     ev.view.hot_limit = TIER == 2 ? dfa.hot_entries : 0u;
+    {
+        const uint32_t rel = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;
+        ev.view.settled_a = dfa.settled[0] == 0xFFFFFFFFu ? 0xFFFFFFFFu : dfa.settled[0] + rel;
+        ev.view.settled_b = dfa.settled[1] == 0xFFFFFFFFu ? 0xFFFFFFFFu : dfa.settled[1] + rel;
+        ev.view.settle = dfa.settle;
+    }
     ev.names.nv = a.names;
     const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in the smem-table tiers
     ev.start = dfa.start + reloc;

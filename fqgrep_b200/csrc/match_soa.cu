@@ -304,6 +304,12 @@ match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_
     __syncthreads();
 
     DfaView<(TIER == 3 ? 2 : TIER)> view{smem_addr(s_tab), reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), TIER == 2 ? dfa.hot_entries : 0u};
+    {
+        const uint32_t rel = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // same relocation as the start state below
+        view.settled_a = dfa.settled[0] == 0xFFFFFFFFu ? 0xFFFFFFFFu : dfa.settled[0] + rel;
+        view.settled_b = dfa.settled[1] == 0xFFFFFFFFu ? 0xFFFFFFFFu : dfa.settled[1] + rel;
+        view.settle = dfa.settle;
+    }
     GramView gview{smem_addr(s_tab), dfa.gram, reinterpret_cast<const uint32_t*>(dfa.table), smem_addr(s_cls), dfa.start, dfa.accept_from};
     const uint32_t reloc = kSmemTable<TIER> ? smem_addr(s_tab) : 0u;      // states are shared addresses in tiers 0/1
     const uint32_t st_start = dfa.start + reloc, st_accept = dfa.accept_from + reloc;

@@ -204,6 +204,8 @@ def main():
         k = int(rng.integers(3, 17))
         r300.append(p[:k] + "[" + p[k] + "N]" + p[k + 1:])
     run_soa("extra_regexset_300x20mers_one_class_25M", F.REGEX_SET, r300, False, True, 25_000_000, p10k[1000:1020], out)
+    anch = ["^" + p[:12] for p in p10k[2000:4000]]      # 2000 barcodes anchored at the read start: dead state, early stop
+    run_soa("extra_anchored_2000x12_25M", F.REGEX_SET, anch, False, False, 25_000_000, [], out)
     run_soa("extra_regexset_400_25M", F.REGEX_SET, r400[:400], False, False, 25_000_000, p10k[:20], out)      # class-indexed smem table (tier 1)
     run_soa("extra_regexset_1200_25M", F.REGEX_SET, r400, False, False, 25_000_000, p10k[:20], out)           # table through L2 (tier 2)
     run_soa("extra_1000x10mers_25M", F.FIXED_SET, [p[:10] for p in p1k], False, False, 25_000_000, [p[:10] for p in p1k[:20]], out)

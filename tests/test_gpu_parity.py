@@ -359,3 +359,29 @@ def test_regexes_with_finite_languages_take_the_gram_filter():
     # a member without a finite language (or with the empty string in it) keeps the whole set on the automaton / split path
     assert F.Matcher(F.REGEX_SET, pats + ["ACGTACGTAC.*TTTTGGGGCC"]).dfa_info().tier in (2, 5)
     assert F.Matcher(F.REGEX_SET, pats[:3] + ["A*"]).dfa_info().tier in (0, 1, 2, 4)
+
+
+def test_anchored_sets_stop_at_settled_states():
+    """^-anchored pattern sets (barcodes at the start of the read) have a dead state: the slower tiers stop walking a read
+    once it is dead or accepted for good.  Same selection as the oracle, with and without -v / reverse complement, on
+    reads that also carry N and lowercase (the exact non-ACGT path) and on reads shorter than the patterns."""
+    rng = random.Random(41)
+    codes = ["".join(rng.choice("ACGT") for _ in range(rng.randint(8, 14))) for _ in range(1500)]
+    pats = ["^" + c for c in codes]
+    info = F.Matcher(F.REGEX_SET, pats).dfa_info()
+    assert info.tier in (1, 2, 4)
+    seqs = []
+    for i in range(30000):
+        L = rng.choice([0, 3, 9, 20, 75, 150, 151])
+        alpha = "ACGT" if i % 4 else rng.choice(["ACGTN", "ACGTacgt"])
+        s = "".join(rng.choice(alpha) for _ in range(L))
+        if i % 3 == 0:
+            c = codes[rng.randrange(len(codes))]
+            s = (c + s)[:max(L, len(c))] if i % 6 else s[:5] + c + s[5:]        # at the start (a match) or further in (not one)
+        seqs.append(s)
+    bases, offs = soa(seqs)
+    for inv, rc in ((False, False), (True, False), (False, True)):
+        cnt = check(F.REGEX_SET, pats, inv, rc, bases, offs)
+        assert 0 < cnt < len(seqs)
+    # a set that mixes anchored and unanchored members has no dead state: nothing to stop at, same answers
+    check(F.REGEX_SET, pats[:200] + ["GGGGGGGG"], False, False, bases, offs)
