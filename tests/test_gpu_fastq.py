@@ -428,3 +428,23 @@ def test_fuzz_valid_and_damaged_fastq_against_the_oracle():
                 _dump_failing_input("damaged_it%d_%s" % (it, "oracle_err" if e is None else "oracle_ok"), bad, mate)
                 raise
     assert n_err > 20 and n_ok > 20     # the damage produced both kinds
+
+
+def test_anchored_barcode_set_through_the_fastq_path():
+    """The fused kernel shares the table walk with the SoA kernel, including the stop at settled states (dead state of a
+    ^-anchored set, tiers 1 / 2 / 4)."""
+    rng = random.Random(43)
+    codes = ["".join(rng.choice("ACGT") for _ in range(rng.randint(8, 14))) for _ in range(1500)]
+    pats = ["^" + c for c in codes]
+    assert F.Matcher(F.REGEX_SET, pats).dfa_info().tier in (1, 2, 4)
+    seqs = []
+    for i in range(20000):
+        s = "".join(rng.choice("ACGTN" if i % 5 == 0 else "ACGT") for _ in range(rng.choice([0, 5, 36, 150, 151])))
+        if i % 3 == 0:
+            s = codes[rng.randrange(len(codes))] + s
+        seqs.append(s)
+    data = fastq(seqs)
+    for inv in (False, True):
+        g = both(F.REGEX_SET, pats, inv, False, data, check_output=False)
+        assert 0 < g["count"] < len(seqs)
+    both(F.REGEX_SET, pats, False, False, data, fastq([s[::-1] for s in seqs]), mode=F.PAIRED, check_output=False)
