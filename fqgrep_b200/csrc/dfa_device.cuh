@@ -112,8 +112,10 @@ __device__ __noinline__ uint32_t walk_shared_bytes(const DfaView<TIER>& d, uint3
 }
 
 // walk `len` bytes starting at shared address p (any alignment)
-template <int TIER>
-__device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st0) {
+// SETTLE: leave the walk once the state is the dead or the all-accepting one (only instantiated where the automaton
+// has a dead state: the check costs a crossbar-bound loop like tier 4's 20 % when it sits there unused)
+template <int TIER, bool SETTLE>
+__device__ __forceinline__ uint32_t walk_shared_impl(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st0) {
     const uint32_t sh = (p & 3u) * 8u;
     uint32_t wp = p & ~3u;
     uint32_t w0 = lds_u32_volatile(wp);
@@ -132,8 +134,8 @@ __device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t
             st = d.step1(st, (w >> 16) & 0xFFu);
             st = d.step1(st, w >> 24);
         }
-        // decided for good (not in tier 0, whose loop has no room for a branch); `bad` words were still seen in full
-        if (TIER != 0 && d.settle && !bad && (st == d.settled_a || st == d.settled_b)) return st;
+        // decided for good; a word with a non-ACGT byte (`bad`) makes the packed tiers re-walk the read below instead
+        if (SETTLE && !bad && (st == d.settled_a || st == d.settled_b)) return st;
     }
     if (kPackedCodes<TIER> && bad) return walk_shared_bytes(d, p, len, st0);
     const uint32_t rem = len & 3u;
@@ -144,6 +146,12 @@ __device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t
         if (rem > 2) st = d.step1(st, (w >> 16) & 0xFFu);
     }
     return st;
+}
+
+template <int TIER>
+__device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st0) {
+    if (TIER != 0 && d.settle) return walk_shared_impl<TIER, true>(d, p, len, st0);      // warp-uniform choice
+    return walk_shared_impl<TIER, false>(d, p, len, st0);
 }
 
 // fallback for reads that do not fit the shared-memory staging (very long reads): straight from global memory
