@@ -168,7 +168,12 @@ int read_input(const char* path, int decompress, int pinned, uint8_t** out, size
     }
     if (done) {
     } else if (!gz) {
-        for (;;) {
+        if (f != stdin && std::fseek(f, 0, SEEK_END) == 0) {      // regular file: one allocation of the right size
+            const long sz = std::ftell(f);
+            std::rewind(f);
+            if (sz > 0 && !buf.reserve((size_t)sz + kChunk + 1, err)) rc = FQG_E_CUDA;      // (+ one chunk: the loop asks for a full chunk of room)
+        }
+        while (rc == FQG_OK) {
             if (!buf.reserve(buf.n + kChunk, err)) { rc = FQG_E_CUDA; break; }
             size_t k = std::fread(buf.p + buf.n, 1, kChunk, f);
             buf.n += k;
