@@ -348,3 +348,21 @@ def test_parallel_write_back_fuzz_against_the_serial_walk(monkeypatch):
             serial = run(mask, r1, second, mode, split)
             monkeypatch.setenv("FQG_WRITE_SHARD_BYTES", rng.choice(("700", "5000", "60000")))
             assert run(mask, r1, second, mode, split) == serial, (it, mode, split)
+
+
+def test_tier_choice_follows_the_measured_policy():
+    """Which device layout a pattern set gets (fqg_dfa_info.tier), as DESIGN.md section 3 states it: the q-gram filter only
+    where it pays, regexes with small finite languages counted as literals, short dense sets left to the automaton."""
+    rng = np.random.default_rng(7)
+    k20 = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(3000)]
+    tier = lambda kind, pats, rc=False: F.Matcher(kind, pats, opts(False, rc)).dfa_info().tier
+    assert tier(F.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], True) == 0            # configs[1]
+    assert tier(F.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"]) == 0                          # small automaton: stays a table
+    assert tier(F.FIXED_SET, k20[:1000]) == 3                                      # long literals: filter, one probe per 8 bases
+    assert tier(F.REGEX_SET, k20[:1000]) == 3                                      # the same set given without -F
+    assert tier(F.FIXED_SET, [p[:10] for p in k20[:1000]]) in (1, 2)               # 1000 x 10-mers: too dense for the filter
+    assert tier(F.FIXED_SET, [p[:15] for p in k20[:60]]) == 4                      # stride-4 filter loses to 2-base rows
+    classy = [p[:9] + "[" + p[9] + "N]" + p[10:] for p in k20[:300]]
+    assert tier(F.REGEX_SET, classy, True) == 3                                    # finite languages multiplied out
+    assert tier(F.REGEX_SET, classy + ["ACGT.*TTTTTTTTTTTT"], True) == 5           # one real regex: split set
+    assert tier(F.REGEX_SET, ["^" + p[:12] for p in k20[:2000]]) in (1, 2)         # anchored barcodes: table + early stop
