@@ -11,6 +11,8 @@ SYMBOLS = [
     "fqg_matcher_dfa_info", "fqg_matcher_dfa_export", "fqg_ctx_create", "fqg_ctx_destroy", "fqg_device_count",
     "fqg_alloc_pinned", "fqg_free_pinned", "fqg_match_bases_device", "fqg_match_bases_host",
     "fqg_grep_fastq_host", "fqg_grep_fastq_device", "fqg_write_selected", "fqg_kernel_launches", "fqg_synth_reads_device", "fqg_fastq_split", "fqg_iupac_expand", "fqg_read_input", "fqg_free_input", "fqg_index_fastq_device", "fqg_compact_bases_device", "fqg_is_gzip_path", "fqg_is_fastq_path",
+    "fqg_grep_fastq_host_write", "fqg_grep_fastq_host_multi", "fqg_stream_open", "fqg_stream_acquire", "fqg_stream_submit", "fqg_stream_feed",
+    "fqg_stream_in_flight", "fqg_stream_next", "fqg_stream_close", "fqg_fastq_cut", "fqg_write_spans",
 ]
 
 
@@ -23,6 +25,21 @@ class Result(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_units", C.c_uint64), ("n_selected", C.c_uint64),
                 ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class Span(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("len", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class StreamOpts(C.Structure):
+    _fields_ = [("n_slots", C.c_uint32), ("want_spans", C.c_uint32), ("slot_bytes", C.c_size_t)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("seq", C.c_uint64), ("n_records", C.c_uint64), ("n_units", C.c_uint64), ("n_selected", C.c_uint64),
+                ("unit_mask", C.POINTER(C.c_uint32)), ("spans", C.POINTER(Span)), ("n_spans", C.c_uint64),
+                ("r1", C.c_void_p), ("r2", C.c_void_p), ("n1", C.c_size_t), ("n2", C.c_size_t),
+                ("h2d_ms", C.c_double), ("kernel_ms", C.c_double)]
 
 
 def lib():
@@ -62,6 +79,19 @@ def lib():
     L.fqg_is_gzip_path.argtypes = [C.c_char_p]
     L.fqg_is_fastq_path.argtypes = [C.c_char_p]
     L.fqg_iupac_expand.argtypes = [C.c_char_p, C.c_int, vp, sz, C.POINTER(sz)]
+    L.fqg_grep_fastq_host_write.argtypes = [vp, vp, C.c_int, vp, sz, vp, sz, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz), C.POINTER(Result)]
+    L.fqg_grep_fastq_host_multi.argtypes = [C.POINTER(vp), u32, vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz),
+                                            C.POINTER(Result)]
+    L.fqg_stream_open.argtypes = [vp, vp, C.c_int, C.POINTER(StreamOpts), C.POINTER(vp)]
+    L.fqg_stream_acquire.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
+    L.fqg_stream_submit.argtypes = [vp, sz, sz]
+    L.fqg_stream_feed.argtypes = [vp, vp, sz, vp, sz]
+    L.fqg_stream_in_flight.argtypes = [vp]
+    L.fqg_stream_next.argtypes = [vp, C.POINTER(Batch)]
+    L.fqg_stream_close.argtypes = [vp]
+    L.fqg_stream_close.restype = None
+    L.fqg_fastq_cut.argtypes = [C.c_int, vp, sz, vp, sz, sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+    L.fqg_write_spans.argtypes = [C.POINTER(Span), u64, vp, sz, vp, sz, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]
     _lib = L
     return L
 

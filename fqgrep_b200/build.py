@@ -7,7 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfqgrep_b200.so")
 CLI = os.path.join(HERE, "fqgrep-b200")      # the reference's command line over the device path (csrc/cli.cc)
-SOURCES = ["api.cu", "match_soa.cu", "match_fastq.cu", "synth.cu", "regex_compile.cc", "ac_build.cc", "gram_filter.cc", "names.cc", "fastq_host.cc", "input_host.cc"]
+SOURCES = ["api.cu", "fastq_pipeline.cu", "stream.cu", "match_soa.cu", "match_fastq.cu", "synth.cu", "regex_compile.cc", "ac_build.cc", "gram_filter.cc", "names.cc",
+           "fastq_host.cc", "input_host.cc"]
+HOST_SOURCES = ["fastq_cut.cc"]      # plain g++: per-function target attributes (AVX2 newline counting with a run-time check)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
@@ -37,6 +39,12 @@ def build(force=False, verbose=False):
         objs.append(obj)
         cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    cxx = os.environ.get("CXX", "g++")
+    for src in HOST_SOURCES:
+        obj = os.path.join(objdir, src + ".o")
+        objs.append(obj)
+        cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-Wall", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
         out, _ = p.communicate()
@@ -47,7 +55,6 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz"]
     subprocess.check_call(cmd)
     # host-only C++ above the C ABI: links the library by relative rpath so the pair travels together
-    cxx = os.environ.get("CXX", "g++")
     subprocess.check_call([cxx, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"), os.path.join(CSRC, "cli.cc"),
                            "-o", CLI, "-L", HERE, "-lfqgrep_b200", "-Wl,-rpath,$ORIGIN"])
     with open(os.path.join(objdir, "build.log"), "w") as f:

@@ -1,7 +1,5 @@
 // api.cu -- the C ABI (include/fqgrep_b200.h): matcher construction, device contexts, match entry points.
 // No CPU matching path exists in this library: every match call launches the CUDA kernels or fails.
-#include "../../include/fqgrep_b200.h"
-
 #include <atomic>
 #include <cstring>
 #include <map>
@@ -10,78 +8,22 @@
 #include <string>
 #include <vector>
 
-#include "automata.hpp"
-#include "fastq_host.hpp"
-#include "kernels.hpp"
+#include "internal.hpp"
 
 using namespace fqg;
 
 namespace {
-
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+namespace fqg {
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
-#define CU_TRY(expr)                                                                                         \
-    do {                                                                                                     \
-        cudaError_t _e = (expr);                                                                             \
-        if (_e != cudaSuccess) return fail(FQG_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
-    } while (0)
-
-struct DeviceTables {
-    void* table = nullptr;
-    uint8_t* byte_class = nullptr;
-    // q-gram filter
-    uint32_t *g_bitmap = nullptr, *g_kv = nullptr;
-    uint8_t* g_pool = nullptr;
-    // names
-    uint64_t* slots = nullptr;
-    uint32_t* slot_off = nullptr;
-    uint8_t* pool = nullptr;
-};
-
-}  // namespace
-
-struct fqg_matcher {
-    int kind = 0;
-    uint32_t opts = 0;
-    Dfa dfa;
-    NameTable names;
-    GramFilter gram;
-    int tier = 0;
-    uint32_t row = 0;
-    std::vector<uint16_t> t16;
-    std::vector<uint32_t> t32;
-    uint8_t lut[256] = {0};   // byte -> class in the form the tier's kernel wants
-    uint32_t settled[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // states that only lead to themselves (see DeviceDfa), found in build_tables
-    uint32_t settle = 0;
-    std::mutex mu;
-    std::map<int, DeviceTables> dev;
-    // Mixed -e/-f sets (many plain literals + a few real regexes) determinise into automata far too large for shared
-    // memory.  For the SoA kernels they are split: `split_lit` (the literal members: q-gram filter) runs first and leaves
-    // its "found" bits in the mask, `split_rest` (the regex members: small automaton) ORs them in before invert_match.
-    // `dfa` above is still the automaton of the WHOLE set (fused FASTQ kernel, introspection).
-    std::unique_ptr<fqg_matcher> split_lit, split_rest;
-};
-
-struct fqg_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    // grow-only device scratch
-    void* d_buf[8] = {nullptr};
-    size_t d_cap[8] = {0};
-    void* h_pinned = nullptr;
-    size_t h_cap = 0;
-    cudaEvent_t ev[6] = {nullptr};
-    cudaEvent_t chunk_ev[8] = {nullptr};
-    FastqDeviceState fq;
-};
-
-namespace {
+void count_launches(uint64_t n) { g_launches += n; }
 
 int ensure_dev(fqg_ctx* c, int slot, size_t bytes, void** out) {
     if (c->d_cap[slot] < bytes) {
@@ -95,6 +37,10 @@ int ensure_dev(fqg_ctx* c, int slot, size_t bytes, void** out) {
     *out = c->d_buf[slot];
     return 0;
 }
+
+}  // namespace fqg
+
+namespace {
 
 void build_tables(fqg_matcher* m) {
     const Dfa& d = m->dfa;
@@ -157,6 +103,10 @@ void build_tables(fqg_matcher* m) {
         for (uint64_t i = 0; i < n * nc; i++) m->t32[i] = (uint32_t)(d.next[i] * nc);
     }
 }
+
+}  // namespace
+
+namespace fqg {
 
 int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
     fqg_matcher* m = const_cast<fqg_matcher*>(cm);
@@ -222,300 +172,17 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Raw-FASTQ pipeline shared by the host and the device entry points.
-//   host source  : chunked cudaMemcpyAsync on the copy stream into one device buffer; after each chunk the fused
-//                  kernel is launched (compute stream, event-ordered) over the tiles that are now complete, so copy
-//                  and compute overlap (the reference overlaps its reader thread and worker pool the same way,
-//                  src/lib/seq_io.rs:287-368).
-//   device source: one launch per stream.
-enum { S_BUF = 0, S_STATE = 1, S_COUNTERS = 2, S_MASK = 3, S_IDH = 4 };
-struct StreamPlan {
-    const uint8_t* src = nullptr;   // as given (host or device)
-    size_t n = 0;                   // bytes with trailing newlines stripped
-    const uint8_t* d = nullptr;     // device bytes
-    uint32_t tiles = 0;
-    unsigned long long* state = nullptr;
-    uint32_t* counters = nullptr;
-    uint32_t* mask = nullptr;
-    uint32_t* idh = nullptr;
-    uint64_t mask_bits = 0, idh_cap = 0, mask_words = 0;
-    size_t copied = 0;
-    uint32_t tiles_done = 0, launches = 0;
-};
-constexpr size_t kCopyChunk = 64ull << 20;
-constexpr uint32_t kMaxLaunches = 1u << 16;
-
-int fq_ensure(fqg_ctx* c, int stream_idx, int what, size_t bytes, void** out) {
-    int slot = stream_idx * 5 + what;
-    FastqDeviceState& f = c->fq;
-    if (f.cap[slot] < bytes) {
-        if (f.scratch[slot]) cudaFree(f.scratch[slot]);
-        f.scratch[slot] = nullptr;
-        f.cap[slot] = 0;
-        size_t want = bytes + bytes / 16 + 4096;
-        CU_TRY(cudaMalloc(&f.scratch[slot], want));
-        f.cap[slot] = want;
-    }
-    *out = f.scratch[slot];
+int get_names_view(fqg_ctx* c, const fqg_matcher* cm, NamesView* out) {
+    int rc = get_device_dfa(c, cm, nullptr);      // uploads the table on first use
+    if (rc) return rc;
+    fqg_matcher* m = const_cast<fqg_matcher*>(cm);
+    std::lock_guard<std::mutex> lock(m->mu);
+    const DeviceTables& t = m->dev[c->device];
+    out->slots = t.slots; out->slot_off = t.slot_off; out->pool = t.pool; out->mask = m->names.n_slots / 4 - 1;
     return 0;
 }
 
-const char* fastq_err_name(unsigned code) {
-    switch (code) {
-        case 1: return "expected '@' at record start (InvalidStart)";
-        case 2: return "expected '+' separator line (InvalidSep)";
-        case 3: return "sequence and quality lengths differ (UnequalLengths)";
-        case 4: return "truncated record (UnexpectedEnd)";
-        case 6: return "record bitmask capacity exceeded (records shorter than 8 bytes, or 16 bytes with pair id check)";
-    }
-    return "unknown";
-}
-
-struct IndexOut {                    // K0: optional per-record index of stream 1 (device arrays owned by the caller)
-    unsigned long long* seq_start = nullptr;
-    uint32_t* seq_len = nullptr;
-    uint64_t cap = 0;
-};
-
-// m == nullptr: index only (parse, validate, index; no matching)
-int grep_fastq_once(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, bool on_device,
-                    uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res, cudaStream_t user_stream, unsigned min_record_bytes,
-                    bool* capacity_hit, const IndexOut* idx = nullptr, unsigned keep_newline_mask = 0, unsigned* stripped_mask = nullptr) {
-    std::memset(res, 0, sizeof *res);
-    *capacity_hit = false;
-    if (stripped_mask) *stripped_mask = 0;
-    if (mode != FQG_SINGLE && mode != FQG_INTERLEAVED && mode != FQG_PAIRED) return fail(FQG_E_INVALID_ARG, "unknown mode");
-    if ((n1 && !r1) || (mode == FQG_PAIRED && n2 && !r2)) return fail(FQG_E_INVALID_ARG, "NULL input");
-    CU_TRY(cudaSetDevice(c->device));
-    DeviceDfa dd;
-    int rc = m ? get_device_dfa(c, m, &dd) : 0;
-    if (rc) return rc;
-    const bool names = m && m->kind == FQG_NAMES;
-    NamesView nv;
-    if (names) {
-        std::lock_guard<std::mutex> lock(const_cast<fqg_matcher*>(m)->mu);
-        const DeviceTables& t = const_cast<fqg_matcher*>(m)->dev[c->device];
-        nv.slots = t.slots; nv.slot_off = t.slot_off; nv.pool = t.pool; nv.mask = m->names.n_slots / 4 - 1;
-    }
-    const int n_streams = mode == FQG_PAIRED ? 2 : 1;
-    const bool check_ids = mode != FQG_SINGLE;
-    cudaStream_t cs = on_device ? user_stream : c->stream;       // compute stream
-    cudaStream_t xs = c->copy_stream;                            // H2D stream (host sources)
-    const uint32_t kTile = fastq_tile_bytes(), kLoad = kTile + fastq_overlap_bytes();
-
-    StreamPlan sp[2];
-    sp[0].src = r1; sp[0].n = n1;
-    sp[1].src = r2; sp[1].n = n2;
-    for (int i = 0; i < n_streams; i++) {
-        StreamPlan& s = sp[i];
-        // strip trailing newline bytes (seq_io tolerates a missing final newline and trailing blank lines)
-        uint8_t tail[4096];
-        size_t n = s.n;
-        while (n) {
-            size_t k = n < sizeof tail ? n : sizeof tail;
-            if (on_device) CU_TRY(cudaMemcpy(tail, s.src + n - k, k, cudaMemcpyDeviceToHost));
-            else std::memcpy(tail, s.src + n - k, k);
-            size_t j = k;
-            while (j && (tail[j - 1] == '\n' || tail[j - 1] == '\r')) j--;
-            n -= k - j;
-            if (j) break;
-        }
-        if (n < s.n) {
-            // Trailing line terminators were dropped.  That is right unless the last record's quality line is EMPTY: then
-            // one of them ended its '+' line (seq_io accepts "...+\n<EOF>" as a record with empty quality).  Which case
-            // this is depends on the line count of the whole stream, so the caller finds out by trying: a parse that
-            // fails with the terminators dropped is repeated with one of them kept.
-            uint8_t first2[2] = {0, 0};
-            const size_t k = s.n - n < 2 ? s.n - n : 2;
-            if (on_device) CU_TRY(cudaMemcpy(first2, s.src + n, k, cudaMemcpyDeviceToHost));
-            else std::memcpy(first2, s.src + n, k);
-            const size_t term = (first2[0] == '\r' && k == 2 && first2[1] == '\n') ? 2 : 1;
-            if (first2[0] == '\n' || term == 2) {
-                if (stripped_mask) *stripped_mask |= 1u << i;
-                if ((keep_newline_mask >> i) & 1u) n += term;
-            }
-        }
-        s.n = n;
-        const uint64_t stream_len = n ? n + 1 : 0;
-        if (stream_len / kTile >= 0xFFFFFFF0ull) return fail(FQG_E_TOO_LARGE, "input stream too large");
-        s.tiles = (uint32_t)((stream_len + kTile - 1) / kTile);
-        s.mask_bits = n / min_record_bytes + 64;      // capacity for records of >= min_record_bytes on average
-        s.mask_words = (s.mask_bits + 31) / 32 + 2;
-        s.idh_cap = check_ids ? s.mask_bits : 0;
-        void* p;
-        if (!on_device) {
-            if ((rc = fq_ensure(c, i, S_BUF, n + 64, &p))) return rc;
-            s.d = (const uint8_t*)p;
-        } else s.d = s.src;
-        // look-back state: one word per tile, then one per segment of 32 tiles
-        if ((rc = fq_ensure(c, i, S_STATE, ((size_t)s.tiles + s.tiles / 32 + 2) * 8, &p))) return rc;
-        s.state = (unsigned long long*)p;
-        if ((rc = fq_ensure(c, i, S_COUNTERS, kMaxLaunches * 4, &p))) return rc;
-        s.counters = (uint32_t*)p;
-        if ((rc = fq_ensure(c, i, S_MASK, s.mask_words * 4, &p))) return rc;
-        s.mask = (uint32_t*)p;
-        if (check_ids) {
-            if ((rc = fq_ensure(c, i, S_IDH, s.idh_cap * 4 + 16, &p))) return rc;
-            s.idh = (uint32_t*)p;
-        }
-    }
-    // control block: [0] err, [1] count, [2] id mismatch, [3] lines r1, [4] lines r2
-    void* p;
-    if ((rc = ensure_dev(c, 4, 64, &p))) return rc;
-    unsigned long long* ctl = (unsigned long long*)p;
-    void* d_units;
-    const uint64_t max_units_words = sp[0].mask_words;
-    if ((rc = ensure_dev(c, 5, max_units_words * 4 + 16, &d_units))) return rc;
-
-    const unsigned long long ctl_init[5] = {~0ull, 0ull, ~0ull, 0ull, 0ull};
-    CU_TRY(cudaEventRecord(c->ev[0], cs));
-    CU_TRY(cudaMemcpyAsync(ctl, ctl_init, sizeof ctl_init, cudaMemcpyHostToDevice, cs));
-    for (int i = 0; i < n_streams; i++) {
-        CU_TRY(cudaMemsetAsync(sp[i].state, 0, ((size_t)sp[i].tiles + sp[i].tiles / 32 + 2) * 8, cs));
-        CU_TRY(cudaMemsetAsync(sp[i].counters, 0, kMaxLaunches * 4, cs));
-        CU_TRY(cudaMemsetAsync(sp[i].mask, 0, sp[i].mask_words * 4, cs));
-    }
-
-    auto launch = [&](int i, uint32_t tile_end) -> int {
-        StreamPlan& s = sp[i];
-        if (tile_end <= s.tiles_done) return 0;
-        if (s.launches >= kMaxLaunches) return fail(FQG_E_TOO_LARGE, "too many launches for one stream");
-        FastqArgs a{};
-        a.buf = s.d; a.nbytes = s.n; a.virtual_final_nl = 1;
-        a.tile_first = s.tiles_done; a.tile_count = tile_end - s.tiles_done;
-        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_state = s.state + s.tiles + 1; a.lines_out = ctl + 3 + i;
-        a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
-        a.count = mode == FQG_SINGLE ? ctl + 1 : nullptr;
-        a.err = ctl + 0;
-        a.invert = (m && (m->opts & FQG_INVERT_MATCH)) ? 1u : 0u;
-        a.names = nv;
-        if (idx && i == 0) { a.seq_start = idx->seq_start; a.seq_len = idx->seq_len; a.span_cap = idx->cap; }
-        CU_TRY(launch_match_fastq(dd, names, m == nullptr, a, c->sm_count, cs));
-        g_launches++;
-        s.launches++;
-        s.tiles_done = tile_end;
-        return 0;
-    };
-
-    uint64_t h2d_bytes = 0;
-    if (on_device) {
-        for (int i = 0; i < n_streams; i++) if ((rc = launch(i, sp[i].tiles))) return rc;
-    } else {
-        // interleave the streams chunk by chunk so mates progress together
-        CU_TRY(cudaEventRecord(c->ev[1], xs));
-        bool more = true;
-        int ev_slot = 0;
-        while (more) {
-            more = false;
-            for (int i = 0; i < n_streams; i++) {
-                StreamPlan& s = sp[i];
-                if (s.copied >= s.n) continue;
-                size_t k = s.n - s.copied < kCopyChunk ? s.n - s.copied : kCopyChunk;
-                CU_TRY(cudaMemcpyAsync(const_cast<uint8_t*>(s.d) + s.copied, s.src + s.copied, k, cudaMemcpyHostToDevice, xs));
-                s.copied += k;
-                h2d_bytes += k;
-                cudaEvent_t e = c->chunk_ev[ev_slot++ % 8];
-                CU_TRY(cudaEventRecord(e, xs));
-                CU_TRY(cudaStreamWaitEvent(cs, e, 0));
-                uint32_t ready = s.copied >= s.n ? s.tiles : (s.copied >= kLoad ? (uint32_t)((s.copied - kLoad) / kTile + 1) : 0u);
-                if ((rc = launch(i, ready))) return rc;
-                if (s.copied < s.n) more = true;
-            }
-        }
-        CU_TRY(cudaEventRecord(c->ev[2], xs));
-        for (int i = 0; i < n_streams; i++) if ((rc = launch(i, sp[i].tiles))) return rc;   // empty streams / leftovers
-    }
-
-    // ---- mates -> units (src/main.rs:749-755), id agreement (:741-747)
-    const uint32_t* unit_mask_dev = sp[0].mask;
-    if (mode == FQG_PAIRED) {
-        const uint64_t w = sp[0].mask_words < sp[1].mask_words ? sp[0].mask_words : sp[1].mask_words;
-        const uint64_t nrec = sp[0].idh_cap < sp[1].idh_cap ? sp[0].idh_cap : sp[1].idh_cap;
-        CU_TRY(launch_combine_pairs(sp[0].mask, sp[1].mask, (uint32_t*)d_units, w, sp[0].idh, sp[1].idh, nrec, ctl + 3, ctl + 4, ctl + 1, ctl + 2, cs));
-        g_launches++;
-        unit_mask_dev = (const uint32_t*)d_units;
-    } else if (mode == FQG_INTERLEAVED) {
-        CU_TRY(launch_combine_interleaved(sp[0].mask, (uint32_t*)d_units, sp[0].mask_words / 2, sp[0].idh, sp[0].idh_cap, ctl + 3, ctl + 1, ctl + 2, cs));
-        g_launches++;
-        unit_mask_dev = (const uint32_t*)d_units;
-    }
-    CU_TRY(cudaEventRecord(c->ev[3], cs));
-
-    unsigned long long h_ctl[5];
-    CU_TRY(cudaMemcpyAsync(h_ctl, ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, cs));
-    CU_TRY(cudaStreamSynchronize(cs));
-    uint64_t d2h_bytes = sizeof h_ctl;
-
-    if (h_ctl[0] != ~0ull) {
-        unsigned code = (unsigned)(h_ctl[0] & 15);
-        if (code == 6) *capacity_hit = true;
-        return fail(code >= 6 ? FQG_E_TOO_LARGE : FQG_E_FASTQ, std::string("FASTQ parse error at byte ") + std::to_string(h_ctl[0] >> 4) + ": " + fastq_err_name(code));
-    }
-    uint64_t lines[2] = {sp[0].n ? h_ctl[3] : 0, sp[1].n ? h_ctl[4] : 0};
-    for (int i = 0; i < n_streams; i++)
-        if (lines[i] % 4) return fail(FQG_E_FASTQ, "FASTQ parse error: truncated final record (UnexpectedEnd)");
-    const uint64_t rec1 = lines[0] / 4, rec2 = lines[1] / 4;
-    uint64_t units = rec1;
-    if (mode == FQG_PAIRED) {
-        if (rec1 != rec2) return fail(FQG_E_PAIR_MISMATCH, "FASTQ files out of sync: R1 has " + std::to_string(rec1) + " records, R2 has " + std::to_string(rec2));
-    } else if (mode == FQG_INTERLEAVED) {
-        if (rec1 % 2) return fail(FQG_E_FASTQ, "FASTQ file does not have an even number of records.");
-        units = rec1 / 2;
-    }
-    if (check_ids && h_ctl[2] != ~0ull) return fail(FQG_E_PAIR_MISMATCH, "Mismatching read pair! (pair " + std::to_string(h_ctl[2]) + ")");
-    res->n_records = rec1 + (mode == FQG_PAIRED ? rec2 : 0);
-    res->n_units = units;
-    res->n_selected = h_ctl[1];
-    if (unit_mask_out) {
-        const uint64_t need = (units + 31) / 32;
-        if (need > unit_mask_words) return fail(FQG_E_INVALID_ARG, "unit_mask_out too small: need " + std::to_string(need) + " words");
-        if (need) {
-            CU_TRY(cudaMemcpyAsync(unit_mask_out, unit_mask_dev, need * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, cs));
-            CU_TRY(cudaEventRecord(c->ev[4], cs));
-            CU_TRY(cudaStreamSynchronize(cs));
-            if (!on_device) d2h_bytes += need * 4;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
-            res->d2h_ms = ms;
-        }
-    }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]);
-    res->kernel_ms = ms;
-    if (!on_device && h2d_bytes) {
-        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
-        res->h2d_ms = ms;
-    }
-    res->h2d_bytes = h2d_bytes;
-    res->d2h_bytes = d2h_bytes;
-    return FQG_OK;
-}
-
-// Output arrays are sized for records of >= 32 bytes first; denser files (the reference's 4-base test fixtures) retry at 8.
-int grep_fastq(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, bool on_device,
-               uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res, cudaStream_t user_stream) {
-    bool hit = false;
-    unsigned stripped = 0, min_rec = 32;
-    int rc = grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, res, user_stream, min_rec, &hit, nullptr, 0, &stripped);
-    if (rc && hit) rc = grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, res, user_stream, min_rec = 8, &hit, nullptr, 0, &stripped);
-    if ((rc == FQG_E_FASTQ || rc == FQG_E_PAIR_MISMATCH) && stripped) {
-        // a last record with an empty quality line, in either stream? (see where the trailing terminators are dropped)
-        const std::string first_error = fqg_last_error();
-        for (unsigned keep = 1; keep <= 3; keep++) {
-            if ((keep & stripped) != keep) continue;
-            fqg_result again;
-            if (grep_fastq_once(c, m, mode, r1, n1, r2, n2, on_device, unit_mask_out, unit_mask_words, &again, user_stream, min_rec, &hit, nullptr, keep) == FQG_OK) {
-                *res = again;
-                return FQG_OK;
-            }
-        }
-        return fail(rc, first_error);
-    }
-    return rc;
-}
-
-}  // namespace
+}  // namespace fqg
 
 extern "C" {
 
@@ -679,9 +346,6 @@ int fqg_ctx_create(int device, fqg_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (auto& ev : c->ev) CU_TRY(cudaEventCreate(&ev));
-    for (auto& ev : c->chunk_ev) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     *out = c.release();
     return FQG_OK;
 }
@@ -690,13 +354,9 @@ void fqg_ctx_destroy(fqg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    fastq_state_free(&c->fq);
+    lanes_free(c);
     for (auto& b : c->d_buf) cudaFree(b);
-    if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : c->chunk_ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -721,15 +381,11 @@ int fqg_match_bases_device(fqg_ctx* c, const fqg_matcher* m, const uint8_t* d_ba
     if (rc) return rc;
     if (m->kind == FQG_NAMES) {      // the spans are header lines (without '@'), not sequences
         NamesView nv;
-        {
-            std::lock_guard<std::mutex> lock(const_cast<fqg_matcher*>(m)->mu);
-            const DeviceTables& t = const_cast<fqg_matcher*>(m)->dev[c->device];
-            nv.slots = t.slots; nv.slot_off = t.slot_off; nv.pool = t.pool; nv.mask = m->names.n_slots / 4 - 1;
-        }
+        if ((rc = get_names_view(c, m, &nv))) return rc;
         SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
                    (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr};
         CU_TRY(launch_match_names_soa(nv, b, c->sm_count, (cudaStream_t)stream));
-        g_launches++;
+        count_launches(1);
         return FQG_OK;
     }
     if (m->split_lit) {
@@ -741,13 +397,13 @@ int fqg_match_bases_device(fqg_ctx* c, const fqg_matcher* m, const uint8_t* d_ba
         SoaBatch b2{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
                     (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, d_mask_out};
         CU_TRY(launch_match_soa(d2, b2, c->sm_count, (cudaStream_t)stream));
-        g_launches += 2;
+        count_launches(2);
         return FQG_OK;
     }
     SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
                (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr};
     CU_TRY(launch_match_soa(dd, b, c->sm_count, (cudaStream_t)stream));
-    g_launches++;
+    count_launches(1);
     return FQG_OK;
 }
 
@@ -817,20 +473,33 @@ int fqg_synth_reads_device(fqg_ctx* c, uint8_t* d_out, uint64_t n_reads, uint64_
     p.plant_blob = (const uint8_t*)d_blob;
     p.plant_offs = (const uint32_t*)d_offs;
     CU_TRY(launch_synth(p, st));
-    g_launches++;
+    count_launches(1);
     return FQG_OK;
 }
 
 int fqg_grep_fastq_device(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* d_r1, size_t n1, const uint8_t* d_r2, size_t n2,
                           uint32_t* d_unit_mask_out, size_t unit_mask_words, fqg_result* res, void* stream) {
     if (!c || !m || !res) return fail(FQG_E_INVALID_ARG, "NULL argument");
-    return grep_fastq(c, m, mode, d_r1, n1, d_r2, n2, true, d_unit_mask_out, unit_mask_words, res, (cudaStream_t)stream);
-}
-
-int fqg_grep_fastq_host(fqg_ctx* c, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2,
-                        uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res) {
-    if (!c || !m || !res) return fail(FQG_E_INVALID_ARG, "NULL argument");
-    return grep_fastq(c, m, mode, r1, n1, r2, n2, false, unit_mask_out, unit_mask_words, res, c->stream);
+    std::memset(res, 0, sizeof *res);
+    BatchIn in;
+    in.mode = mode;
+    in.r[0] = d_r1; in.n[0] = n1; in.r[1] = d_r2; in.n[1] = n2;
+    in.on_device = true;
+    in.user_stream = (cudaStream_t)stream;
+    BatchOut out;
+    FastqLane* lane = lane_lease(c);
+    struct Release { fqg_ctx* c; FastqLane* l; ~Release() { lane_release(c, l); } } release{c, lane};
+    int rc = grep_fastq_batch(c, lane, m, in, &out);
+    if (rc) return rc;
+    *res = out.res;
+    if (d_unit_mask_out) {
+        if (out.mask_words > unit_mask_words) return fail(FQG_E_INVALID_ARG, "unit_mask_out too small: need " + std::to_string(out.mask_words) + " words");
+        if (out.mask_words) {
+            CU_TRY(cudaMemcpyAsync(d_unit_mask_out, out.unit_mask_dev, out.mask_words * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        }
+    }
+    return FQG_OK;
 }
 
 int fqg_iupac_expand(const char* pattern, int to_regex, char* out, size_t cap, size_t* out_len) {
@@ -869,18 +538,18 @@ int fqg_index_fastq_device(fqg_ctx* c, const uint8_t* d_fastq, size_t n, uint64_
     idx.seq_start = reinterpret_cast<unsigned long long*>(d_seq_start);
     idx.seq_len = d_seq_len;
     idx.cap = capacity;
-    fqg_result res;
-    bool hit = false;
-    unsigned stripped = 0, min_rec = 32;
-    int rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, min_rec, &hit, &idx, 0, &stripped);
-    if (rc && hit) rc = grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, min_rec = 8, &hit, &idx, 0, &stripped);
-    if (rc == FQG_E_FASTQ && stripped) {      // last record with an empty quality line, see grep_fastq
-        const std::string first_error = fqg_last_error();
-        if (grep_fastq_once(c, nullptr, FQG_SINGLE, d_fastq, n, nullptr, 0, true, nullptr, 0, &res, (cudaStream_t)stream, min_rec, &hit, &idx, 1) != FQG_OK)
-            return fail(rc, first_error);
-        rc = FQG_OK;
-    }
+    BatchIn in;
+    in.mode = FQG_SINGLE;
+    in.r[0] = d_fastq; in.n[0] = n;
+    in.on_device = true;
+    in.user_stream = (cudaStream_t)stream;
+    in.idx = &idx;
+    BatchOut out;
+    FastqLane* lane = lane_lease(c);
+    struct Release { fqg_ctx* c; FastqLane* l; ~Release() { lane_release(c, l); } } release{c, lane};
+    int rc = grep_fastq_batch(c, lane, nullptr, in, &out);
     if (rc) return rc;
+    const fqg_result& res = out.res;
     *n_records = res.n_records;
     if (res.n_records > capacity) return fail(FQG_E_INVALID_ARG, "index arrays too small: " + std::to_string(res.n_records) + " records");
     return FQG_OK;
@@ -895,7 +564,7 @@ int fqg_compact_bases_device(fqg_ctx* c, const uint8_t* d_fastq, const uint64_t*
     if (rc) return rc;
     CU_TRY(launch_compact_bases(d_fastq, reinterpret_cast<const unsigned long long*>(d_seq_start), d_seq_len, n_records, d_bases_out, d_offsets_out,
                                 (uint32_t*)scratch, (cudaStream_t)stream));
-    g_launches += n_records ? 4 : 0;
+    count_launches(n_records ? 4 : 0);
     return FQG_OK;
 }
 

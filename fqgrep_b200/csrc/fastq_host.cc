@@ -14,19 +14,9 @@
 #include <thread>
 #include <vector>
 
-#include <cuda_runtime.h>
-
 #include "../../include/fqgrep_b200.h"
 
 namespace fqg {
-
-void fastq_state_free(FastqDeviceState* s) {
-    for (auto& p : s->scratch) {
-        if (p) cudaFree(p);
-        p = nullptr;
-    }
-    for (auto& c : s->cap) c = 0;
-}
 
 namespace {
 inline const uint8_t* eol(const uint8_t* p, const uint8_t* e) {
@@ -279,6 +269,72 @@ int write_selected_host(int mode, const uint8_t* r1, size_t n1, const uint8_t* r
     }
     *out_len = (size_t)(o - out);
     if (out2_len) *out2_len = out2 ? (size_t)(o2 - out2) : 0;
+    return 0;
+}
+
+// ---- write-back from device spans (K5) -----------------------------------------------------------------------------------
+// The fused kernel already knows where every record starts and ends and whether its bytes are in write_to form, so the
+// selected records arrive as (offset, length, flags) in output order and the host's share of src/main.rs:641-657 /
+// write_paired_record (:682-727) is a gather: byte copies, and re-formatting only for records with CR line ends, a
+// "+name" separator line or no final newline.  Output positions are a prefix sum of the span lengths, so large
+// batches are copied by all host threads at once.
+int write_spans_host(const fqg_span* spans, uint64_t n_spans, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, uint8_t* out, size_t out_cap,
+                     size_t* out_len, uint8_t* out2, size_t out2_cap, size_t* out2_len, std::string* err) {
+    if (!out_len || (n_spans && (!spans || !out))) { *err = "NULL argument"; return FQG_E_INVALID_ARG; }
+    *out_len = 0;
+    if (out2_len) *out2_len = 0;
+    if (n_spans == 0) return 0;
+    auto source = [&](const fqg_span& sp, const uint8_t** buf, size_t* n) { const bool second = (sp.flags & FQG_SPAN_R2) != 0; *buf = second ? r2 : r1; *n = second ? n2 : n1; };
+    // pass 1: where every span lands
+    std::vector<size_t> at(n_spans);
+    size_t o1 = 0, o2 = 0;
+    for (uint64_t i = 0; i < n_spans; i++) {
+        const fqg_span& sp = spans[i];
+        const uint8_t* buf;
+        size_t n;
+        source(sp, &buf, &n);
+        if (!buf || sp.offset > n || sp.len > n - sp.offset) { *err = "span outside its input"; return FQG_E_INVALID_ARG; }
+        size_t len = sp.len;
+        if (sp.flags & FQG_SPAN_NORMALISE) {
+            HostRecord r;
+            size_t pos = 0;
+            if (next_host_record(buf + sp.offset, sp.len, &pos, &r, err) != 1) return FQG_E_FASTQ;
+            len = r.head_len + r.seq_len + r.qual_len + 6;
+        }
+        size_t& o = (out2 && (sp.flags & FQG_SPAN_R2)) ? o2 : o1;
+        at[i] = o;
+        o += len;
+    }
+    if (o1 > out_cap || o2 > out2_cap) { *err = "output buffer too small for the selected records"; return FQG_E_TOO_LARGE; }
+    // pass 2: copy / re-format
+    auto emit_range = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; i++) {
+            const fqg_span& sp = spans[i];
+            const uint8_t* buf;
+            size_t n;
+            source(sp, &buf, &n);
+            uint8_t* dst = ((out2 && (sp.flags & FQG_SPAN_R2)) ? out2 : out) + at[i];
+            if (sp.flags & FQG_SPAN_NORMALISE) {
+                HostRecord r;
+                size_t pos = 0;
+                std::string e;
+                if (next_host_record(buf + sp.offset, sp.len, &pos, &r, &e) == 1) emit(dst, r);
+            } else {
+                memcpy(dst, buf + sp.offset, sp.len);
+            }
+        }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 4;
+    if (nt > 16) nt = 16;
+    if (n_spans < 65536 || nt < 2) emit_range(0, n_spans);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(emit_range, n_spans * t / nt, n_spans * (t + 1) / nt);
+        for (auto& th : pool) th.join();
+    }
+    *out_len = o1;
+    if (out2_len) *out2_len = o2;
     return 0;
 }
 

@@ -4,14 +4,9 @@
 #include <cstdint>
 #include <string>
 
-namespace fqg {
+#include "../../include/fqgrep_b200.h"
 
-// Device-side scratch owned by a context for the raw-FASTQ path (filled in by fastq path code).
-struct FastqDeviceState {
-    void* scratch[10] = {nullptr};
-    size_t cap[10] = {0};
-};
-void fastq_state_free(FastqDeviceState* s);
+namespace fqg {
 
 // One FASTQ record as seq_io 0.3.4 exposes it (head without '@', CR stripped).
 struct HostRecord {
@@ -28,6 +23,15 @@ int read_input(const char* path, int decompress, int pinned, uint8_t** out, size
 void free_input(uint8_t* p, int pinned);
 
 size_t find_record_start(const uint8_t* buf, size_t n, size_t pos);
+
+// batch cutter of the streaming path (fastq_cut.cc); see fqg_fastq_cut in include/fqgrep_b200.h
+int fastq_cut(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, size_t limit, bool final, bool exact, size_t* cut1, size_t* cut2);
+uint64_t count_newlines(const uint8_t* p, size_t n);
+size_t offset_after_newline(const uint8_t* p, size_t n, uint64_t k);
+
+// write-back from device spans (fastq_host.cc); see fqg_write_spans
+int write_spans_host(const fqg_span* spans, uint64_t n_spans, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, uint8_t* out, size_t out_cap,
+                     size_t* out_len, uint8_t* out2, size_t out2_cap, size_t* out2_len, std::string* err);
 
 // Ordered write-back of selected units (src/main.rs:641-657, 682-727).
 int write_selected_host(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, const uint32_t* unit_mask, uint8_t* out,

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/fqgrep_b200.h"
+
 namespace fqg {
 
 // Device-resident automaton in the layout the kernels index directly.
@@ -76,7 +78,7 @@ struct FastqArgs {
     unsigned long long* lines_out;     // total newline count, written by the stream's last tile
     uint32_t* mask;                // zeroed record bitmask, bit = global record number
     uint64_t mask_bits;
-    uint32_t* id_hash;             // optional, one per record (pair id check)
+    unsigned long long* id_hash;   // optional, one 64-bit id hash per record (pair id check, src/main.rs:741-747)
     uint64_t id_hash_cap;
     unsigned long long* count;     // optional
     unsigned long long* err;       // min over (position << 4 | code), initialised to ~0
@@ -85,6 +87,16 @@ struct FastqArgs {
     unsigned long long* seq_start;  // optional record index (K0): stream offset of every record's sequence line ...
     uint32_t* seq_len;              // ... and its length without line terminator
     uint64_t span_cap;
+    // optional record spans (K5, write-back without re-parsing): stream offset of every record's '@' with bit 63 set when
+    // the record is not already in seq_io's write_to form (CR line ends, "+name" separator, missing final newline), and
+    // its length in bytes including the final newline when there is one
+    unsigned long long* rec_off;
+    uint32_t* rec_len;
+    uint64_t rec_cap;
+    // 0x0A0A0A0A and 0x7F7F7F7F, filled in by launch_match_fastq.  They travel as kernel PARAMETERS because the newline test
+    // needs two constants per LOP3 and the instruction takes one immediate: as literals (even behind an asm mov, which
+    // ptxas folds) every byte-test costs five instructions per word; as constant-bank operands it costs three.
+    uint32_t nl_xor, nl_low7;
 };
 // -N over SoA headers: spans are header lines without '@'; the id ends at the first space (matcher.rs:631-638)
 cudaError_t launch_match_names_soa(const NamesView& nv, const SoaBatch& b, int sm_count, cudaStream_t stream);
@@ -96,11 +108,18 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only
 cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n_records,
                                  uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream);
 uint64_t compact_scratch_words(uint64_t n_records);
-cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
+cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const unsigned long long* h1, const unsigned long long* h2,
                                  uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
                                  unsigned long long* id_mismatch, cudaStream_t stream);
-cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const uint32_t* h, uint64_t idh_cap,
+cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const unsigned long long* h, uint64_t idh_cap,
                                        const unsigned long long* lines, unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream);
+
+// K5: order-preserving compaction of the selected records' spans (fqg_span, include/fqgrep_b200.h) by the unit mask.
+// `lines` is the device line count of stream 1 (units = lines / 4, / 8 when interleaved); n_spans_out receives the count.
+uint64_t span_scan_words(uint64_t mask_words);
+cudaError_t launch_select_spans(const uint32_t* unit_mask, uint64_t mask_words, int mode, const unsigned long long* lines, const unsigned long long* off0,
+                                const uint32_t* len0, const unsigned long long* off1, const uint32_t* len1, fqg_span* out, unsigned long long* n_spans_out,
+                                uint32_t* block_sums, cudaStream_t stream);
 
 // Synthetic benchmark input generator; see synth.cu.
 struct SynthParams {

@@ -8,14 +8,24 @@
 //     src/main.rs:635-640 -> src/lib/matcher.rs:164-175), incl. QueryNameMatcher::read_match (:631-638);
 //   * the per-record `found` flag (src/main.rs:558-575, 635-657), emitted as one bit per record.
 //
-// Shape: the byte stream is cut into 16 KB tiles.  A CTA takes the next tile id from an atomic counter
-// (in-order acquisition), pulls tile + 2 KB of overlap into shared memory with one bulk async copy (TMA),
-// builds a newline bitmap with SIMD-within-register byte compares, and obtains the number of newlines
-// before its tile by a decoupled look-back over per-tile aggregates (single pass, no second read of HBM).
-// With the global line number known, every record that STARTS in the tile is handled by one thread:
-// the four line ends come from the bitmap, the sequence line is walked through the DFA straight out of
-// shared memory, and the selection bit is OR-ed into the global record bitmask.  Records that do not end
-// inside tile+overlap (reads longer than ~1 kb) fall back to a global-memory walk.
+// Shape: WARP-AUTONOMOUS TILES.  The byte stream is cut into tiles of 29 x 336 = 9744 bytes.  Every warp of the
+// persistent grid runs the whole tile loop on its own, with no CTA-wide barrier after start-up:
+//   1. claim the next tile id from an atomic counter (in order), pull tile + 1008 bytes of overlap into the warp's own
+//      shared-memory buffer with ONE bulk async copy (TMA, completion on the warp's mbarrier);
+//   2. newline masks: lane l owns the 336 bytes [336 l, 336 l + 336) of the buffer -- 21 LDS.128 at a lane stride of 21
+//      16-byte units, which is bank-conflict free because 21 is odd -- and turns them into 11 bitmap words held in
+//      REGISTERS (exact per-byte test in 3 integer ops per word, bits gathered by IDP.4A);
+//   3. popcounts -> warp scan -> the tile's newline count is published for the decoupled look-back;
+//   4. every newline's position is scattered into a small shared list at its rank (so line k of the tile is list[k]);
+//   5. the look-back (two levels, see lookback_resolve) yields the global line number of the tile's first byte, hence
+//      the record phase (line number mod 4) and the global record number of the tile's first record;
+//   6. lane k takes record k of the tile: five list entries give the record start and its four line ends, the
+//      record is validated by seq_io's rules and its sequence line is walked through the DFA straight out of shared
+//      memory (or its id probed in the name table); ballot -> atomicOr into the global record bitmask.
+// Records that do not end inside tile + overlap (reads longer than ~400 bases) are walked in global memory.
+// Round 1's kernel shared one 19 KB tile between the four warps of a "tile group" and needed four group barriers, a
+// shared bitmap, a binary search per record and a bit-scan per line end: 80 warp-instructions per record and 8.9 barrier
+// stalls per issue (profiles/r1zz_match_fastq_ncu_full.txt); this shape does the same work in about half the instructions.
 #include "dfa_device.cuh"
 #include "kernels.hpp"
 #include "names_device.cuh"
@@ -23,11 +33,20 @@
 namespace fqg {
 namespace {
 
-constexpr uint32_t kTile = 19456;            // 19 KB: ~61 records of 317 B, i.e. two almost full warps in the record phase
-constexpr uint32_t kOverlap = 1024;
-constexpr uint32_t kLoad = kTile + kOverlap;
-constexpr uint32_t kGroups = kLoad / 32;          // one bitmap word per 32 bytes
-constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kUnits = 21;                        // 16-byte units per lane; ODD => lane-strided LDS.128 hits 8 distinct bank groups
+constexpr uint32_t kLaneBytes = kUnits * 16u;          // 336
+constexpr uint32_t kTileLanes = 29;                    // lanes 0..28 hold the tile proper, lanes 29..31 the overlap
+constexpr uint32_t kTile = kTileLanes * kLaneBytes;    // 9744: ~30.7 records of 317 bytes, one per lane in the record phase
+constexpr uint32_t kLoad = 32u * kLaneBytes;           // 10752 bytes staged per tile
+constexpr uint32_t kOverlap = kLoad - kTile;           // 1008
+constexpr uint32_t kWords = (kUnits + 1u) / 2u;        // 11 bitmap words per lane (the last one holds 16 bits)
+constexpr uint32_t kListCap = 1024;                    // newline positions per window; denser tiles take several windows
+constexpr uint32_t kWindowStep = kListCap - 8u;        // ranks a window is responsible for (a record needs 5 consecutive ranks)
+// per-warp shared memory: [mbarrier, 128][newline list, 2 * kListCap + 128][tile, kLoad + 128]
+constexpr uint32_t kWarpListOff = 128u, kWarpTileOff = kWarpListOff + 2u * kListCap + 128u;
+constexpr uint32_t kWarpBytes = kWarpTileOff + kLoad + 128u;
+static_assert(kWarpBytes % 128u == 0 && kWarpTileOff % 128u == 0, "TMA destination alignment");
+static_assert(kTile % 16u == 0, "tiles start on 16-byte boundaries (bulk copy source alignment)");
 
 enum : uint32_t { kErrInvalidStart = 1, kErrInvalidSep = 2, kErrUnequal = 3, kErrUnexpectedEnd = 4, kErrMaskOverflow = 6 };
 
@@ -45,12 +64,30 @@ __device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t a) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
 
-// 4 bytes -> 4 bits: bit i set iff byte i == '\n'.  Exact per-byte zero test (no borrow false positives).
-__device__ __forceinline__ uint32_t newline_nibble(uint32_t w) {
-    const uint32_t x = w ^ 0x0A0A0A0Au;
-    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where the byte is zero
-    return (z * 0x00204081u) >> 28;
+// 0x80 in every byte of w that is '\n', 0 elsewhere.  Exact (no borrow between bytes): the low 7 bits of a byte of
+// w ^ '\n' overflow into bit 7 of the sum unless they are all zero, and bit 7 of w itself must be clear.  c0a = 0x0A0A0A0A
+// and c7f = 0x7F7F7F7F are passed in REGISTERS so that each of the three steps is one instruction (LOP3 takes a single
+// immediate, and two are needed otherwise; they arrive as kernel parameters, see FastqArgs).
+__device__ __forceinline__ uint32_t newline_flags(uint32_t w, uint32_t c0a, uint32_t c7f) {
+    const uint32_t t = ((w ^ c0a) & c7f) + c7f;
+    uint32_t z;
+    asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(z) : "r"(t), "r"(w), "r"(c7f));      // ~(t | w | c7f) as ONE instruction
+    return z;
+}
+// 16 bytes -> 128 * (16-bit mask, bit i = byte i is '\n'): the flag bytes (0x80) are gathered by two integer dot products
+// per 8 bytes, 0x80 * (1,2,4,8) + 0x80 * (16,32,64,128), so the mask comes out in stream order without any bit shuffling
+__device__ __forceinline__ uint32_t newline_mask8x128(uint32_t w0, uint32_t w1, uint32_t c0a, uint32_t c7f) {
+    uint32_t a = __dp4a(newline_flags(w0, c0a, c7f), 0x08040201u, 0u);
+    return __dp4a(newline_flags(w1, c0a, c7f), 0x80402010u, a);
 }
 
 struct NamesProbe {
@@ -64,6 +101,24 @@ struct NamesProbe {
     }
 };
 
+// Read-id hash for the pair check (src/main.rs:741-747 asserts r1.id_bytes() == r2.id_bytes()).  Two independent 32-bit
+// multiply-xor lanes over the id's little-endian words, the length folded in at the end: ids that differ in a single
+// aligned word can never collide (each step is a bijection of the state), any other pair of different ids collides
+// with probability 2^-64.
+struct IdHash {
+    uint32_t a = 0x811C9DC5u, b = 0x9E3779B9u;
+    __device__ __forceinline__ void word(uint32_t w) {
+        a = (a ^ w) * 0x01000193u;
+        b = (b ^ w) * 0x85EBCA6Bu;
+    }
+    __device__ __forceinline__ unsigned long long finish(uint32_t len) const {
+        uint32_t x = a ^ len, y = b + len * 0x27D4EB2Fu;
+        x ^= x >> 15;
+        y ^= y >> 13;
+        return ((unsigned long long)y << 32) | x;
+    }
+};
+
 // TIER 0,1,2,4: DFA tiers (see kernels.hpp); TIER 3: read-name lookup; TIER 5: index only (no matching).
 template <int TIER>
 struct RecordEval {
@@ -72,15 +127,16 @@ struct RecordEval {
     uint32_t start, accept_from;
     bool invert;
 
-    // record fully in shared memory: s = '@' position, p0..p3 = the four line ends (shared-window addresses)
-    __device__ __forceinline__ bool eval_shared(uint32_t tile, uint32_t s, uint32_t p0, uint32_t p1, uint32_t seq_len, uint32_t* idh, bool want_idh) const {
+    // record fully in shared memory: s = '@' position, p0 = end of the header line (positions in the tile at shared address `tile`)
+    __device__ __forceinline__ bool eval_shared(uint32_t tile, uint32_t s, uint32_t p0, uint32_t seq_len, unsigned long long* idh, bool want_idh) const {
         uint32_t head_end = p0;
         if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
         uint32_t id_len = 0;
         if (TIER == 3 || want_idh) {      // id = header up to the first space; scanned and hashed four bytes at a time
             // (a malformed record may "start" on an empty line: p0 == s, no header bytes at all)
             const uint32_t a0 = tile + s + 1u, n = head_end > s + 1u ? head_end - (s + 1u) : 0u, sh = (a0 & 3u) * 8u;
-            uint32_t wp = a0 & ~3u, w0 = lds_u32_volatile(wp), h = 0x811C9DC5u;
+            uint32_t wp = a0 & ~3u, w0 = lds_u32_volatile(wp);
+            IdHash h;
             id_len = n;
             for (uint32_t i = 0; i < n; i += 4u) {
                 wp += 4u;
@@ -93,15 +149,14 @@ struct RecordEval {
                 if (v < 4u) z &= (1u << (8u * v)) - 1u;
                 if (z) {                                                            // the id ends at the first space
                     const uint32_t bidx = ((uint32_t)__ffs(z) - 1u) >> 3;
-                    if (bidx) h = (h ^ (w & ((1u << (8u * bidx)) - 1u))) * 0x01000193u;
+                    if (bidx) h.word(w & ((1u << (8u * bidx)) - 1u));
                     id_len = i + bidx;
                     break;
                 }
                 if (v < 4u) w &= (1u << (8u * v)) - 1u;
-                h = (h ^ w) * 0x01000193u;
+                h.word(w);
             }
-            h ^= id_len;
-            if (want_idh) *idh = h ^ (h >> 15);
+            if (want_idh) *idh = h.finish(id_len);
         }
         bool found;
         if (TIER == 5) found = false;
@@ -109,18 +164,17 @@ struct RecordEval {
         else found = walk_shared(view, tile + p0 + 1, seq_len, start) >= accept_from;
         return found != invert;
     }
-    __device__ __noinline__ bool eval_global(const uint8_t* head, uint32_t head_len, const uint8_t* seq, uint32_t seq_len, uint32_t* idh, bool want_idh) const {
+    __device__ __noinline__ bool eval_global(const uint8_t* head, uint32_t head_len, const uint8_t* seq, uint32_t seq_len, unsigned long long* idh, bool want_idh) const {
         uint32_t id_len = 0;
         while (id_len < head_len && head[id_len] != ' ') id_len++;
         if (want_idh) {                 // same word-wise hash as eval_shared, assembled from bytes
-            uint32_t h = 0x811C9DC5u;
+            IdHash h;
             for (uint32_t i = 0; i < id_len; i += 4u) {
                 uint32_t w = 0;
                 for (uint32_t b = 0; b < 4u && i + b < id_len; b++) w |= (uint32_t)head[i + b] << (8u * b);
-                h = (h ^ w) * 0x01000193u;
+                h.word(w);
             }
-            h ^= id_len;
-            *idh = h ^ (h >> 15);
+            *idh = h.finish(id_len);
         }
         bool found;
         if (TIER == 5) found = false;
@@ -129,8 +183,6 @@ struct RecordEval {
         return found != invert;
     }
 };
-
-// ---- the phases of one tile, shared by the two kernel shapes below ---------------------------------------------------
 
 struct TileGeom {
     uint32_t t;            // global tile id
@@ -151,66 +203,19 @@ __device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, ui
     return g;
 }
 
-// newline bitmap: one word per 32 bytes, built by `nthreads` cooperating threads
-__device__ __forceinline__ void build_bitmap(uint32_t tile_sa, uint32_t* s_bitmap, const TileGeom& g, uint32_t rtid, uint32_t nthreads) {
-    for (uint32_t grp32 = rtid; grp32 < kGroups + 2; grp32 += nthreads) {
-        uint32_t bits = 0;
-        if (grp32 * 32u < g.real_avail) {
-            const uint4 lo = lds_v4_volatile(tile_sa + grp32 * 32u), hi = lds_v4_volatile(tile_sa + grp32 * 32u + 16u);
-            bits = newline_nibble(lo.x) | (newline_nibble(lo.y) << 4) | (newline_nibble(lo.z) << 8) | (newline_nibble(lo.w) << 12) |
-                   (newline_nibble(hi.x) << 16) | (newline_nibble(hi.y) << 20) | (newline_nibble(hi.z) << 24) | (newline_nibble(hi.w) << 28);
-            if (grp32 * 32u + 32u > g.real_avail) bits &= (1u << (g.real_avail - grp32 * 32u)) - 1u;
-        }
-        if (g.real_avail < g.avail && (g.real_avail >> 5) == grp32) bits |= 1u << (g.real_avail & 31u);   // the virtual final newline
-        s_bitmap[grp32] = bits;
-    }
+// ---- decoupled look-back by one warp ------------------------------------------------------------------------------------
+// Number of newlines before tile t.  Two levels.  Every resident warp works on its own tile at about the same time
+// (~2000 tiles in flight), so a flat look-back finds nothing but aggregates for a whole wave and needs wave/32 dependent L2
+// round trips per tile.  Tiles are therefore grouped in segments of 32: the tile that closes a segment publishes the
+// segment's aggregate as soon as it has seen its 31 predecessors' aggregates, and a look-back sums its own segment first
+// (one round), then hops 32 segments (1024 tiles) per round.  State words: flag << 62 | value, flag 1 = aggregate, 2 =
+// inclusive prefix.  Tiles are handed out in order, so every state a tile waits for belongs to a warp that is already
+// running and publishes it without waiting for anything later: no circular wait.
+// Split in two so that the scatter of the newline list runs between publishing the aggregate and polling the predecessors.
+__device__ __forceinline__ void lookback_publish(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
+    if (t > 0 && lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
 }
-
-// exclusive prefix of newline counts per 32-byte group (thread i owns groups [i*GPT, (i+1)*GPT)); `sync` is the team barrier
-template <uint32_t NTHREADS, typename Sync>
-__device__ __forceinline__ void prefix_counts(const uint32_t* s_bitmap, uint16_t* s_pre, uint32_t* s_wsum, uint32_t rtid, Sync sync) {
-    constexpr uint32_t GPT = (kGroups + NTHREADS - 1) / NTHREADS, NW = NTHREADS / 32;
-    const uint32_t lane = rtid & 31u, warp = rtid >> 5;
-    uint32_t cnt[GPT], mine = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < GPT; k++) {
-        const uint32_t grp32 = rtid * GPT + k;
-        cnt[k] = grp32 < kGroups ? __popc(s_bitmap[grp32]) : 0u;
-        mine += cnt[k];
-    }
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
-        if (lane >= (uint32_t)d) incl += v;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-    sync();
-    uint32_t warp_base = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < NW; w++) if (w < warp) warp_base += s_wsum[w];
-    uint32_t run = warp_base + incl - mine;
-#pragma unroll
-    for (uint32_t k = 0; k < GPT; k++) {
-        const uint32_t grp32 = rtid * GPT + k;
-        if (grp32 <= kGroups) s_pre[grp32] = (uint16_t)run;
-        run += cnt[k];
-    }
-    sync();
-}
-__device__ __forceinline__ uint32_t region_newlines(const uint32_t* s_bitmap, const uint16_t* s_pre, uint32_t region) {
-    return (region & 31u) == 0 ? s_pre[region >> 5] : s_pre[region >> 5] + __popc(s_bitmap[region >> 5]);
-}
-
-// Decoupled look-back by one warp: number of newlines before tile t; publishes this tile's aggregate / inclusive prefix.
-// Two levels.  Every resident tile group works on its own tile at about the same time (1184 tiles in flight), so a flat
-// look-back finds nothing but aggregates for a whole wave and needs wave/32 dependent L2 round trips per tile -- measured,
-// that chain WAS the kernel's run time.  Tiles are therefore grouped in segments of 32: the tile that closes a segment
-// publishes the segment's aggregate as soon as it has seen its 31 predecessors' aggregates, and a look-back sums its own
-// segment first (one round), then hops 32 segments (1024 tiles) per round.  State words: flag << 62 | value, flag 1 =
-// aggregate, 2 = inclusive prefix.  Tiles are handed out in order, so every state a tile waits for belongs to a group that
-// is already running and publishes it without waiting for anything later: no circular wait.
-__device__ __forceinline__ unsigned long long lookback(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
+__device__ __forceinline__ unsigned long long lookback_resolve(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
     const unsigned long long kValue = (1ull << 62) - 1;
     auto poll = [](const unsigned long long* p) {
         unsigned long long st;
@@ -230,7 +235,6 @@ __device__ __forceinline__ unsigned long long lookback(const FastqArgs& a, uint3
     unsigned long long excl = 0;
     const uint32_t r = t & 31u;                    // predecessors inside this tile's own segment
     if (t > 0) {
-        if (lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
         bool done = false;
         const bool mine = lane < r;
         excl = fold(mine ? poll(a.tile_state + (t - 1u - lane)) : 0ull, mine, done);
@@ -247,107 +251,6 @@ __device__ __forceinline__ unsigned long long lookback(const FastqArgs& a, uint3
         if (r == 31u) atomicExch(a.seg_state + (t >> 5), (2ull << 62) | (excl + agg));
     }
     return excl;
-}
-
-// one thread per record that starts in the tile; `rwarp`/`nthreads` describe the team of warps that shares the records
-template <int TIER>
-__device__ __forceinline__ unsigned long long match_records(const FastqArgs& a, const RecordEval<TIER>& ev, uint32_t tile_sa, const uint32_t* s_bitmap,
-                                                            const uint16_t* s_pre, const TileGeom& g, unsigned long long Lt, uint32_t agg,
-                                                            uint64_t stream_len, uint32_t rwarp, uint32_t lane, uint32_t nthreads) {
-    const bool want_idh = a.id_hash != nullptr;
-    unsigned long long local_count = 0;
-    // record k begins right after the newline of local rank j0 + 4 (k - extra)
-    const bool first_global = g.t == 0;
-    const uint32_t extra = first_global ? 1u : 0u;
-    const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
-    const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
-    uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
-    if (g.T0 + g.region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
-    // position of the newline with local rank r (< agg): binary search in the per-group prefix counts, then bit select
-    const uint32_t n_groups_region = (g.region + 31u) >> 5;
-    auto newline_of_rank = [&](uint32_t r) -> uint32_t {
-        uint32_t lo = 0, hi = n_groups_region;             // s_pre[lo] <= r < s_pre[hi]
-        while (hi - lo > 1u) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_pre[mid] <= r) lo = mid; else hi = mid;
-        }
-        uint32_t bits = s_bitmap[lo];
-        for (uint32_t n = r - s_pre[lo]; n; n--) bits &= bits - 1u;
-        return lo * 32u + (uint32_t)__ffs(bits) - 1u;
-    };
-    const uint32_t n_groups_avail = (g.avail + 31u) >> 5;
-    auto next_nl = [&](uint32_t p) -> uint32_t {
-        uint32_t grp32 = p >> 5;
-        if (grp32 >= n_groups_avail) return kNone;
-        uint32_t w = s_bitmap[grp32] & (0xFFFFFFFFu << (p & 31u));
-        while (!w) {
-            if (++grp32 >= n_groups_avail) return kNone;
-            w = s_bitmap[grp32];
-        }
-        return grp32 * 32u + (uint32_t)__ffs(w) - 1u;
-    };
-    const uint64_t T0 = g.T0;
-    for (uint32_t k0 = rwarp * 32u; k0 < n_list; k0 += nthreads) {
-        const uint32_t k = k0 + lane;
-        const bool valid = k < n_list;
-        bool sel = false;
-        uint32_t idh = 0, seq_n = 0;
-        unsigned long long seq_pos = 0;
-        if (valid) {
-            const uint32_t s = k < extra ? 0u : newline_of_rank(j0 + 4u * (k - extra)) + 1u;
-            const uint32_t p0 = next_nl(s);
-            const uint32_t p1 = p0 == kNone ? kNone : next_nl(p0 + 1u);
-            const uint32_t p2 = p1 == kNone ? kNone : next_nl(p1 + 1u);
-            const uint32_t p3 = p2 == kNone ? kNone : next_nl(p2 + 1u);
-            if (p3 != kNone) {
-                const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
-                const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
-                const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
-                if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
-                else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
-                else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
-                seq_pos = T0 + p0 + 1u;
-                seq_n = seq_len;
-                sel = ev.eval_shared(tile_sa, s, p0, p1, seq_len, &idh, want_idh);
-            } else {
-                // record runs past tile+overlap (or the stream is truncated): walk it in global memory
-                const uint8_t* base = a.buf;
-                const uint64_t gs = T0 + s;
-                uint64_t q[4];
-                uint64_t p = gs;
-                int found = 0;
-                for (; found < 4 && p < stream_len; p++)
-                    if (p == a.nbytes || base[p] == '\n') q[found++] = p;
-                if (found < 4) report(a, gs, kErrUnexpectedEnd);
-                else {
-                    const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
-                    const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
-                    const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
-                    const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
-                    if (base[gs] != '@') report(a, gs, kErrInvalidStart);
-                    else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
-                    else if (seq_len != qual_len) report(a, gs, kErrUnequal);
-                    seq_pos = q[0] + 1;
-                    seq_n = (uint32_t)seq_len;
-                    sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
-                }
-            }
-        }
-        const unsigned long long R_w = R_base + k0;      // record number of lane 0
-        if (valid) {
-            if (R_base + k >= a.mask_bits || (want_idh && R_base + k >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
-            else if (want_idh) a.id_hash[R_base + k] = idh;
-            if (a.seq_start && R_base + k < a.span_cap) { a.seq_start[R_base + k] = seq_pos; a.seq_len[R_base + k] = seq_n; }
-        }
-        const uint32_t m = __ballot_sync(kFullMask, sel);
-        if (lane == 0 && m) {
-            const uint32_t sh = (uint32_t)(R_w & 31ull);
-            atomicOr(a.mask + (R_w >> 5), m << sh);
-            if (sh && (m >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, m >> (32u - sh));
-            local_count += __popc(m);
-        }
-    }
-    return local_count;
 }
 
 template <int TIER>
@@ -379,91 +282,214 @@ __device__ __forceinline__ void stage_automaton(const DeviceDfa& dfa, uint8_t* s
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
 }
 
-// ---- the kernel: symmetric tile groups ----------------------------------------------------------------------------------
-// (A warp-specialised shape -- 2 scanner + 2 matcher warps per group over two tile buffers -- was built and measured this
-// round: same results, 0.95x on the DFA path and 0.83x on -N, because two buffers per group halve the groups an SM can hold
-// and the 16 remaining warps hide less latency than the overlap wins.  It was removed; see DESIGN.md.)
-// per-group shared memory: [mbarrier 8][prefix 8][misc 240][tile kLoad+32][bitmap][pre], 128-byte aligned
-constexpr uint32_t kGroupBytes = ((256u + (kLoad + 32u) + (kGroups + 2u) * 4u + (kGroups + 2u) * 2u) + 127u) & ~127u;
-
-// A CTA is up to 8 independent "tile groups" of THREADS threads (named barriers 1..8) that share one copy of the
-// automaton in shared memory; each group runs the tile loop on its own buffers, so one SM keeps up to 8 tiles in
-// different phases (copy / scan / look-back / match) in flight.
-template <int TIER, int THREADS>
-__global__ void __launch_bounds__(1024, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+// ---- the kernel ---------------------------------------------------------------------------------------------------------
+template <int TIER>
+__global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t grp = threadIdx.x / THREADS, tid = threadIdx.x % THREADS, lane = tid & 31u, warp = tid >> 5;
-    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1u), "n"(THREADS) : "memory"); };
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    // ---- smem carve-up
+    // ---- smem carve-up: [automaton][class LUT 256][per-warp regions]
     uint8_t* s_tab = smem;
-    uint8_t* s_cls = smem + table_smem_bytes;                                // 256 B, shared by all groups
-    uint8_t* s_grp = s_cls + 256 + (size_t)grp * kGroupBytes;                // this group's private region (128-byte aligned)
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp);
-    unsigned long long* s_prefix = reinterpret_cast<unsigned long long*>(s_bar + 1);
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2);               // warp sums, [40] = tile id
-    uint8_t* s_tile = s_grp + 256;                                           // kLoad + 32, 128-byte aligned for the bulk copy
-    uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_tile + kLoad + 32);   // kGroups + 2
-    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bitmap + kGroups + 2);   // kGroups + 2
+    uint8_t* s_cls = smem + table_smem_bytes;
+    uint8_t* s_warp = s_cls + 256 + (size_t)warp * kWarpBytes;
+    const uint32_t bar = smem_addr(s_warp), list_sa = bar + kWarpListOff, tile_sa = bar + kWarpTileOff;
 
     stage_automaton<TIER>(dfa, s_tab, s_cls);
-    if (tid == 0) mbar_init(smem_addr(s_bar), 1);
+    if (lane == 0) mbar_init(bar, 1);
     mbar_fence_init();
     __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
 
     const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
-    const uint32_t tile_sa = smem_addr(s_tile), bar = smem_addr(s_bar);
     // the stream always ends with a newline: a real one, or a virtual one at offset nbytes (missing final '\n')
     const uint64_t stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
+    const bool want_idh = a.id_hash != nullptr;
+    const uint32_t c0a = a.nl_xor, c7f = a.nl_low7;     // see FastqArgs: not compile-time constants on purpose
+    const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
     for (;;) {
-        if (tid == 0) s_misc[40] = atomicAdd(a.tile_counter, 1u);
-        group_sync();
-        if (s_misc[40] >= a.tile_count) break;
-        const TileGeom g = tile_geom(a, a.tile_first + s_misc[40], stream_len);
+        uint32_t claim = 0;
+        if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
+        claim = __shfl_sync(kFullMask, claim, 0);
+        if (claim >= a.tile_count) break;
+        const TileGeom g = tile_geom(a, a.tile_first + claim, stream_len);
         if (g.real_avail) {
-            if (tid == 0) {
+            if (lane == 0) {
                 const uint32_t bytes = (g.real_avail + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
-                // Tiles are handed out in order, so the tile one full wave ahead (one per resident group) is the one some
-                // group will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~24 MB) so that copy
-                // only pays L2 latency.  Each group has a single tile buffer, hence no other way to keep HBM busy.
-                const uint32_t ahead = s_misc[40] + gridDim.x * (blockDim.x / THREADS);
+                // Tiles are handed out in order, so the tile one full wave ahead (one per resident warp) is the one some
+                // warp will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~22 MB) so that copy
+                // only pays L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
+                const uint32_t ahead = claim + gridDim.x * nwarps;
                 if (ahead < a.tile_count) {
                     const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
                     if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
                 }
-                // one thread polls the transaction barrier; the rest of the group sleeps on the (hardware) named barrier
-                // instead of spinning on try_wait and stealing issue slots from the other groups of the SM
-                mbar_wait(bar, phase);
             }
+            mbar_wait(bar, phase);       // try_wait suspends the warp in hardware; no issue slots are burnt
             phase ^= 1u;
-            group_sync();
         }
-        build_bitmap(tile_sa, s_bitmap, g, tid, THREADS);
-        group_sync();
-        prefix_counts<THREADS>(s_bitmap, s_pre, s_misc, tid, group_sync);
-        const uint32_t agg = region_newlines(s_bitmap, s_pre, g.region);
-        if (warp == 0) {
-            const unsigned long long excl = lookback(a, g.t, agg, lane);
-            if (lane == 0) {
-                *s_prefix = excl;
-                if (g.T0 + g.region == stream_len) *a.lines_out = excl + agg;
+
+        // ---- 2. newline masks of this lane's 336 bytes, in registers
+        uint32_t m[kWords];
+        {
+            const uint32_t base = tile_sa + lane_pos;
+#pragma unroll
+            for (uint32_t j = 0; j < kWords; j++) {
+                const uint4 lo = lds_v4_volatile(base + 32u * j);
+                const uint32_t a0 = newline_mask8x128(lo.x, lo.y, c0a, c7f), b0 = newline_mask8x128(lo.z, lo.w, c0a, c7f);
+                if (2u * j + 1u < kUnits) {
+                    const uint4 hi = lds_v4_volatile(base + 32u * j + 16u);
+                    const uint32_t a1 = newline_mask8x128(hi.x, hi.y, c0a, c7f), b1 = newline_mask8x128(hi.z, hi.w, c0a, c7f);
+                    m[j] = (a0 >> 7) + (b0 << 1) + (a1 << 9) + (b1 << 17);
+                } else {
+                    m[j] = (a0 >> 7) + (b0 << 1);
+                }
+            }
+            if (g.real_avail < kLoad) {      // warp-uniform and rare: the stream ends inside this buffer
+#pragma unroll
+                for (uint32_t j = 0; j < kWords; j++) {
+                    const uint32_t lo = lane_pos + 32u * j, width = (2u * j + 1u < kUnits) ? 32u : 16u;
+                    if (lo + width > g.real_avail) m[j] &= g.real_avail > lo ? (1u << (g.real_avail - lo)) - 1u : 0u;     // stale bytes
+                    if (g.real_avail < g.avail && g.real_avail >= lo && g.real_avail < lo + width) m[j] |= 1u << (g.real_avail - lo);   // the virtual final newline
+                }
             }
         }
-        group_sync();
-        local_count += match_records<TIER>(a, ev, tile_sa, s_bitmap, s_pre, g, *s_prefix, agg, stream_len, warp, lane, THREADS);
-        group_sync();   // tile and bitmap are free for the next iteration
+
+        // ---- 3. ranks: newlines before this lane's bytes; the tile's own count (lanes 0..28, or everything in the stream's last tile)
+        uint32_t cnt = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < kWords; j++) cnt += (uint32_t)__popc(m[j]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (uint32_t)d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        const uint32_t agg = g.region == kTile ? __shfl_sync(kFullMask, incl, kTileLanes - 1u) : total;
+        lookback_publish(a, g.t, agg, lane);
+
+        unsigned long long Lt = 0;
+        bool have_Lt = false;
+        for (uint32_t win_lo = 0;; win_lo += kWindowStep) {
+            // ---- 4. scatter: list[rank - win_lo] = position in the tile
+            {
+                uint32_t idx = incl - cnt - win_lo;       // may wrap below zero: compared unsigned against the capacity
+#pragma unroll
+                for (uint32_t j = 0; j < kWords; j++) {
+                    uint32_t w = m[j];
+                    const uint32_t pos0 = lane_pos + 32u * j;
+                    while (w) {
+                        const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+                        if (idx < kListCap) sts_u16(list_sa + 2u * idx, pos0 + b);
+                        idx++;
+                        w &= w - 1u;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- 5. global line number of the tile's first byte (once per tile; the scatter above ran while the predecessors published)
+            if (!have_Lt) {
+                Lt = lookback_resolve(a, g.t, agg, lane);
+                have_Lt = true;
+                if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
+            }
+            // ---- 6. one lane per record that starts in the tile
+            // record k begins right after the newline of local rank j0 + 4 (k - extra)
+            const bool first_global = g.t == 0;
+            const uint32_t extra = first_global ? 1u : 0u;
+            const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
+            const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
+            uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
+            if (g.T0 + g.region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
+            const uint64_t T0 = g.T0;
+            for (uint32_t k0 = 0; k0 < n_list; k0 += 32u) {
+                const uint32_t k = k0 + lane;
+                // ranks: qa = the newline before the record (none for the stream's first record), r0.. r0+3 = its four line ends
+                const uint32_t qa = k < extra ? 0u : j0 + 4u * (k - extra);
+                const uint32_t r0 = k < extra ? 0u : qa + 1u;
+                const bool valid = k < n_list && qa >= win_lo && qa < win_lo + kWindowStep;
+                bool sel = false;
+                unsigned long long idh = 0, seq_pos = 0, rec_off = 0;
+                uint32_t seq_n = 0, rec_n = 0;
+                if (valid) {
+                    const uint32_t li = list_sa + 2u * (r0 - win_lo);
+                    const uint32_t s = k < extra ? 0u : lds_u16_volatile(list_sa + 2u * (qa - win_lo)) + 1u;
+                    if (r0 + 3u < total) {
+                        const uint32_t p0 = lds_u16_volatile(li), p1 = lds_u16_volatile(li + 2u), p2 = lds_u16_volatile(li + 4u), p3 = lds_u16_volatile(li + 6u);
+                        const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
+                        const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
+                        const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
+                        if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
+                        else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
+                        else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
+                        seq_pos = T0 + p0 + 1u;
+                        seq_n = seq_len;
+                        if (a.rec_off) {
+                            const uint32_t cr0 = (p0 > s + 1u && lds_u8_volatile(tile_sa + p0 - 1u) == '\r') ? 1u : 0u;
+                            const bool virt = T0 + p3 == a.nbytes;
+                            const bool norm = (cr0 | cr1 | cr3) != 0 || p2 - p1 != 2u || virt;
+                            rec_off = (T0 + s) | (norm ? 1ull << 63 : 0ull);
+                            rec_n = p3 - s + (virt ? 0u : 1u);
+                        }
+                        sel = ev.eval_shared(tile_sa, s, p0, seq_len, &idh, want_idh);
+                    } else {
+                        // record runs past tile+overlap (or the stream is truncated): walk it in global memory
+                        const uint8_t* base = a.buf;
+                        const uint64_t gs = T0 + s;
+                        uint64_t q[4];
+                        uint64_t p = gs;
+                        int found = 0;
+                        for (; found < 4 && p < stream_len; p++)
+                            if (p == a.nbytes || base[p] == '\n') q[found++] = p;
+                        if (found < 4) report(a, gs, kErrUnexpectedEnd);
+                        else {
+                            const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
+                            const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
+                            const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
+                            const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
+                            if (base[gs] != '@') report(a, gs, kErrInvalidStart);
+                            else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
+                            else if (seq_len != qual_len) report(a, gs, kErrUnequal);
+                            seq_pos = q[0] + 1;
+                            seq_n = (uint32_t)seq_len;
+                            if (a.rec_off) {
+                                const bool virt = q[3] == a.nbytes;
+                                const bool norm = (cr0 | cr1 | cr3) != 0 || q[2] - q[1] != 2u || virt;
+                                rec_off = gs | (norm ? 1ull << 63 : 0ull);
+                                rec_n = (uint32_t)(q[3] - gs + (virt ? 0u : 1u));
+                            }
+                            sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
+                        }
+                    }
+                    const unsigned long long R = R_base + k;
+                    if (R >= a.mask_bits || (want_idh && R >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
+                    else if (want_idh) a.id_hash[R] = idh;
+                    if (a.seq_start && R < a.span_cap) { a.seq_start[R] = seq_pos; a.seq_len[R] = seq_n; }
+                    if (a.rec_off && R < a.rec_cap) { a.rec_off[R] = rec_off; a.rec_len[R] = rec_n; }
+                }
+                const unsigned long long R_w = R_base + k0;      // record number of lane 0
+                const uint32_t mk = __ballot_sync(kFullMask, sel);
+                if (lane == 0 && mk) {
+                    const uint32_t sh = (uint32_t)(R_w & 31ull);
+                    atomicOr(a.mask + (R_w >> 5), mk << sh);
+                    if (sh && (mk >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, mk >> (32u - sh));
+                    local_count += __popc(mk);
+                }
+            }
+            __syncwarp();       // every lane is done with the list (next window) and the tile (next bulk copy)
+            if (win_lo + kWindowStep >= agg) break;
+        }
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
 
 // pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747).
 // Record counts are still on the device (written by the streams' last tiles), so they are read here.
-__global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
+__global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const unsigned long long* h1, const unsigned long long* h2,
                                      uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
                                      unsigned long long* id_mismatch) {
     const uint64_t r1 = *lines1 >> 2, r2 = *lines2 >> 2;
@@ -487,7 +513,7 @@ __global__ void combine_pairs_kernel(const uint32_t* m1, const uint32_t* m2, uin
 }
 
 // interleaved mates (records 2k, 2k+1 of one stream): unit k = bit 2k | bit 2k+1
-__global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const uint32_t* h, uint64_t idh_cap,
+__global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const unsigned long long* h, uint64_t idh_cap,
                                            const unsigned long long* lines, unsigned long long* count, unsigned long long* id_mismatch) {
     uint64_t n_pairs = *lines >> 3;
     uint64_t n_out_words = (n_pairs + 31) >> 5;
@@ -518,22 +544,21 @@ template <int TIER>
 cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
-    constexpr int THREADS = 128;
-    uint32_t groups = (budget - table_smem - 256u - 128u) / kGroupBytes;
-    if (groups > 8u) groups = 8u;
-    if (groups < 1u) groups = 1u;
-    if (a.tile_count < (uint32_t)sm_count * groups) {          // small inputs: spread the tiles over the SMs first
-        groups = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
-        if (groups < 1u) groups = 1u;
+    uint32_t warps = (budget - table_smem - 256u - 128u) / kWarpBytes;      // one tile buffer per warp
+    if (warps > 16u) warps = 16u;
+    if (warps < 1u) warps = 1u;
+    if (a.tile_count < (uint32_t)sm_count * warps) {          // small inputs: spread the tiles over the SMs first
+        warps = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
+        if (warps < 1u) warps = 1u;
     }
-    const uint32_t smem = table_smem + 256u + groups * kGroupBytes + 128u;
-    auto kern = match_fastq_kernel<TIER, THREADS>;
+    const uint32_t smem = table_smem + 256u + warps * kWarpBytes;
+    auto kern = match_fastq_kernel<TIER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uint32_t grid = (a.tile_count + groups - 1u) / groups;
+    uint32_t grid = (a.tile_count + warps - 1u) / warps;
     if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
     if (grid == 0) return cudaSuccess;
-    kern<<<grid, groups * THREADS, smem, stream>>>(a, dfa, table_smem);
+    kern<<<grid, warps * 32u, smem, stream>>>(a, dfa, table_smem);
     return cudaGetLastError();
 }
 
@@ -542,7 +567,10 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_coun
 uint32_t fastq_tile_bytes() { return kTile; }
 uint32_t fastq_overlap_bytes() { return kOverlap; }
 
-cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only, const FastqArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only, const FastqArgs& args, int sm_count, cudaStream_t stream) {
+    FastqArgs a = args;
+    a.nl_xor = 0x0A0A0A0Au;
+    a.nl_low7 = 0x7F7F7F7Fu;
     if (index_only) return launch_fastq_t<5>(dfa, a, sm_count, stream);
     if (names) return launch_fastq_t<3>(dfa, a, sm_count, stream);
     switch (dfa.tier) {
@@ -621,9 +649,77 @@ __global__ void gather_bases_kernel(const uint8_t* fastq, const unsigned long lo
         for (uint32_t i = lane; i < L; i += 32u) dst[i] = src[i];
     }
 }
+
+// ---- K5: spans of the selected records, in output order ----------------------------------------------------------------
+// The write-back of the reference (src/main.rs:641-657, write_paired_record :682-727) walks the records again on the
+// main thread; here the fused kernel has already left every record's (offset, length, "needs normalising") behind, so
+// selecting is an order-preserving compaction of those by the unit mask: popcount per block, scan of the block sums,
+// then every thread deals out the spans of its own mask words.  Pairs emit R1 then R2.
+constexpr uint32_t kSelWordsPerThread = 4, kSelBlockWords = kScanBlock * kSelWordsPerThread;
+
+__device__ __forceinline__ uint64_t sel_units(int mode, const unsigned long long* lines, uint64_t cap_units) {
+    const uint64_t n = mode == FQG_INTERLEAVED ? (*lines >> 3) : (*lines >> 2);
+    return n < cap_units ? n : cap_units;
+}
+__global__ void select_count_kernel(const uint32_t* mask, int mode, const unsigned long long* lines, uint64_t cap_units, uint32_t* block_sums) {
+    __shared__ uint32_t s_w[kScanBlock / 32];
+    const uint64_t n_words = (sel_units(mode, lines, cap_units) + 31) >> 5;
+    const uint64_t w0 = (uint64_t)blockIdx.x * kSelBlockWords + (uint64_t)threadIdx.x * kSelWordsPerThread;
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < kSelWordsPerThread; i++) if (w0 + i < n_words) v += (uint32_t)__popc(mask[w0 + i]);
+    uint32_t tot;
+    block_exclusive_scan(v, s_w, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void select_emit_kernel(const uint32_t* mask, int mode, const unsigned long long* lines, uint64_t cap_units, const uint32_t* block_sums, uint32_t n_blocks,
+                                   const unsigned long long* off0, const uint32_t* len0, const unsigned long long* off1, const uint32_t* len1,
+                                   fqg_span* out, unsigned long long* n_spans_out) {
+    __shared__ uint32_t s_w[kScanBlock / 32];
+    const uint64_t n_words = (sel_units(mode, lines, cap_units) + 31) >> 5;
+    const uint64_t w0 = (uint64_t)blockIdx.x * kSelBlockWords + (uint64_t)threadIdx.x * kSelWordsPerThread;
+    uint32_t word[kSelWordsPerThread], v = 0;
+    for (uint32_t i = 0; i < kSelWordsPerThread; i++) { word[i] = w0 + i < n_words ? mask[w0 + i] : 0u; v += (uint32_t)__popc(word[i]); }
+    uint32_t tot;
+    uint64_t rank = (uint64_t)block_sums[blockIdx.x] + block_exclusive_scan(v, s_w, &tot);
+    const unsigned long long kOff = (1ull << 63) - 1;
+    auto span_of = [&](const unsigned long long* off, const uint32_t* len, uint64_t r, uint32_t flags) {
+        const unsigned long long o = off[r];
+        fqg_span sp;
+        sp.offset = o & kOff;
+        sp.len = len[r];
+        sp.flags = flags | ((o >> 63) ? FQG_SPAN_NORMALISE : 0u);
+        return sp;
+    };
+    for (uint32_t i = 0; i < kSelWordsPerThread; i++) {
+        uint32_t w = word[i];
+        while (w) {
+            const uint64_t u = (w0 + i) * 32u + (uint32_t)__ffs((int)w) - 1u;
+            w &= w - 1u;
+            if (mode == FQG_SINGLE) out[rank] = span_of(off0, len0, u, 0u);
+            else if (mode == FQG_PAIRED) { out[2 * rank] = span_of(off0, len0, u, 0u); out[2 * rank + 1] = span_of(off1, len1, u, FQG_SPAN_R2); }
+            else { out[2 * rank] = span_of(off0, len0, 2 * u, 0u); out[2 * rank + 1] = span_of(off0, len0, 2 * u + 1, 0u); }
+            rank++;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_spans_out = (unsigned long long)block_sums[n_blocks] * (mode == FQG_SINGLE ? 1u : 2u);
+}
 }  // namespace
 
 uint64_t compact_scratch_words(uint64_t n_records) { return (n_records + kScanTile - 1) / kScanTile + 2; }
+
+uint64_t span_scan_words(uint64_t mask_words) { return (mask_words + kSelBlockWords - 1) / kSelBlockWords + 2; }
+
+cudaError_t launch_select_spans(const uint32_t* unit_mask, uint64_t mask_words, int mode, const unsigned long long* lines, const unsigned long long* off0,
+                                const uint32_t* len0, const unsigned long long* off1, const uint32_t* len1, fqg_span* out, unsigned long long* n_spans_out,
+                                uint32_t* block_sums, cudaStream_t stream) {
+    const uint32_t n_blocks = (uint32_t)((mask_words + kSelBlockWords - 1) / kSelBlockWords);
+    if (n_blocks == 0) return cudaMemsetAsync(n_spans_out, 0, 8, stream);
+    const uint64_t cap_units = mask_words * 32u;
+    select_count_kernel<<<n_blocks, kScanBlock, 0, stream>>>(unit_mask, mode, lines, cap_units, block_sums);
+    scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(block_sums, n_blocks);
+    select_emit_kernel<<<n_blocks, kScanBlock, 0, stream>>>(unit_mask, mode, lines, cap_units, block_sums, n_blocks, off0, len0, off1, len1, out, n_spans_out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n_records,
                                  uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream) {
@@ -636,13 +732,13 @@ cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long*
     return cudaGetLastError();
 }
 
-cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const uint32_t* h1, const uint32_t* h2,
+cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const unsigned long long* h1, const unsigned long long* h2,
                                  uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,
                                  unsigned long long* id_mismatch, cudaStream_t stream) {
     combine_pairs_kernel<<<148 * 4, 256, 0, stream>>>(m1, m2, out, cap_words, h1, h2, idh_cap, lines1, lines2, count, id_mismatch);
     return cudaGetLastError();
 }
-cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const uint32_t* h, uint64_t idh_cap,
+cudaError_t launch_combine_interleaved(const uint32_t* m, uint32_t* out, uint64_t cap_out_words, const unsigned long long* h, uint64_t idh_cap,
                                        const unsigned long long* lines, unsigned long long* count, unsigned long long* id_mismatch, cudaStream_t stream) {
     combine_interleaved_kernel<<<148 * 4, 256, 0, stream>>>(m, out, cap_out_words, h, idh_cap, lines, count, id_mismatch);
     return cudaGetLastError();

@@ -135,6 +135,44 @@ class Matcher:
             out["mask"] = np.unpackbits(mask.view(np.uint8), bitorder="little")[:res.n_units].astype(bool)
         return out
 
+    def grep_fastq_write(self, r1, r2=None, mode=SINGLE, device=0, split=False, devices=None):
+        """Parse + match + ordered write-back of the selected records (src/main.rs:641-657, 682-727): the device returns
+        the selected records' spans, the host copies them.  devices=[...] deals the batches to several GPUs.
+        Returns dict(count, units, records, out[, out2], result)."""
+        a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)
+        b = None if r2 is None else (r2 if isinstance(r2, np.ndarray) else np.frombuffer(bytes(r2), dtype=np.uint8))
+        cap = a.size + (0 if b is None else b.size) + 64
+        out = np.zeros(cap, dtype=np.uint8)
+        out2 = np.zeros(cap, dtype=np.uint8) if split else None
+        n1, n2 = C.c_size_t(0), C.c_size_t(0)
+        res = _ffi.Result()
+        L = _ffi.lib()
+        if devices is None:
+            _check(L.fqg_grep_fastq_host_write(context(device), self._h, mode, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size,
+                                               _ptr(out), cap, C.byref(n1), _ptr(out2), cap if split else 0, C.byref(n2), C.byref(res)))
+        else:
+            ctxs = (C.c_void_p * len(devices))(*[context(d) for d in devices])
+            _check(L.fqg_grep_fastq_host_multi(ctxs, len(devices), self._h, mode, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size, None, 0,
+                                               _ptr(out), cap, C.byref(n1), _ptr(out2), cap if split else 0, C.byref(n2), C.byref(res)))
+        ret = {"count": res.n_selected, "units": res.n_units, "records": res.n_records, "result": res, "out": out[:n1.value].tobytes()}
+        if split:
+            ret["out2"] = out2[:n2.value].tobytes()
+        return ret
+
+    def grep_fastq_multi(self, r1, r2=None, mode=SINGLE, devices=(0,)):
+        """One input over several GPUs of the box (batches dealt round-robin, results gathered in batch order on the host):
+        same mask and count as grep_fastq."""
+        a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)
+        b = None if r2 is None else (r2 if isinstance(r2, np.ndarray) else np.frombuffer(bytes(r2), dtype=np.uint8))
+        words = a.size // 8 // 32 + 2
+        mask = np.zeros(words, dtype=np.uint32)
+        res = _ffi.Result()
+        ctxs = (C.c_void_p * len(devices))(*[context(d) for d in devices])
+        _check(_ffi.lib().fqg_grep_fastq_host_multi(ctxs, len(devices), self._h, mode, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size,
+                                                    _ptr(mask), words, None, 0, None, None, 0, None, C.byref(res)))
+        return {"count": res.n_selected, "units": res.n_units, "records": res.n_records, "result": res, "mask_words": mask,
+                "mask": np.unpackbits(mask.view(np.uint8), bitorder="little")[:res.n_units].astype(bool)}
+
     # -- per-record convenience with the reference's names (1-record batches; tests and KATs only)
     def bases_match(self, bases, device=0):
         """Matcher::bases_match: pattern found != invert_match (matcher.rs:204,250,507,570); no reverse complement."""
@@ -154,6 +192,83 @@ class Matcher:
         b = np.frombuffer(_b(seq), dtype=np.uint8)
         bits, _ = self.match_bases(b, np.array([0, b.size], dtype=np.uint64), device)
         return bool(bits[0])
+
+
+class FastqStream:
+    """The streaming batcher (fqg_stream_*): a ring of batches in flight on one GPU, results in submission order.
+    Replaces reader thread -> worker pool -> ordered main thread of the reference (src/main.rs:61-87,
+    src/lib/seq_io.rs:149-198, 253-282, 327-364)."""
+
+    def __init__(self, matcher, mode=SINGLE, device=0, n_slots=3, slot_bytes=64 << 20, want_spans=False):
+        self._m = matcher
+        self.mode = mode
+        opts = _ffi.StreamOpts(n_slots, int(want_spans), slot_bytes)
+        h = C.c_void_p()
+        _check(_ffi.lib().fqg_stream_open(context(device), matcher._h, mode, C.byref(opts), C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    def feed(self, r1, r2=None):
+        """Submit a batch of whole records living in the caller's memory (kept alive until its result is taken)."""
+        a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)
+        b = None if r2 is None else (r2 if isinstance(r2, np.ndarray) else np.frombuffer(bytes(r2), dtype=np.uint8))
+        _check(_ffi.lib().fqg_stream_feed(self._h, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size))
+        self._keep.append((a, b))
+
+    def fill(self, r1, r2=None):
+        """Copy a batch into the next free slot's pinned buffers and submit it (what a reader thread does)."""
+        p1, p2, cap = C.c_void_p(), C.c_void_p(), C.c_size_t(0)
+        _check(_ffi.lib().fqg_stream_acquire(self._h, C.byref(p1), C.byref(p2), C.byref(cap)))
+        for src, dst in ((r1, p1), (r2, p2)):
+            if src is not None:
+                b = bytes(src)
+                assert len(b) <= cap.value
+                C.memmove(dst, b, len(b))
+        _check(_ffi.lib().fqg_stream_submit(self._h, len(bytes(r1)), 0 if r2 is None else len(bytes(r2))))
+        self._keep.append(None)
+
+    def in_flight(self):
+        return _ffi.lib().fqg_stream_in_flight(self._h)
+
+    def next(self):
+        """Result of the oldest batch in flight: dict(seq, count, units, records, mask, spans, out)."""
+        b = _ffi.Batch()
+        rc = _ffi.lib().fqg_stream_next(self._h, C.byref(b))
+        if self._keep:
+            self._keep.pop(0)
+        _check(rc)
+        words = (b.n_units + 31) // 32
+        mw = np.ctypeslib.as_array(b.unit_mask, shape=(max(words, 1),))[:words].copy() if words else np.zeros(0, dtype=np.uint32)
+        out = {"seq": b.seq, "count": b.n_selected, "units": b.n_units, "records": b.n_records, "mask_words": mw,
+               "mask": np.unpackbits(mw.view(np.uint8), bitorder="little")[:b.n_units].astype(bool)}
+        if b.n_spans:
+            cap = b.n1 + b.n2 + 64
+            buf = np.zeros(cap, dtype=np.uint8)
+            n1, n2 = C.c_size_t(0), C.c_size_t(0)
+            _check(_ffi.lib().fqg_write_spans(b.spans, b.n_spans, b.r1, b.n1, b.r2, b.n2, _ptr(buf), cap, C.byref(n1), None, 0, C.byref(n2)))
+            out["out"] = buf[:n1.value].tobytes()
+            out["spans"] = [(b.spans[i].offset, b.spans[i].len, b.spans[i].flags) for i in range(min(b.n_spans, 1 << 16))]
+        else:
+            out["out"] = b""
+            out["spans"] = []
+        return out
+
+    def close(self):
+        if self._h:
+            _ffi.lib().fqg_stream_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def fastq_cut(r1, r2=None, mode=SINGLE, limit=0, final=False, exact=False):
+    """fqg_fastq_cut: largest prefixes of whole records (mates in lock step) of at most `limit` bytes."""
+    a = r1 if isinstance(r1, np.ndarray) else np.frombuffer(bytes(r1), dtype=np.uint8)
+    b = None if r2 is None else (r2 if isinstance(r2, np.ndarray) else np.frombuffer(bytes(r2), dtype=np.uint8))
+    c1, c2 = C.c_size_t(0), C.c_size_t(0)
+    _check(_ffi.lib().fqg_fastq_cut(mode, _ptr(a), a.size, _ptr(b), 0 if b is None else b.size, limit, int(final), int(exact), C.byref(c1), C.byref(c2)))
+    return (c1.value, c2.value) if mode == PAIRED else c1.value
 
 
 def is_gzip_path(path):

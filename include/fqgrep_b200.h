@@ -136,16 +136,99 @@ typedef struct fqg_result {
     uint64_t h2d_bytes, d2h_bytes;
 } fqg_result;
 
+/* One selected record in write-back order (K5): the device leaves these behind so that the ordered write-back
+ * (src/main.rs:641-657, write_paired_record :682-727) copies byte ranges instead of parsing the input a second time. */
+typedef struct fqg_span {
+    uint64_t offset;   /* byte offset of the record's '@' in its input (r1, or r2 when FQG_SPAN_R2 is set) */
+    uint32_t len;      /* bytes the record occupies in the input, final newline included when there is one */
+    uint32_t flags;
+} fqg_span;
+#define FQG_SPAN_R2 1u         /* the record belongs to r2 (FQG_PAIRED) */
+#define FQG_SPAN_NORMALISE 2u  /* not already in seq_io's write_to form (CR line ends, "+name" separator line, missing final
+                                  newline): emit "@head\nseq\n+\nqual\n" from its fields instead of copying the bytes */
+
 /* Replaces the whole per-input body of fqgrep_from_opts' main loop (src/main.rs:550-665) up to the selected flags:
  * parse records (seq_io rules), decide read_match per record, combine mates.  FASTQ bytes are in HOST memory
- * (pinned memory from fqg_alloc_pinned streams fastest).  unit_mask_out: optional uint32[ceil(n_units/32)]
- * sized by the caller from an upper bound (bytes/8 records is always enough); bit k = unit k selected. */
+ * (pinned memory from fqg_alloc_pinned streams fastest) and may be far larger than device memory: the input is cut into
+ * batches of whole records (R1/R2 in lock step) that flow through a ring of device slots, the copy of one batch
+ * overlapping the kernels of the one before (fqg_stream_* below is the same machinery, driven by the caller).
+ * unit_mask_out: optional uint32[ceil(n_units/32)] sized by the caller from an upper bound (bytes/8 records is always
+ * enough); bit k = unit k selected. */
 int fqg_grep_fastq_host(fqg_ctx* ctx, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2,
                         uint32_t* unit_mask_out, size_t unit_mask_words, fqg_result* res);
 
-/* Same with the FASTQ bytes already resident in device memory (d_r1/d_r2 readable 16 bytes past the end). */
+/* Same, and the selected records themselves (src/main.rs:641-657, 682-727): written in input order, in seq_io's write_to
+ * form, R1 then R2 for pairs, into out[0..out_cap) -- or R1 into out and R2 into out2 (the hidden `--output a b`) when
+ * out2 is not NULL.  *out_len / *out2_len receive the byte counts; FQG_E_TOO_LARGE if a buffer is too small
+ * (n1 + n2 bytes always suffice).  The device returns the selected records' spans, the host only copies them. */
+int fqg_grep_fastq_host_write(fqg_ctx* ctx, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2,
+                              uint8_t* out, size_t out_cap, size_t* out_len, uint8_t* out2, size_t out2_cap, size_t* out2_len, fqg_result* res);
+
+/* Several GPUs, one process: the batches of ONE input are dealt round-robin to the contexts (one per device, any count)
+ * and their results taken back in batch order, so masks, counts and output are identical to the single-GPU call.
+ * No device-to-device traffic: the only "collective" is this host-side gather. */
+int fqg_grep_fastq_host_multi(fqg_ctx* const* ctxs, uint32_t n_ctx, const fqg_matcher* m, int mode, const uint8_t* r1, size_t n1, const uint8_t* r2,
+                              size_t n2, uint32_t* unit_mask_out, size_t unit_mask_words, uint8_t* out, size_t out_cap, size_t* out_len, uint8_t* out2,
+                              size_t out2_cap, size_t* out2_len, fqg_result* res);
+
+/* Same with the FASTQ bytes already resident in device memory (d_r1/d_r2 16-byte aligned, readable 16 bytes past the end). */
 int fqg_grep_fastq_device(fqg_ctx* ctx, const fqg_matcher* m, int mode, const uint8_t* d_r1, size_t n1, const uint8_t* d_r2, size_t n2,
                           uint32_t* d_unit_mask_out, size_t unit_mask_words, fqg_result* res, void* stream);
+
+/* ---- matching: streaming batcher ---------------------------------------------------------------------------------
+ * Replaces the reader thread -> worker pool -> ordered main thread pipeline of the reference (spawn_reader
+ * src/main.rs:61-87; PairedFastqReader::fill_data lock-step batches src/lib/seq_io.rs:149-198; OrderedReader and the
+ * reorder buffer :253-282, 327-364) with a ring of `n_slots` batches in flight on one GPU.  Memory is bounded by the
+ * ring: per slot and input stream one pinned host buffer and one device buffer of `slot_bytes`, whatever the input size.
+ *
+ *   fqg_stream_acquire  the pinned buffers of the next free slot, for reader threads to fill (file read, gunzip)
+ *   fqg_stream_submit   the slot now holds n1 (and n2) bytes of WHOLE records -- R1/R2 with equal record counts,
+ *                       interleaved input with an even count (fqg_fastq_cut finds such prefixes); enqueues H2D copy,
+ *                       kernels and the copies back, returns at once
+ *   fqg_stream_feed     same for a batch that lives in the caller's own (ideally pinned) memory: no slot buffer is used
+ *   fqg_stream_next     blocks for the OLDEST batch in flight and hands out its result; batches complete in submission
+ *                       order, which is input order.  Pointers in fqg_batch stay valid until the slot is reused, i.e.
+ *                       until n_slots further batches have been submitted.
+ * A batch whose R1/R2 record counts differ, or that ends inside a record, fails in fqg_stream_next with the reference's
+ * error (FQG_E_PAIR_MISMATCH / FQG_E_FASTQ); the stream stays usable, so a caller that cut optimistically can re-cut
+ * exactly (fqg_fastq_cut with exact=1) and resubmit. */
+typedef struct fqg_stream fqg_stream;
+typedef struct fqg_stream_opts {
+    uint32_t n_slots;     /* batches in flight, 0 = 3 */
+    uint32_t want_spans;  /* also return the selected records' spans (for the write-back) */
+    size_t slot_bytes;    /* capacity of a slot per input stream, 0 = 64 MiB */
+} fqg_stream_opts;
+typedef struct fqg_batch {
+    uint64_t seq;                 /* batch number, 0-based, in submission order */
+    uint64_t n_records, n_units, n_selected;
+    const uint32_t* unit_mask;    /* bit k = unit k of this batch selected; ceil(n_units/32) words */
+    const fqg_span* spans;        /* want_spans: selected records in output order, offsets relative to r1 / r2 below */
+    uint64_t n_spans;
+    const uint8_t *r1, *r2;       /* the batch's bytes as submitted (slot buffers, or the caller's memory) */
+    size_t n1, n2;
+    double h2d_ms, kernel_ms;
+} fqg_batch;
+int fqg_stream_open(fqg_ctx* ctx, const fqg_matcher* m, int mode, const fqg_stream_opts* opts, fqg_stream** out);
+int fqg_stream_acquire(fqg_stream* s, uint8_t** r1_buf, uint8_t** r2_buf, size_t* capacity);
+int fqg_stream_submit(fqg_stream* s, size_t n1, size_t n2);
+int fqg_stream_feed(fqg_stream* s, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2);
+int fqg_stream_in_flight(const fqg_stream* s);
+int fqg_stream_next(fqg_stream* s, fqg_batch* out);
+void fqg_stream_close(fqg_stream* s);
+
+/* The batch cutter (PairedFastqReader::fill_data's "same number of records from R2", src/lib/seq_io.rs:155-163, and
+ * InterleavedFastqReader's even record count, :60-80, without a parsing reader thread): the largest prefixes
+ * r1[0..*cut1) / r2[0..*cut2) of at most `limit` bytes each that consist of whole records -- in lock step for
+ * FQG_PAIRED, an even number of records for FQG_INTERLEAVED.  final=1 says the inputs end here (the prefixes are then
+ * the whole buffers).  exact=0 aligns the mates by their read ids next to the cut (constant work; the device verifies
+ * every batch, so a wrong guess cannot go unnoticed); exact=1 counts records on all host threads.  *cut1 == 0 means
+ * `limit` does not hold one whole unit. */
+int fqg_fastq_cut(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, size_t limit, int final, int exact, size_t* cut1, size_t* cut2);
+
+/* Copies the selected records of one batch to `out` (and R2 records to `out2` when it is not NULL): plain byte copies for
+ * spans already in write_to form, re-formatting for FQG_SPAN_NORMALISE ones.  Uses all host threads for large batches. */
+int fqg_write_spans(const fqg_span* spans, uint64_t n_spans, const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, uint8_t* out, size_t out_cap,
+                    size_t* out_len, uint8_t* out2, size_t out2_cap, size_t* out2_len);
 
 /* K0, for callers that parse once and match many times (the batcher of north_star: "finds record and line boundaries ...
  * and compacts the sequence lines into an SoA bases buffer with per-read offsets").  Replaces the reader thread's record

@@ -27,6 +27,9 @@ def both(kind, pats, inv, rc, r1, r2=None, mode=F.SINGLE, check_output=True):
     assert (g["mask"] == (e["flags"] != 0)).all()
     if check_output:
         assert F.write_selected(g["mask_words"], r1, r2, mode=mode) == e["out"]
+        # the same bytes from the device's record spans (K5): no second parse on the host
+        w = m.grep_fastq_write(r1, r2, mode=mode)
+        assert w["count"] == e["count"] and w["out"] == e["out"]
     return g
 
 
