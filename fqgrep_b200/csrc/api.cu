@@ -421,7 +421,11 @@ int fqg_match_bases_host(fqg_ctx* c, const fqg_matcher* m, const uint8_t* bases,
         uint64_t r1 = r0;
         while (r1 < n_reads && offsets[r1 + 1] - offsets[r0] <= kChunkBytes) r1++;
         if (r1 == r0) return fail(FQG_E_TOO_LARGE, "a single read exceeds 1 GiB");
-        if (r1 < n_reads) { r1 = r0 + ((r1 - r0) & ~31ull); if (r1 == r0) r1 = r0 + 1; }
+        if (r1 < n_reads) {
+            // chunks must hold a multiple of 32 reads so that their mask words line up with the caller's
+            r1 = r0 + ((r1 - r0) & ~31ull);
+            if (r1 == r0) return fail(FQG_E_TOO_LARGE, "32 consecutive reads exceed 1 GiB; use fqg_match_bases_device with your own batching");
+        }
         const uint64_t n = r1 - r0, nbytes = offsets[r1] - offsets[r0], words = (n + 31) / 32;
         rel.resize(n + 1);
         for (uint64_t i = 0; i <= n; i++) {

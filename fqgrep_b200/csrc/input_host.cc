@@ -183,7 +183,8 @@ int read_input(const char* path, int decompress, int pinned, uint8_t** out, size
         z_stream zs;
         std::memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) { *err = "zlib init failed"; rc = FQG_E_INVALID_ARG; }
-        bool stream_open = true, any_member = false;
+        bool stream_open = true;
+        size_t member_in = 0;      // compressed bytes consumed by the member being inflated (inflateReset zeroes total_in)
         while (rc == FQG_OK) {
             size_t k = std::fread(&in[0], 1, kChunk, f);
             if (k == 0) break;
@@ -198,16 +199,17 @@ int read_input(const char* path, int decompress, int pinned, uint8_t** out, size
                 zs.next_out = buf.p + buf.n;
                 const size_t room = buf.cap - 64 - buf.n;
                 zs.avail_out = (uInt)(room > (1u << 30) ? (1u << 30) : room);
-                const uInt before = zs.avail_out;
+                const uInt before = zs.avail_out, before_in = zs.avail_in;
                 int zr = inflate(&zs, Z_NO_FLUSH);
                 buf.n += before - zs.avail_out;
-                if (zr == Z_STREAM_END) { stream_open = false; any_member = true; }
+                member_in += before_in - zs.avail_in;
+                if (zr == Z_STREAM_END) { stream_open = false; member_in = 0; }
                 else if (zr != Z_OK && zr != Z_BUF_ERROR) { *err = std::string("gzip decode error in ") + path; rc = FQG_E_FASTQ; }
             }
         }
-        if (rc == FQG_OK && stream_open && (any_member || zs.total_in)) {
-            if (zs.total_in && !any_member) { *err = std::string("truncated gzip stream in ") + path; rc = FQG_E_FASTQ; }
-        }
+        // The input ended inside a member -- the first or any later one (flate2's MultiGzDecoder raises UnexpectedEof there,
+        // which the reference turns into a panic, exit 101): partial data must never be returned as if it were the file.
+        if (rc == FQG_OK && stream_open && member_in) { *err = std::string("truncated gzip stream in ") + path; rc = FQG_E_FASTQ; }
         inflateEnd(&zs);
     }
     if (f != stdin) std::fclose(f);

@@ -436,7 +436,12 @@ private:
                 case 'U': break;
                 case 'u': f_.u = v; break;
                 case 'x': f_.x = v; break;
-                case 'R': f_.R = v; break;
+                case 'R':
+                    // CRLF mode changes `.`, and `^` / `$` under (?m) (\r\n as one line terminator); only the former was ever
+                    // modelled here, so switching it ON is refused instead of being half honoured
+                    if (v) throw ParseError{"the CRLF flag (?R) is not supported"};
+                    f_.R = false;
+                    break;
                 default: throw ParseError{"unrecognized flag"};
             }
             any = true;

@@ -650,6 +650,10 @@ typedef struct fqo_matcher {
     Regex *re;
     /* names: open addressing */
     uint64_t *slot_hash; int32_t *slot_idx; size_t nslots;
+    /* FIXED_SET whose patterns all have the same length: window hashing instead of one memmem per pattern (set_len > 0).
+       Same answers as the memmem loop -- tests/test_oracle_kat.py checks the two against each other on random sets; it
+       exists so that bench.py can check WHOLE 2 M-read masks for 10 000-pattern sets in seconds. */
+    size_t set_len; int use_naive_set;
 } fqo_matcher;
 
 static uint64_t fnv(const uint8_t *p, size_t n) { uint64_t h = 1469598103934665603ull; for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; } return h | 1; }
@@ -676,6 +680,20 @@ fqo_matcher *fqo_matcher_new(int kind, const uint8_t *blob, const uint64_t *offs
             }
         }
     }
+    if (kind == FQO_FIXED_SET && n >= 32) {
+        size_t L = m->plen[0]; int same = L > 0;
+        for (int i = 1; i < n && same; i++) same = m->plen[i] == L;
+        if (same) {
+            m->set_len = L;
+            m->nslots = 16; while (m->nslots < (size_t)n * 2 + 2) m->nslots *= 2;
+            m->slot_hash = calloc(m->nslots, sizeof(uint64_t)); m->slot_idx = calloc(m->nslots, sizeof(int32_t));
+            for (int i = 0; i < n; i++) {
+                uint64_t h = fnv(m->pat[i], L); size_t s = h & (m->nslots - 1);
+                while (m->slot_hash[s]) s = (s + 1) & (m->nslots - 1);
+                m->slot_hash[s] = h; m->slot_idx[s] = i;
+            }
+        }
+    }
     if (kind == FQO_NAMES) {
         m->nslots = 16; while (m->nslots < (size_t)n * 2 + 2) m->nslots *= 2;
         m->slot_hash = calloc(m->nslots, sizeof(uint64_t)); m->slot_idx = calloc(m->nslots, sizeof(int32_t));
@@ -687,6 +705,8 @@ fqo_matcher *fqo_matcher_new(int kind, const uint8_t *blob, const uint64_t *offs
     }
     return m;
 }
+
+void fqo_matcher_set_naive(fqo_matcher *m, int naive) { m->use_naive_set = naive; }
 
 /* mod.rs:129-155 */
 static uint8_t COMP[256]; static int comp_init = 0;
@@ -702,7 +722,20 @@ void fqo_revcomp(const uint8_t *s, size_t n, uint8_t *out) { init_comp(); for (s
 static int found_in(const fqo_matcher *m, const uint8_t *s, size_t n) {
     switch (m->kind) {
         case FQO_FIXED: return m->plen[0] == 0 || memmem(s, n, m->pat[0], m->plen[0]) != NULL;          /* bstr find */
-        case FQO_FIXED_SET: for (int i = 0; i < m->npat; i++) if (m->plen[i] == 0 || memmem(s, n, m->pat[i], m->plen[i])) return 1; return 0;
+        case FQO_FIXED_SET:
+            if (m->set_len && !m->use_naive_set) {      /* every window of the common length: is it one of the patterns? */
+                const size_t L = m->set_len;
+                for (size_t i = 0; i + L <= n; i++) {
+                    uint64_t h = fnv(s + i, L); size_t q = h & (m->nslots - 1);
+                    while (m->slot_hash[q]) {
+                        if (m->slot_hash[q] == h && !memcmp(m->pat[m->slot_idx[q]], s + i, L)) return 1;
+                        q = (q + 1) & (m->nslots - 1);
+                    }
+                }
+                return 0;
+            }
+            for (int i = 0; i < m->npat; i++) if (m->plen[i] == 0 || memmem(s, n, m->pat[i], m->plen[i])) return 1;      /* aho-corasick is_match */
+            return 0;
         case FQO_REGEX: return regex_is_match(&m->re[0], s, n);
         case FQO_REGEX_SET: for (int i = 0; i < m->npat; i++) if (regex_is_match(&m->re[i], s, n)) return 1; return 0;
         case FQO_BITMASK: case FQO_BITMASK_SET: {      /* matcher.rs:392-395, 442-450: encode(bases) then any needle */

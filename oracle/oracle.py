@@ -36,6 +36,7 @@ def lib():
         L.fqo_matcher_new.restype = C.c_void_p
         L.fqo_matcher_new.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.fqo_matcher_free.argtypes = [C.c_void_p]
+        L.fqo_matcher_set_naive.argtypes = [C.c_void_p, C.c_int]
         L.fqo_bases_match.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.fqo_read_match.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.fqo_revcomp.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
@@ -91,6 +92,10 @@ class Matcher:
         if getattr(self, "_h", None):
             lib().fqo_matcher_free(self._h)
             self._h = None
+
+    def set_naive(self, naive=True):
+        """FIXED_SET only: use the plain one-memmem-per-pattern loop even when all patterns have the same length."""
+        lib().fqo_matcher_set_naive(self._h, int(naive))
 
     def bases_match(self, seq):
         s = _b(seq)

@@ -92,6 +92,16 @@ def test_invalid_regex_message():
             O.Matcher(O.REGEX, [bad])
 
 
+def test_crlf_flag_is_refused_not_half_honoured():
+    """(?R) would make \\r\\n one line terminator for `.` AND for ^ / $ under (?m); only the former was ever modelled, so
+    turning it on is a construction error (exit 2) rather than a silently different language.  Turning it off is a no-op."""
+    for bad in ["(?R)A$", "(?Rm)A$", "(?m:(?R)^A)", "A(?R:.)C"]:
+        with pytest.raises(F.FqgrepError) as e:
+            F.Matcher(F.REGEX, [bad])
+        assert e.value.exit_code == 2 and e.value.message.startswith("Invalid regular expression")
+    assert F.Matcher(F.REGEX, ["(?-R)A.C"]).dfa_info().n_states > 0
+
+
 BASELINE_REGEXES = ["GACGAGATTA", "GACGTGATTA", "AC[GT]{3}TT(A|G)CA"]
 
 SYNTAX_CASES = [

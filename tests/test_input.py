@@ -102,3 +102,31 @@ def test_bgzf_members_are_inflated_in_parallel_and_checked(tmp_path):
     # empty BGZF file (only the EOF marker)
     open(str(tmp_path / "empty.fq.bgz"), "wb").write(bgzf(b""))
     assert F.read_input(str(tmp_path / "empty.fq.bgz")).size == 0
+
+
+def test_truncated_gzip_is_an_error_wherever_the_cut_falls(tmp_path):
+    """flate2's MultiGzDecoder raises UnexpectedEof when the input ends inside a member -- the first or a later one --
+    and the reference turns that into a panic (exit 101).  Partial data must never come back as if it were the file."""
+    a = fastq(["ACGT" * 30] * 300)
+    b = fastq(["TTGA" * 25] * 400)
+    za, zb = gzip.compress(a), gzip.compress(b)
+    cases = {
+        "first_member_cut.fq.gz": za[: len(za) // 2],
+        "second_member_cut.fq.gz": za + zb[: len(zb) // 2],
+        "second_member_header_only.fq.gz": za + zb[:5],
+        "third_member_cut.fq.gz": za + zb + za[: len(za) - 3],
+        "bgzf_cut.fq.gz": bgzf(a + b)[: len(bgzf(a + b)) // 2],            # no longer pure BGZF: the serial decoder sees the cut
+        "bgzf_last_block_cut.fq.bgz": bgzf(a + b, eof=False)[:-9],
+    }
+    for name, z in cases.items():
+        p = str(tmp_path / name)
+        open(p, "wb").write(z)
+        with pytest.raises(F.FqgrepError) as e:
+            F.read_input(p)
+        assert "truncated" in str(e.value) or "gzip" in str(e.value), name
+        assert e.value.exit_code == 101, name
+    # whole members are fine, with or without the empty BGZF EOF block
+    open(str(tmp_path / "ok.fq.gz"), "wb").write(za + zb)
+    assert F.read_input(str(tmp_path / "ok.fq.gz")).tobytes() == a + b
+    open(str(tmp_path / "ok2.fq.bgz"), "wb").write(bgzf(a + b, eof=False))
+    assert F.read_input(str(tmp_path / "ok2.fq.bgz")).tobytes() == a + b

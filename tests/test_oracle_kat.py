@@ -156,3 +156,62 @@ def test_fastq_rules():
     # id ends at the first space only; a tab is part of the id (seq_io 0.3.4 id_bytes)
     assert O.Matcher(O.NAMES, ["a\tb"]).grep(fastq(["ACGT"], heads=["a\tb c"]))["count"] == 1
     assert m.grep(b"")["count"] == 0
+
+
+def test_same_length_set_fast_path_equals_the_memmem_loop():
+    """The oracle answers large same-length literal sets by window hashing (so that bench.py can check whole 2 M-read masks
+    of the 10 000-pattern config); it must say exactly what its plain one-memmem-per-pattern loop says."""
+    import numpy as np
+    from tests import synth
+    rng = np.random.default_rng(3)
+    for L, npat in ((20, 500), (8, 64), (31, 33)):
+        pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, L)) for _ in range(npat)]
+        mat = synth.bases(20_000, seed=9)
+        synth.plant(mat, pats[:40], rate=0.05, seed=5)
+        mat[7, :3] = np.frombuffer(b"NNN", dtype=np.uint8)
+        bases, offs = synth.soa(mat)
+        for inv, rc in ((False, False), (True, True)):
+            fast = O.Matcher(O.FIXED_SET, pats, inv, rc)
+            slow = O.Matcher(O.FIXED_SET, pats, inv, rc)
+            slow.set_naive(True)
+            c1, f1 = fast.match_soa(bases, offs, threads=4)
+            c2, f2 = slow.match_soa(bases, offs, threads=4)
+            assert c1 == c2 and (f1 == f2).all() and 0 < c1 < 20_000
+
+
+def test_oracle_agrees_with_gnu_grep_on_the_baseline_patterns(tmp_path):
+    """GNU grep -c -F / -E on the extracted sequence lines is an independent implementation; the oracle (and so
+    everything checked against it) must count the same lines for the BASELINE.json patterns, -v included."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from tests import synth
+    if not shutil.which("grep"):
+        import pytest
+        pytest.skip("no grep")
+    n = 30_000
+    mat = synth.bases(n, seed=1)
+    rng = np.random.default_rng(7)
+    p1k = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(1000)]
+    synth.plant(mat, ["GACGAGATTA", "GACGTGATTA", "ACGTGTTACA"] + p1k[:30], rate=0.05, seed=99, revcomp_half=False)
+    seqfile = tmp_path / "seqs.txt"
+    seqfile.write_bytes(b"\n".join(bytes(r) for r in mat) + b"\n")
+    patfile = tmp_path / "pats.txt"
+    patfile.write_text("\n".join(p1k) + "\n")
+    bases, offs = synth.soa(mat)
+
+    def grep(args):
+        r = subprocess.run(["grep", "-c"] + args + [str(seqfile)], capture_output=True, text=True, env={"LC_ALL": "C"})
+        return int(r.stdout.strip() or 0)
+    cases = [
+        (O.FIXED, ["GACGAGATTA"], False, ["-F", "GACGAGATTA"]),                                   # configs[0] with -F
+        (O.REGEX, ["GACGAGATTA"], False, ["-E", "GACGAGATTA"]),                                   # configs[0]
+        (O.REGEX_SET, ["GACGAGATTA", "GACGTGATTA"], False, ["-E", "-e", "GACGAGATTA", "-e", "GACGTGATTA"]),   # configs[1] without RC
+        (O.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], True, ["-v", "-E", "AC[GT]{3}TT(A|G)CA"]),          # configs[3]
+        (O.REGEX_SET, ["AC[GT]{3}TT(A|G)CA"], False, ["-E", "AC[GT]{3}TT(A|G)CA"]),
+        (O.FIXED_SET, p1k, False, ["-F", "-f", str(patfile)]),                                    # configs[2] / [4a] shape
+    ]
+    for kind, pats, inv, args in cases:
+        cnt, _ = O.Matcher(kind, pats, inv, False).match_soa(bases, offs, threads=4)
+        assert cnt == grep(args), (kind, pats[:2], inv)
+        assert 0 < cnt < n
