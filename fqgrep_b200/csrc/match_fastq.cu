@@ -17,11 +17,13 @@
 //      REGISTERS (exact per-byte test in 3 integer ops per word, bits gathered by IDP.4A);
 //   3. popcounts -> warp scan -> the tile's newline count is published for the decoupled look-back;
 //   4. every newline's position is scattered into a small shared list at its rank (so line k of the tile is list[k]);
-//   5. the look-back (two levels, see lookback_resolve) yields the global line number of the tile's first byte, hence
-//      the record phase (line number mod 4) and the global record number of the tile's first record;
+//   5. the line phase (line number mod 4 of the tile's first byte) is guessed from the tile's own first records;
 //   6. lane k takes record k of the tile: five list entries give the record start and its four line ends, the
 //      record is validated by seq_io's rules and its sequence line is walked through the DFA straight out of shared
-//      memory (or its id probed in the name table); ballot -> atomicOr into the global record bitmask.
+//      memory (or its id probed in the name table), results held in registers;
+//   7. the look-back (two levels, see lookback_resolve) yields the global line number of the tile's first byte -- by now
+//      its inputs have long been published, so it does not wait; it confirms the guess (else step 6 runs again) and
+//      gives the global record number of the tile's first record; ballot -> atomicOr into the global record bitmask.
 // Records that do not end inside tile + overlap (reads longer than ~400 bases) are walked in global memory.
 // Round 1's kernel shared one 19 KB tile between the four warps of a "tile group" and needed four group barriers, a
 // shared bitmap, a binary search per record and a bit-scan per line end: 80 warp-instructions per record and 8.9 barrier
@@ -219,7 +221,7 @@ __device__ __forceinline__ unsigned long long lookback_resolve(const FastqArgs& 
     const unsigned long long kValue = (1ull << 62) - 1;
     auto poll = [](const unsigned long long* p) {
         unsigned long long st;
-        do { st = *reinterpret_cast<const volatile unsigned long long*>(p); } while ((st >> 62) == 0);
+        while (((st = *reinterpret_cast<const volatile unsigned long long*>(p)) >> 62) == 0) __nanosleep(40);      // spinning would steal issue slots
         return st;
     };
     // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix
@@ -282,11 +284,170 @@ __device__ __forceinline__ void stage_automaton(const DeviceDfa& dfa, uint8_t* s
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = __ldg(dfa.byte_class + i);
 }
 
+// ---- one record, one lane ---------------------------------------------------------------------------------------------------
+// Everything a lane finds out about its record.  Nothing is written to global memory while a record is evaluated: the
+// record phase may run under a GUESSED line phase (see the kernel), so outputs -- mask bit, id hash, spans, errors -- are
+// committed only once the look-back has confirmed the guess.
+struct RecOut {
+    bool sel = false;
+    uint32_t err = 0;                    // 0 or one of kErr*
+    unsigned long long err_pos = 0;
+    unsigned long long idh = 0, seq_pos = 0, rec_off = 0;
+    uint32_t seq_n = 0, rec_n = 0;
+};
+
+struct TileCtx {
+    uint32_t tile_sa, list_sa;           // shared addresses of the staged bytes and of the newline list
+    uint32_t total;                      // newlines in the staged bytes (list entries when total <= kListCap)
+    uint64_t T0, stream_len;
+    bool want_idh;
+};
+
+// Record whose line ends have ranks r0 .. r0+3 in the newline list (list entry of rank r = list[r - win_lo]) and that starts
+// at tile position s.
+template <int TIER>
+__device__ __forceinline__ RecOut eval_record(const FastqArgs& a, const RecordEval<TIER>& ev, const TileCtx& c, uint32_t s, uint32_t r0, uint32_t win_lo) {
+    RecOut o;
+    const uint64_t T0 = c.T0;
+    if (r0 + 3u < c.total) {
+        const uint32_t li = c.list_sa + 2u * (r0 - win_lo);
+        const uint32_t p0 = lds_u16_volatile(li), p1 = lds_u16_volatile(li + 2u), p2 = lds_u16_volatile(li + 4u), p3 = lds_u16_volatile(li + 6u);
+        const uint32_t tile_sa = c.tile_sa;
+        const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
+        const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
+        const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
+        if (lds_u8_volatile(tile_sa + s) != '@') { o.err = kErrInvalidStart; o.err_pos = T0 + s; }
+        else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') { o.err = kErrInvalidSep; o.err_pos = T0 + p1 + 1u; }
+        else if (seq_len != qual_len) { o.err = kErrUnequal; o.err_pos = T0 + s; }
+        o.seq_pos = T0 + p0 + 1u;
+        o.seq_n = seq_len;
+        if (a.rec_off) {
+            const uint32_t cr0 = (p0 > s + 1u && lds_u8_volatile(tile_sa + p0 - 1u) == '\r') ? 1u : 0u;
+            const bool virt = T0 + p3 == a.nbytes;
+            const bool norm = (cr0 | cr1 | cr3) != 0 || p2 - p1 != 2u || virt;
+            o.rec_off = (T0 + s) | (norm ? 1ull << 63 : 0ull);
+            o.rec_n = p3 - s + (virt ? 0u : 1u);
+        }
+        unsigned long long idh = 0;
+        o.sel = ev.eval_shared(tile_sa, s, p0, seq_len, &idh, c.want_idh);
+        o.idh = idh;
+    } else {
+        // record runs past tile+overlap (or the stream is truncated): walk it in global memory
+        const uint8_t* base = a.buf;
+        const uint64_t gs = T0 + s;
+        uint64_t q[4];
+        uint64_t p = gs;
+        int found = 0;
+        for (; found < 4 && p < c.stream_len; p++)
+            if (p == a.nbytes || base[p] == '\n') q[found++] = p;
+        if (found < 4) { o.err = kErrUnexpectedEnd; o.err_pos = gs; }
+        else {
+            const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
+            const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
+            const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
+            const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
+            if (base[gs] != '@') { o.err = kErrInvalidStart; o.err_pos = gs; }
+            else if (base[q[1] + 1] != '+') { o.err = kErrInvalidSep; o.err_pos = q[1] + 1; }
+            else if (seq_len != qual_len) { o.err = kErrUnequal; o.err_pos = gs; }
+            o.seq_pos = q[0] + 1;
+            o.seq_n = (uint32_t)seq_len;
+            if (a.rec_off) {
+                const bool virt = q[3] == a.nbytes;
+                const bool norm = (cr0 | cr1 | cr3) != 0 || q[2] - q[1] != 2u || virt;
+                o.rec_off = gs | (norm ? 1ull << 63 : 0ull);
+                o.rec_n = (uint32_t)(q[3] - gs + (virt ? 0u : 1u));
+            }
+            unsigned long long idh = 0;      // (its address goes to an out-of-line function: keep that away from `o`, which lives in registers)
+            o.sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, c.want_idh);
+            o.idh = idh;
+        }
+    }
+    return o;
+}
+
+// Writes what 32 lanes found out about records R_w .. R_w + 31 (lane i: record R_w + i, `valid` lanes only); returns the number selected.
+__device__ __forceinline__ uint32_t commit_records(const FastqArgs& a, const TileCtx& c, RecOut o, bool valid, unsigned long long R_w, uint32_t lane) {
+    if (valid) {
+        const unsigned long long R = R_w + lane;
+        if (o.err) report(a, o.err_pos, o.err);
+        if (R >= a.mask_bits || (c.want_idh && R >= a.id_hash_cap)) { report(a, c.T0, kErrMaskOverflow); o.sel = false; }
+        else if (c.want_idh) a.id_hash[R] = o.idh;
+        if (a.seq_start && R < a.span_cap) { a.seq_start[R] = o.seq_pos; a.seq_len[R] = o.seq_n; }
+        if (a.rec_off && R < a.rec_cap) { a.rec_off[R] = o.rec_off; a.rec_len[R] = o.rec_n; }
+    }
+    const uint32_t mk = __ballot_sync(kFullMask, valid && o.sel);
+    if (lane == 0 && mk) {
+        const uint32_t sh = (uint32_t)(R_w & 31ull);
+        atomicOr(a.mask + (R_w >> 5), mk << sh);
+        if (sh && (mk >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, mk >> (32u - sh));
+    }
+    return (uint32_t)__popc(mk);
+}
+
+// records that start in the tile, given the number of newlines before it
+struct TilePhase {
+    uint32_t extra, j0, n_list;
+    unsigned long long R_base;
+};
+__device__ __forceinline__ TilePhase tile_phase(const TileGeom& g, uint32_t j0, unsigned long long Lt, uint32_t agg, uint64_t stream_len) {
+    // record k begins right after the newline of local rank j0 + 4 (k - extra); j0 = first local rank that ends a record
+    TilePhase p;
+    const bool first_global = g.t == 0;
+    p.extra = first_global ? 1u : 0u;
+    p.j0 = j0;
+    p.R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
+    p.n_list = p.extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
+    if (g.T0 + g.region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) p.n_list--;   // the stream's final newline starts nothing
+    return p;
+}
+
+// Tiles with more newlines than the list holds (records of a few bytes: the reference's own test fixtures): several windows
+// over the ranks, each scattered and consumed in turn.  Rare, so kept out of line; no guessing here.
+struct LaneWords { uint32_t w[kWords]; };      // a lane's newline bitmap, by value: the hot path keeps it in registers
+template <int TIER>
+__device__ __noinline__ uint32_t dense_tile(const FastqArgs& a, const RecordEval<TIER>& ev, const TileCtx& c, const TileGeom& g, LaneWords m, uint32_t excl,
+                                            uint32_t agg, unsigned long long Lt, uint32_t lane) {
+    const TilePhase ph = tile_phase(g, 3u - (uint32_t)(Lt & 3ull), Lt, agg, c.stream_len);
+    const uint32_t lane_pos = lane * kLaneBytes;
+    uint32_t selected = 0;
+    for (uint32_t win_lo = 0;; win_lo += kWindowStep) {
+        uint32_t idx = excl - win_lo;       // may wrap below zero: compared unsigned against the capacity
+#pragma unroll
+        for (uint32_t j = 0; j < kWords; j++) {
+            uint32_t w = m.w[j];
+            const uint32_t pos0 = lane_pos + 32u * j;
+            while (w) {
+                const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+                if (idx < kListCap) sts_u16(c.list_sa + 2u * idx, pos0 + b);
+                idx++;
+                w &= w - 1u;
+            }
+        }
+        __syncwarp();
+        for (uint32_t k0 = 0; k0 < ph.n_list; k0 += 32u) {
+            const uint32_t k = k0 + lane;
+            // ranks: qa = the newline before the record (none for the stream's first record), r0 .. r0+3 = its four line ends
+            const uint32_t qa = k < ph.extra ? 0u : ph.j0 + 4u * (k - ph.extra);
+            const uint32_t r0 = k < ph.extra ? 0u : qa + 1u;
+            const bool valid = k < ph.n_list && qa >= win_lo && qa < win_lo + kWindowStep;
+            RecOut o;
+            if (valid) {
+                const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(c.list_sa + 2u * (qa - win_lo)) + 1u;
+                o = eval_record<TIER>(a, ev, c, s, r0, win_lo);
+            }
+            selected += commit_records(a, c, o, valid, ph.R_base + k0, lane);
+        }
+        __syncwarp();       // every lane is done with the list before the next window overwrites it
+        if (win_lo + kWindowStep >= agg) break;
+    }
+    return selected;
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
 template <int TIER>
 __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
     // ---- smem carve-up: [automaton][class LUT 256][per-warp regions]
     uint8_t* s_tab = smem;
@@ -300,34 +461,39 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
 
     const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
+    TileCtx c;
+    c.tile_sa = tile_sa;
+    c.list_sa = list_sa;
     // the stream always ends with a newline: a real one, or a virtual one at offset nbytes (missing final '\n')
-    const uint64_t stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
-    const bool want_idh = a.id_hash != nullptr;
+    c.stream_len = a.nbytes + (a.virtual_final_nl ? 1u : 0u);
+    c.want_idh = a.id_hash != nullptr;
+    const uint64_t stream_len = c.stream_len;
     const uint32_t c0a = a.nl_xor, c7f = a.nl_low7;     // see FastqArgs: not compile-time constants on purpose
     const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
-    for (;;) {
-        uint32_t claim = 0;
-        if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
-        claim = __shfl_sync(kFullMask, claim, 0);
-        if (claim >= a.tile_count) break;
+    // Tiles are claimed in order from an atomic counter, one claim AHEAD: while a tile is processed the warp already
+    // holds the id of its next one, so the claim's round trip is never waited for and the next tile's bytes can be
+    // pulled into L2 (126 MB) long before the bulk copy asks for them -- a warp has a single tile buffer, this is how
+    // HBM is kept busy.  (A tile claimed early publishes its newline count late; that is harmless because look-backs are
+    // resolved at the END of a tile's processing, see step 5.)
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
+    claim = __shfl_sync(kFullMask, claim, 0);
+    while (claim < a.tile_count) {
         const TileGeom g = tile_geom(a, a.tile_first + claim, stream_len);
-        if (g.real_avail) {
-            if (lane == 0) {
+        c.T0 = g.T0;
+        uint32_t next_claim = 0;
+        if (lane == 0) {
+            if (g.real_avail) {
                 const uint32_t bytes = (g.real_avail + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
-                // Tiles are handed out in order, so the tile one full wave ahead (one per resident warp) is the one some
-                // warp will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~22 MB) so that copy
-                // only pays L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
-                const uint32_t ahead = claim + gridDim.x * nwarps;
-                if (ahead < a.tile_count) {
-                    const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
-                    if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
-                }
             }
+            next_claim = atomicAdd(a.tile_counter, 1u);      // consumed after the record phase
+        }
+        if (g.real_avail) {
             mbar_wait(bar, phase);       // try_wait suspends the warp in hardware; no issue slots are burnt
             phase ^= 1u;
         }
@@ -370,119 +536,109 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         }
         const uint32_t total = __shfl_sync(kFullMask, incl, 31);
         const uint32_t agg = g.region == kTile ? __shfl_sync(kFullMask, incl, kTileLanes - 1u) : total;
+        c.total = total;
         lookback_publish(a, g.t, agg, lane);
+        // the next tile is known by now: warm L2 with it
+        next_claim = __shfl_sync(kFullMask, next_claim, 0);
+        if (lane == 0 && next_claim < a.tile_count) {
+            const TileGeom gn = tile_geom(a, a.tile_first + next_claim, stream_len);
+            if (gn.real_avail) bulk_prefetch_l2(a.buf + gn.T0, (gn.real_avail + 15u) & ~15u);
+        }
 
-        unsigned long long Lt = 0;
-        bool have_Lt = false;
-        for (uint32_t win_lo = 0;; win_lo += kWindowStep) {
-            // ---- 4. scatter: list[rank - win_lo] = position in the tile
+        if (total > kListCap) {
+            const unsigned long long Lt = lookback_resolve(a, g.t, agg, lane);
+            if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
+            LaneWords mw;
+#pragma unroll
+            for (uint32_t j = 0; j < kWords; j++) mw.w[j] = m[j];
+            local_count += dense_tile<TIER>(a, ev, c, g, mw, incl - cnt, agg, Lt, lane);
+        } else {
+            // ---- 4. scatter: list[rank] = position in the tile.  Two branch-free steps per word (a lane rarely has more
+            //         than two newlines in 32 bytes), then a loop for whatever is left in any lane.
             {
-                uint32_t idx = incl - cnt - win_lo;       // may wrap below zero: compared unsigned against the capacity
+                uint32_t addr = list_sa + 2u * (incl - cnt);
 #pragma unroll
                 for (uint32_t j = 0; j < kWords; j++) {
                     uint32_t w = m[j];
                     const uint32_t pos0 = lane_pos + 32u * j;
-                    while (w) {
+#pragma unroll
+                    for (int step = 0; step < 2; step++) {
                         const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
-                        if (idx < kListCap) sts_u16(list_sa + 2u * idx, pos0 + b);
-                        idx++;
+                        if (w) { sts_u16(addr, pos0 + b); addr += 2u; }
+                        w &= w - 1u;
+                    }
+                    while (__any_sync(kFullMask, w != 0)) {
+                        const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+                        if (w) { sts_u16(addr, pos0 + b); addr += 2u; }
                         w &= w - 1u;
                     }
                 }
             }
             __syncwarp();
-            // ---- 5. global line number of the tile's first byte (once per tile; the scatter above ran while the predecessors published)
+
+            // ---- 5. the line phase.  Which local newline ends a record depends on the number of newlines before the tile
+            //         (mod 4), i.e. on the look-back -- which has to wait for the slowest of the ~2000 tiles in flight before
+            //         this one.  Instead of waiting, the phase is GUESSED from the tile itself: lanes 0..7 test, for the four
+            //         candidates and the first two records each, "starts with '@', '+' two lines on, equal lengths".  One
+            //         surviving candidate = the guess; the records are evaluated under it into registers, the look-back is
+            //         resolved afterwards (by then its inputs are there) and only a confirmed guess is committed.  A wrong
+            //         or impossible guess costs a second pass, never a wrong answer.
+            unsigned long long Lt = 0;
+            bool have_Lt = g.t == 0;       // nothing precedes the first tile
+            uint32_t j0 = 3u;
             if (!have_Lt) {
-                Lt = lookback_resolve(a, g.t, agg, lane);
-                have_Lt = true;
-                if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
+                bool ok = false;
+                const uint32_t cand = lane & 3u, r = cand + 4u * (lane >> 2);      // boundary newline rank under this candidate
+                if (lane < 8u && r + 4u < total) {
+                    const uint32_t li = list_sa + 2u * r;
+                    const uint32_t q = lds_u16_volatile(li), p0 = lds_u16_volatile(li + 2u), p1 = lds_u16_volatile(li + 4u), p2 = lds_u16_volatile(li + 6u),
+                                   p3 = lds_u16_volatile(li + 8u);
+                    ok = lds_u8_volatile(tile_sa + q + 1u) == '@' && lds_u8_volatile(tile_sa + p1 + 1u) == '+' && p1 - p0 == p3 - p2;
+                }
+                const uint32_t votes = __ballot_sync(kFullMask, ok);
+                const uint32_t both = votes & (votes >> 4) & 0xFu;              // candidates whose first AND second record look right
+                if (both && (both & (both - 1u)) == 0) j0 = (uint32_t)__ffs((int)both) - 1u;
+                else {
+                    Lt = lookback_resolve(a, g.t, agg, lane);
+                    have_Lt = true;
+                    j0 = 3u - (uint32_t)(Lt & 3ull);
+                }
             }
             // ---- 6. one lane per record that starts in the tile
-            // record k begins right after the newline of local rank j0 + 4 (k - extra)
-            const bool first_global = g.t == 0;
-            const uint32_t extra = first_global ? 1u : 0u;
-            const uint32_t j0 = 3u - (uint32_t)(Lt & 3ull);          // first local newline rank that ends a record
-            const unsigned long long R_base = first_global ? 0ull : (Lt + j0 + 1ull) >> 2;
-            uint32_t n_list = extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
-            if (g.T0 + g.region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) n_list--;   // the stream's final newline starts nothing
-            const uint64_t T0 = g.T0;
-            for (uint32_t k0 = 0; k0 < n_list; k0 += 32u) {
-                const uint32_t k = k0 + lane;
-                // ranks: qa = the newline before the record (none for the stream's first record), r0.. r0+3 = its four line ends
-                const uint32_t qa = k < extra ? 0u : j0 + 4u * (k - extra);
-                const uint32_t r0 = k < extra ? 0u : qa + 1u;
-                const bool valid = k < n_list && qa >= win_lo && qa < win_lo + kWindowStep;
-                bool sel = false;
-                unsigned long long idh = 0, seq_pos = 0, rec_off = 0;
-                uint32_t seq_n = 0, rec_n = 0;
-                if (valid) {
-                    const uint32_t li = list_sa + 2u * (r0 - win_lo);
-                    const uint32_t s = k < extra ? 0u : lds_u16_volatile(list_sa + 2u * (qa - win_lo)) + 1u;
-                    if (r0 + 3u < total) {
-                        const uint32_t p0 = lds_u16_volatile(li), p1 = lds_u16_volatile(li + 2u), p2 = lds_u16_volatile(li + 4u), p3 = lds_u16_volatile(li + 6u);
-                        const uint32_t cr1 = (p1 > p0 + 1u && lds_u8_volatile(tile_sa + p1 - 1u) == '\r') ? 1u : 0u;
-                        const uint32_t cr3 = (p3 > p2 + 1u && lds_u8_volatile(tile_sa + p3 - 1u) == '\r') ? 1u : 0u;
-                        const uint32_t seq_len = p1 - p0 - 1u - cr1, qual_len = p3 - p2 - 1u - cr3;
-                        if (lds_u8_volatile(tile_sa + s) != '@') report(a, T0 + s, kErrInvalidStart);
-                        else if (lds_u8_volatile(tile_sa + p1 + 1u) != '+') report(a, T0 + p1 + 1u, kErrInvalidSep);
-                        else if (seq_len != qual_len) report(a, T0 + s, kErrUnequal);
-                        seq_pos = T0 + p0 + 1u;
-                        seq_n = seq_len;
-                        if (a.rec_off) {
-                            const uint32_t cr0 = (p0 > s + 1u && lds_u8_volatile(tile_sa + p0 - 1u) == '\r') ? 1u : 0u;
-                            const bool virt = T0 + p3 == a.nbytes;
-                            const bool norm = (cr0 | cr1 | cr3) != 0 || p2 - p1 != 2u || virt;
-                            rec_off = (T0 + s) | (norm ? 1ull << 63 : 0ull);
-                            rec_n = p3 - s + (virt ? 0u : 1u);
-                        }
-                        sel = ev.eval_shared(tile_sa, s, p0, seq_len, &idh, want_idh);
-                    } else {
-                        // record runs past tile+overlap (or the stream is truncated): walk it in global memory
-                        const uint8_t* base = a.buf;
-                        const uint64_t gs = T0 + s;
-                        uint64_t q[4];
-                        uint64_t p = gs;
-                        int found = 0;
-                        for (; found < 4 && p < stream_len; p++)
-                            if (p == a.nbytes || base[p] == '\n') q[found++] = p;
-                        if (found < 4) report(a, gs, kErrUnexpectedEnd);
-                        else {
-                            const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
-                            const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
-                            const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
-                            const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
-                            if (base[gs] != '@') report(a, gs, kErrInvalidStart);
-                            else if (base[q[1] + 1] != '+') report(a, q[1] + 1, kErrInvalidSep);
-                            else if (seq_len != qual_len) report(a, gs, kErrUnequal);
-                            seq_pos = q[0] + 1;
-                            seq_n = (uint32_t)seq_len;
-                            if (a.rec_off) {
-                                const bool virt = q[3] == a.nbytes;
-                                const bool norm = (cr0 | cr1 | cr3) != 0 || q[2] - q[1] != 2u || virt;
-                                rec_off = gs | (norm ? 1ull << 63 : 0ull);
-                                rec_n = (uint32_t)(q[3] - gs + (virt ? 0u : 1u));
-                            }
-                            sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, want_idh);
-                        }
+            for (;;) {
+                TilePhase ph = tile_phase(g, j0, Lt, agg, stream_len);
+                bool redo = false;
+                for (uint32_t k0 = 0; k0 < ph.n_list; k0 += 32u) {
+                    const uint32_t k = k0 + lane;
+                    const uint32_t qa = k < ph.extra ? 0u : ph.j0 + 4u * (k - ph.extra);
+                    const uint32_t r0 = k < ph.extra ? 0u : qa + 1u;
+                    const bool valid = k < ph.n_list;
+                    RecOut o;
+                    if (valid) {
+                        const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
+                        o = eval_record<TIER>(a, ev, c, s, r0, 0u);
                     }
-                    const unsigned long long R = R_base + k;
-                    if (R >= a.mask_bits || (want_idh && R >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); sel = false; }
-                    else if (want_idh) a.id_hash[R] = idh;
-                    if (a.seq_start && R < a.span_cap) { a.seq_start[R] = seq_pos; a.seq_len[R] = seq_n; }
-                    if (a.rec_off && R < a.rec_cap) { a.rec_off[R] = rec_off; a.rec_len[R] = rec_n; }
+                    if (!have_Lt) {
+                        Lt = lookback_resolve(a, g.t, agg, lane);
+                        have_Lt = true;
+                        const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
+                        if (exact != j0) { j0 = exact; redo = true; break; }
+                        ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
+                    }
+                    local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
                 }
-                const unsigned long long R_w = R_base + k0;      // record number of lane 0
-                const uint32_t mk = __ballot_sync(kFullMask, sel);
-                if (lane == 0 && mk) {
-                    const uint32_t sh = (uint32_t)(R_w & 31ull);
-                    atomicOr(a.mask + (R_w >> 5), mk << sh);
-                    if (sh && (mk >> (32u - sh))) atomicOr(a.mask + (R_w >> 5) + 1, mk >> (32u - sh));
-                    local_count += __popc(mk);
+                if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed
+                    Lt = lookback_resolve(a, g.t, agg, lane);
+                    have_Lt = true;
+                    const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
+                    if (exact != j0) { j0 = exact; redo = true; }
                 }
+                if (!redo) break;
             }
-            __syncwarp();       // every lane is done with the list (next window) and the tile (next bulk copy)
-            if (win_lo + kWindowStep >= agg) break;
+            if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
         }
+        __syncwarp();       // every lane is done with the list and the tile before the next bulk copy overwrites them
+        claim = next_claim;
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
