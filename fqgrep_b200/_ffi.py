@@ -13,6 +13,7 @@ SYMBOLS = [
     "fqg_grep_fastq_host", "fqg_grep_fastq_device", "fqg_write_selected", "fqg_kernel_launches", "fqg_synth_reads_device", "fqg_fastq_split", "fqg_iupac_expand", "fqg_read_input", "fqg_free_input", "fqg_index_fastq_device", "fqg_compact_bases_device", "fqg_is_gzip_path", "fqg_is_fastq_path",
     "fqg_grep_fastq_host_write", "fqg_grep_fastq_host_multi", "fqg_stream_open", "fqg_stream_acquire", "fqg_stream_submit", "fqg_stream_feed",
     "fqg_stream_in_flight", "fqg_stream_next", "fqg_stream_close", "fqg_fastq_cut", "fqg_write_spans",
+    "fqg_reader_open", "fqg_reader_read", "fqg_reader_close",
 ]
 
 
@@ -90,6 +91,10 @@ def lib():
     L.fqg_stream_next.argtypes = [vp, C.POINTER(Batch)]
     L.fqg_stream_close.argtypes = [vp]
     L.fqg_stream_close.restype = None
+    L.fqg_reader_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.fqg_reader_read.argtypes = [vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
+    L.fqg_reader_close.argtypes = [vp]
+    L.fqg_reader_close.restype = None
     L.fqg_fastq_cut.argtypes = [C.c_int, vp, sz, vp, sz, sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
     L.fqg_write_spans.argtypes = [C.POINTER(Span), u64, vp, sz, vp, sz, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]
     _lib = L

@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfqgrep_b200.so")
 CLI = os.path.join(HERE, "fqgrep-b200")      # the reference's command line over the device path (csrc/cli.cc)
 SOURCES = ["api.cu", "fastq_pipeline.cu", "stream.cu", "match_soa.cu", "match_fastq.cu", "synth.cu", "regex_compile.cc", "ac_build.cc", "gram_filter.cc", "names.cc",
-           "fastq_host.cc", "input_host.cc"]
+           "fastq_host.cc", "input_host.cc", "reader_host.cc"]
 HOST_SOURCES = ["fastq_cut.cc"]      # plain g++: per-function target attributes (AVX2 newline counting with a run-time check)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -532,6 +532,26 @@ int fqg_read_input(const char* path, int decompress, int pinned, uint8_t** out, 
     return FQG_OK;
 }
 void fqg_free_input(uint8_t* p, int pinned) { free_input(p, pinned); }
+
+int fqg_reader_open(const char* path, int decompress, fqg_reader** out) {
+    if (!path || !out) return fail(FQG_E_INVALID_ARG, "NULL argument");
+    std::string err;
+    InputReader* r = nullptr;
+    const int rc = reader_open(path, decompress, &r, &err);
+    if (rc) return fail(rc, err);
+    *out = reinterpret_cast<fqg_reader*>(r);
+    return FQG_OK;
+}
+int fqg_reader_read(fqg_reader* r, uint8_t* dst, size_t cap, size_t* n_read, int* eof) {
+    if (!r || !n_read || !eof || (cap && !dst)) return fail(FQG_E_INVALID_ARG, "NULL argument");
+    std::string err;
+    bool e = false;
+    const int rc = reader_read(reinterpret_cast<InputReader*>(r), dst, cap, n_read, &e, &err);
+    *eof = e ? 1 : 0;
+    if (rc) return fail(rc, err);
+    return FQG_OK;
+}
+void fqg_reader_close(fqg_reader* r) { reader_close(reinterpret_cast<InputReader*>(r)); }
 int fqg_is_gzip_path(const char* path) { return path && is_gzip_path(path) ? 1 : 0; }
 int fqg_is_fastq_path(const char* path) { return path && is_fastq_path(path) ? 1 : 0; }
 

@@ -3,7 +3,7 @@
 // and the 0 / 1 / 2 / 101 exit mapping are fqgrep_from_opts / fqgrep in include/fqgrep_b200.hpp.
 //
 // Accepted for compatibility and without effect on the device path: -t/--threads (the reference's worker-pool size),
-// --no-order (output is always in input order).  --color other than "never" is rejected: the device returns selection
+// --no-order (output is always in input order).  Added: --device, --gpus, --slot-mb (the streaming ring).  --color other than "never" is rejected: the device returns selection
 // bits, not match ranges (src/lib/matcher.rs:43-125 is host-side colouring, out of scope).
 #include <cstdlib>
 #include <cstring>
@@ -44,7 +44,9 @@ void help() {
         "      --protein                  The input files contain protein sequences\n"
         "      --iupac <IUPAC>            never | expand | regex | bit-mask [default: never]\n"
         "      --output <FILE>...         Write selected records to file(s); two files with --paired split R1 / R2\n"
-        "      --device <N>               CUDA device index [default: 0]\n"
+        "      --device <N>               first CUDA device index [default: 0]\n"
+        "      --gpus <N>                 deal the batches of every input to N devices, output still in input order [default: 1]\n"
+        "      --slot-mb <MB>             size of one slot of the batch ring per input stream; bounds host and device memory [default: 64]\n"
         "  -h, --help                     Print help\n"
         "  -V, --version                  Print version");
 }
@@ -106,6 +108,8 @@ int main(int argc, char** argv) {
                 else while (i + 1 < argc && (argv[i + 1][0] != '-' || argv[i + 1][1] == '\0')) o.output.push_back(argv[++i]);
             }
             else if (is_long(a, "--device")) o.device = std::atoi(value(i, a, 8, true).c_str());
+            else if (is_long(a, "--gpus")) o.gpus = std::atoi(value(i, a, 6, true).c_str());
+            else if (is_long(a, "--slot-mb")) o.slot_mb = (size_t)std::atoll(value(i, a, 9, true).c_str());
             else if (is_long(a, "--help")) { help(); return 0; }
             else if (is_long(a, "--version")) { std::printf("fqgrep-b200 %s\n", fqg_version()); return 0; }
             else usage_error(std::string("unexpected argument '") + a + "' found");

@@ -22,6 +22,12 @@ bool is_fastq_path(const char* path);
 int read_input(const char* path, int decompress, int pinned, uint8_t** out, size_t* n_out, std::string* err);
 void free_input(uint8_t* p, int pinned);
 
+// incremental input (reader_host.cc); see fqg_reader_* in include/fqgrep_b200.h
+struct InputReader;
+int reader_open(const char* path, int decompress, InputReader** out, std::string* err);
+int reader_read(InputReader* r, uint8_t* dst, size_t cap, size_t* n, bool* eof, std::string* err);
+void reader_close(InputReader* r);
+
 size_t find_record_start(const uint8_t* buf, size_t n, size_t pos);
 
 // batch cutter of the streaming path (fastq_cut.cc); see fqg_fastq_cut in include/fqgrep_b200.h

@@ -584,9 +584,12 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             //         resolved afterwards (by then its inputs are there) and only a confirmed guess is committed.  A wrong
             //         or impossible guess costs a second pass, never a wrong answer.
             unsigned long long Lt = 0;
-            bool have_Lt = g.t == 0;       // nothing precedes the first tile
+            bool have_Lt = false;
             uint32_t j0 = 3u;
-            if (!have_Lt) {
+            if (g.t == 0) {                // nothing precedes the first tile: no wait, but its prefix must be published for the others
+                Lt = lookback_resolve(a, g.t, agg, lane);
+                have_Lt = true;
+            } else {
                 bool ok = false;
                 const uint32_t cand = lane & 3u, r = cand + 4u * (lane >> 2);      // boundary newline rank under this candidate
                 if (lane < 8u && r + 4u < total) {

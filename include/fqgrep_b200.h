@@ -257,6 +257,14 @@ int fqg_write_selected(int mode, const uint8_t* r1, size_t n1, const uint8_t* r2
  * (-Z) is set and the extension is not .fq/.fastq (src/main.rs:77, src/lib/mod.rs:157-183).  Free with fqg_free_input. */
 int fqg_read_input(const char* path, int decompress, int pinned, uint8_t** out, size_t* n_out);
 void fqg_free_input(uint8_t* p, int pinned);
+/* The same plumbing for inputs that must not be held in memory whole (the reader threads of the streaming path): each
+ * call delivers up to `cap` further bytes of the -- gunzipped when the rules above say so -- input into dst, e.g. straight
+ * into a slot buffer from fqg_stream_acquire.  *eof is set once the input is exhausted.  BGZF members are inflated on all
+ * host threads; an input that ends inside a gzip member is an error (flate2's UnexpectedEof -> the reference's exit 101). */
+typedef struct fqg_reader fqg_reader;
+int fqg_reader_open(const char* path, int decompress, fqg_reader** out);
+int fqg_reader_read(fqg_reader* r, uint8_t* dst, size_t cap, size_t* n_read, int* eof);
+void fqg_reader_close(fqg_reader* r);
 int fqg_is_gzip_path(const char* path);    /* src/lib/mod.rs:170-175 */
 int fqg_is_fastq_path(const char* path);   /* src/lib/mod.rs:177-183 */
 

@@ -10,6 +10,14 @@
 //   read_patterns / read_query_names    src/main.rs:246-271
 //   Opts, fqgrep_from_opts, fqgrep      src/main.rs:142-244, 375-675, 295-311
 //
+//   spawn_reader + the batch readers    src/main.rs:61-87, src/lib/seq_io.rs:34-81, 121-199 -> InputStream / BatchFeeder
+//   ordered_parallel_* + func closures  src/lib/seq_io.rs:287-368, src/main.rs:558-575, 600-614, 641-657 -> run_input
+//
+// Inputs are STREAMED: reader threads fill the pinned slot buffers of a ring of batches in flight on the GPU(s)
+// (fqg_stream_*), batches are cut at record ends with mates in lock step (fqg_fastq_cut), results come back in
+// input order and the selected records are copied out from the device's record spans.  Host and device memory are
+// bounded by the ring whatever the input size.
+//
 // Header-only; every matching call goes to the GPU through the C ABI (no host matching path).  Errors are exceptions
 // carrying the C status and the reference's user-visible message; FqgrepError::exit_code() is what the reference
 // binary would exit with.
@@ -18,6 +26,8 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
+#include <thread>
 #include <memory>
 #include <set>
 #include <sstream>
@@ -173,7 +183,9 @@ struct Opts {
     bool progress = false;
     IupacOption iupac = IupacOption::Never;
     std::vector<std::string> output;        // hidden --output [a [b]]
-    int device = 0;
+    int device = 0;                         // first CUDA device
+    int gpus = 1;                           // devices device .. device+gpus-1 share the batches of every input
+    size_t slot_mb = 64;                    // ring slot size per input stream (memory bound = 3 slots x gpus x streams)
 };
 
 inline std::string slurp(const std::string& path) {
@@ -225,6 +237,134 @@ struct Sink {      // a selected-records destination: file or the caller's strea
         if (n && std::fwrite(v.data(), 1, n, f) != n) throw FqgrepError(FQG_E_PATTERN, "write failed");
     }
 };
+
+// proglog's "Searched N reads" line every 50 M reads (src/main.rs:468-480, 636-638, 737-740); counts arrive per batch here
+struct Progress {
+    bool on;
+    uint64_t seen, reported;
+    void record(uint64_t n) {
+        if (!on) return;
+        seen += n;
+        while (seen - reported >= 50000000ull) {
+            reported += 50000000ull;
+            std::string digits = std::to_string(reported), out;
+            for (size_t i = 0; i < digits.size(); i++) { if (i && (digits.size() - i) % 3 == 0) out.push_back(','); out.push_back(digits[i]); }
+            std::fprintf(stderr, "[fqgrep-progress] Searched %s reads\n", out.c_str());
+        }
+    }
+    void finish() {
+        if (!on) return;
+        std::fprintf(stderr, "[fqgrep-progress] Searched %llu reads in total\n", (unsigned long long)seen);
+    }
+};
+
+// One input file as a stream of bytes (spawn_reader, src/main.rs:61-87), delivered into caller-provided buffers.
+class InputStream {
+  public:
+    InputStream(const std::string& path, bool decompress) { check(fqg_reader_open(path.c_str(), decompress ? 1 : 0, &r_)); }
+    ~InputStream() { if (r_) fqg_reader_close(r_); }
+    InputStream(const InputStream&) = delete;
+    InputStream& operator=(const InputStream&) = delete;
+    bool eof() const { return eof_; }
+    // appends to buf[have .. cap); returns the new fill level.  Errors are kept for the caller's thread (rc / message).
+    size_t fill(uint8_t* buf, size_t have, size_t cap) {
+        while (have < cap && !eof_) {
+            size_t n = 0;
+            int e = 0;
+            rc = fqg_reader_read(r_, buf + have, cap - have, &n, &e);
+            if (rc != FQG_OK) { message = fqg_last_error(); eof_ = true; break; }
+            have += n;
+            if (e) eof_ = true;
+        }
+        return have;
+    }
+    int rc = FQG_OK;
+    std::string message;
+
+  private:
+    fqg_reader* r_ = nullptr;
+    bool eof_ = false;
+};
+
+// The per-input body of fqgrep_from_opts' loops (src/main.rs:550-665) on the streaming path: reader threads fill the next
+// free slot of the ring (R1 and R2 side by side), the batch is cut at record ends with the mates in lock step (counted,
+// like PairedFastqReader::fill_data reads "the same number of records", src/lib/seq_io.rs:155-163), submitted, and the
+// oldest batch in flight is retired: count, progress, ordered write-back from the device's record spans.
+inline void run_input(const Matcher& matcher, int mode, const std::string& f1, const std::string* f2, const Opts& opts, FILE* w1, FILE* w2,
+                      uint64_t* num_matches, uint64_t* num_records, Progress* progress) {
+    InputStream in1(f1, opts.decompress);
+    std::unique_ptr<InputStream> in2;
+    if (f2) in2.reset(new InputStream(*f2, opts.decompress));
+    fqg_stream_opts so{};
+    so.n_slots = 3;
+    so.want_spans = opts.count ? 0u : 1u;
+    so.slot_bytes = opts.slot_mb << 20;
+    const size_t cap = so.slot_bytes;
+    std::vector<fqg_stream*> streams((size_t)opts.gpus, nullptr);
+    struct Closer { std::vector<fqg_stream*>& v; ~Closer() { for (auto* s : v) fqg_stream_close(s); } } closer{streams};
+    for (int g = 0; g < opts.gpus; g++) check(fqg_stream_open(context(opts.device + g), matcher.handle(), mode, &so, &streams[(size_t)g]));
+    std::vector<uint8_t> carry1, carry2, outbuf, outbuf2;
+    uint64_t fed = 0, taken = 0;
+    auto retire = [&]() {
+        fqg_batch b;
+        check(fqg_stream_next(streams[taken % streams.size()], &b));
+        taken++;
+        *num_matches += b.n_selected;
+        *num_records += b.n_records;
+        progress->record(b.n_records);
+        if (opts.count || b.n_spans == 0) return;
+        outbuf.resize(b.n1 + b.n2 + 64);
+        size_t l1 = 0, l2 = 0;
+        if (w2) {
+            outbuf2.resize(b.n2 + 64);
+            check(fqg_write_spans(b.spans, b.n_spans, b.r1, b.n1, b.r2, b.n2, outbuf.data(), outbuf.size(), &l1, outbuf2.data(), outbuf2.size(), &l2));
+        } else {
+            check(fqg_write_spans(b.spans, b.n_spans, b.r1, b.n1, b.r2, b.n2, outbuf.data(), outbuf.size(), &l1, nullptr, 0, &l2));
+        }
+        if (l1 && std::fwrite(outbuf.data(), 1, l1, w1) != l1) throw FqgrepError(FQG_E_PATTERN, "write failed");
+        if (l2 && std::fwrite(outbuf2.data(), 1, l2, w2) != l2) throw FqgrepError(FQG_E_PATTERN, "write failed");
+    };
+    const uint64_t max_in_flight = (uint64_t)so.n_slots * streams.size();
+    for (;;) {
+        if (fed - taken >= max_in_flight) retire();
+        fqg_stream* s = streams[fed % streams.size()];
+        uint8_t *b1 = nullptr, *b2 = nullptr;
+        size_t slot_cap = 0;
+        check(fqg_stream_acquire(s, &b1, &b2, &slot_cap));
+        if (carry1.size() > cap || carry2.size() > cap) throw FqgrepError(FQG_E_TOO_LARGE, "a record (pair) is larger than the ring slot; raise --slot-mb");
+        if (!carry1.empty()) std::memcpy(b1, carry1.data(), carry1.size());
+        if (in2 && !carry2.empty()) std::memcpy(b2, carry2.data(), carry2.size());
+        size_t n1 = carry1.size(), n2 = carry2.size();
+        // the reader threads of the reference (one per input): file read / gunzip of R1 and R2 side by side
+        if (in2) {
+            std::thread t2([&]() { n2 = in2->fill(b2, n2, cap); });
+            n1 = in1.fill(b1, n1, cap);
+            t2.join();
+            if (in2->rc != FQG_OK) throw FqgrepError(in2->rc, in2->message);
+        } else {
+            n1 = in1.fill(b1, n1, cap);
+        }
+        if (in1.rc != FQG_OK) throw FqgrepError(in1.rc, in1.message);
+        const bool final = in1.eof() && (!in2 || in2->eof());
+        size_t c1 = 0, c2 = 0;
+        check(fqg_fastq_cut(mode, b1, n1, b2, n2, 0, final ? 1 : 0, mode == FQG_SINGLE ? 0 : 1, &c1, &c2));
+        if (c1 == 0 && c2 == 0) {
+            if (!final && (n1 >= cap || (in2 && n2 >= cap))) throw FqgrepError(FQG_E_TOO_LARGE, "a record (pair) is larger than the ring slot; raise --slot-mb");
+            // nothing cut although the input has ended: whatever is left goes to the device, which names the error (or finds nothing)
+            c1 = n1;
+            c2 = n2;
+        }
+        if (c1 || c2) {
+            check(fqg_stream_submit(s, c1, c2));
+            fed++;
+        }
+        carry1.assign(b1 + c1, b1 + n1);
+        if (in2) carry2.assign(b2 + c2, b2 + n2);
+        if (final && carry1.empty() && carry2.empty()) break;
+        if (final && c1 == 0 && c2 == 0) break;
+    }
+    while (taken < fed) retire();
+}
 }  // namespace detail
 
 // Returns the number of selected records (single-end) or pairs; throws FqgrepError.  Selected records go to `out`
@@ -233,7 +373,11 @@ inline uint64_t fqgrep_from_opts(const Opts& opts, FILE* out = stdout) {
     std::vector<std::string> regexp = opts.regexp;
     std::set<std::string> query_names;
     const bool by_name = opts.has_read_names_file;
-    if (by_name) query_names = read_query_names(opts.read_names_file);
+    if (by_name) {
+        query_names = read_query_names(opts.read_names_file);
+        // src/main.rs:381-385
+        if (opts.reverse_complement) std::fprintf(stderr, "Warning: --reverse-complement is ignored when using query name matching (-N)\n");
+    }
     else if (opts.has_file) for (auto& p : read_patterns(opts.file)) regexp.push_back(p);
 
     bool has_pattern = false;
@@ -295,42 +439,18 @@ inline uint64_t fqgrep_from_opts(const Opts& opts, FILE* out = stdout) {
 
     uint64_t num_matches = 0, num_records = 0;
     if (files.empty()) files.push_back("-");
-    std::vector<uint8_t> buf1, buf2;
-    auto run = [&](const Input& r1, const Input* r2, int mode) {
-        GrepResult g = matcher->grep_fastq(r1.data(), r1.size(), r2 ? r2->data() : nullptr, r2 ? r2->size() : 0, mode, opts.device);
-        num_matches += g.res.n_selected;
-        num_records += g.res.n_records;
-        if (opts.progress) std::fprintf(stderr, "[fqgrep-b200] records %llu, selected %llu\n", (unsigned long long)num_records, (unsigned long long)num_matches);
-        if (opts.count || !g.res.n_selected) return;
-        const size_t cap = r1.size() + (r2 ? r2->size() : 0) + 64;
-        buf1.resize(cap);
-        size_t n1 = 0, n2 = 0;
-        if (w2.f) {
-            buf2.resize(cap);
-            check(fqg_write_selected(mode, r1.data(), r1.size(), r2 ? r2->data() : nullptr, r2 ? r2->size() : 0, g.unit_mask.data(), buf1.data(), &n1, buf2.data(), &n2));
-            w1.write(buf1, n1);
-            w2.write(buf2, n2);
-        } else {
-            check(fqg_write_selected(mode, r1.data(), r1.size(), r2 ? r2->data() : nullptr, r2 ? r2->size() : 0, g.unit_mask.data(), buf1.data(), &n1, nullptr, &n2));
-            w1.write(buf1, n1);
-        }
+    if (opts.gpus < 1 || opts.gpus > 64) throw FqgrepError(FQG_E_INVALID_ARG, "--gpus must be between 1 and 64");
+    detail::Progress progress{opts.progress, 0, 0};
+    auto run = [&](const std::string& f1, const std::string* f2, int mode) {
+        detail::run_input(*matcher, mode, f1, f2, opts, w1.f, w2.f, &num_matches, &num_records, &progress);
     };
     if (opts.paired) {
-        if (files.size() == 1) {
-            Input in(files[0], opts.decompress);
-            run(in, nullptr, FQG_INTERLEAVED);
-        } else {
-            for (size_t i = 0; i + 1 < files.size(); i += 2) {
-                Input a(files[i], opts.decompress), b(files[i + 1], opts.decompress);
-                run(a, &b, FQG_PAIRED);
-            }
-        }
+        if (files.size() == 1) run(files[0], nullptr, FQG_INTERLEAVED);
+        else for (size_t i = 0; i + 1 < files.size(); i += 2) run(files[i], &files[i + 1], FQG_PAIRED);
     } else {
-        for (auto& f : files) {
-            Input in(f, opts.decompress);
-            run(in, nullptr, FQG_SINGLE);
-        }
+        for (auto& f : files) run(f, nullptr, FQG_SINGLE);
     }
+    progress.finish();
     if (opts.count) std::fprintf(out, "%llu\n", (unsigned long long)num_matches);
     std::fflush(out);
     return num_matches;

@@ -114,6 +114,9 @@ extern "C" {
                               out: *mut u8, out_len: *mut usize, out2: *mut u8, out2_len: *mut usize) -> c_int;
     pub fn fqg_read_input(path: *const c_char, decompress: c_int, pinned: c_int, out: *mut *mut u8, n_out: *mut usize) -> c_int;
     pub fn fqg_free_input(p: *mut u8, pinned: c_int);
+    pub fn fqg_reader_open(path: *const c_char, decompress: c_int, out: *mut *mut c_void) -> c_int;
+    pub fn fqg_reader_read(r: *mut c_void, dst: *mut u8, cap: usize, n_read: *mut usize, eof: *mut c_int) -> c_int;
+    pub fn fqg_reader_close(r: *mut c_void);
     pub fn fqg_is_gzip_path(path: *const c_char) -> c_int;
     pub fn fqg_is_fastq_path(path: *const c_char) -> c_int;
     pub fn fqg_fastq_split(buf: *const u8, n: usize, parts: u32, cuts: *mut u64) -> c_int;
