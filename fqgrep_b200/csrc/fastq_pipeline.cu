@@ -10,6 +10,8 @@
 //   host source  : chunked cudaMemcpyAsync on the copy stream into the lane's device buffer; after each chunk the fused
 //                  kernel is launched (compute stream, event-ordered) over the tiles that are now complete.
 //   device source: one launch per input stream on the caller's CUDA stream.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.hpp"
@@ -18,7 +20,7 @@ namespace fqg {
 
 namespace {
 enum { D_BUF0 = 0, D_BUF1, D_STATE0, D_STATE1, D_COUNTERS0, D_COUNTERS1, D_MASK0, D_MASK1, D_IDH0, D_IDH1, D_RECOFF0, D_RECOFF1, D_RECLEN0, D_RECLEN1,
-       D_CTL, D_UNITS, D_SPANS, D_SCAN, D_N };
+       D_CTL, D_UNITS, D_SPANS, D_SCAN, D_STATS, D_N };
 enum { H_CTL = 0, H_MASK, H_SPANS, H_N };
 constexpr size_t kCopyChunk = 32ull << 20;
 constexpr uint32_t kMaxLaunches = 1u << 12;
@@ -71,6 +73,7 @@ struct FastqLane {
     uint64_t h2d_bytes = 0;
     unsigned stripped = 0;
     bool names = false, have_matcher = false;
+    unsigned long long* stats = nullptr;
 
     int dev_ensure(int slot, size_t bytes, void** out) {
         if (d_cap[slot] < bytes) {
@@ -229,19 +232,28 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         }
     }
     // control block: [0] err, [1] count, [2] id mismatch, [3] lines r1, [4] lines r2, [5] selected spans
-    void* p;
+    void* p = nullptr;
     if ((rc = L->dev_ensure(D_CTL, 64, &p))) return rc;
     unsigned long long* ctl = (unsigned long long*)p;
-    void* d_units;
+    void* d_units = nullptr;
     L->units_words_cap = sp[0].mask_words;
     if ((rc = L->dev_ensure(D_UNITS, L->units_words_cap * 4 + 16, &d_units))) return rc;
     void* h_ctl = nullptr;
-    if ((rc = L->host_ensure(H_CTL, 64, &h_ctl))) return rc;
+    if ((rc = L->host_ensure(H_CTL, 128, &h_ctl))) return rc;
+    static const bool want_stats = std::getenv("FQG_FASTQ_STATS") != nullptr;      // measurement hook: tile statistics of the fused kernel on stderr
+    unsigned long long* d_stats = nullptr;
+    if (want_stats) {
+        void* ps = nullptr;
+        if ((rc = L->dev_ensure(D_STATS, 64, &ps))) return rc;
+        d_stats = (unsigned long long*)ps;
+    }
+    L->stats = d_stats;
 
     unsigned long long* ctl_init = (unsigned long long*)h_ctl;      // pinned: the async copy below reads it when it runs
     ctl_init[0] = ~0ull; ctl_init[1] = 0; ctl_init[2] = ~0ull; ctl_init[3] = 0; ctl_init[4] = 0; ctl_init[5] = 0; ctl_init[6] = 0; ctl_init[7] = 0;
     CU_TRY(cudaEventRecord(L->ev[0], cs));
     CU_TRY(cudaMemcpyAsync(ctl, ctl_init, 64, cudaMemcpyHostToDevice, cs));
+    if (d_stats) CU_TRY(cudaMemsetAsync(d_stats, 0, 64, cs));
     for (int i = 0; i < n_streams; i++) {
         CU_TRY(cudaMemsetAsync(sp[i].state, 0, ((size_t)sp[i].tiles + sp[i].tiles / 32 + 2) * 8, cs));
         CU_TRY(cudaMemsetAsync(sp[i].counters, 0, kMaxLaunches * 4, cs));
@@ -263,6 +275,7 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         a.names = nv;
         if (in.idx && i == 0) { a.seq_start = in.idx->seq_start; a.seq_len = in.idx->seq_len; a.span_cap = in.idx->cap; }
         a.rec_off = s.rec_off; a.rec_len = s.rec_len; a.rec_cap = s.rec_off ? s.mask_bits : 0;
+        a.stats = d_stats;
         CU_TRY(launch_match_fastq(dd, names, m == nullptr, a, c->sm_count, cs));
         count_launches(1);
         s.launches++;
@@ -326,6 +339,7 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
     }
     CU_TRY(cudaEventRecord(L->ev[3], cs));
     CU_TRY(cudaMemcpyAsync(h_ctl, ctl, 64, cudaMemcpyDeviceToHost, cs));
+    if (d_stats) CU_TRY(cudaMemcpyAsync((uint8_t*)h_ctl + 64, d_stats, 64, cudaMemcpyDeviceToHost, cs));
     // The unit mask goes back without waiting for the record count: every word the count could ask for is copied now
     // (1 bit per min_record_bytes of input) into pinned staging, so a host batch needs ONE synchronisation.
     L->eager_mask_words = 0;
@@ -352,6 +366,9 @@ int lane_wait(fqg_ctx* c, FastqLane* L, BatchOut* out) {
     const int mode = in.mode;
     const int n_streams = mode == FQG_PAIRED ? 2 : 1;
     const unsigned long long* h_ctl = (const unsigned long long*)L->h[H_CTL];
+    if (L->stats)
+        std::fprintf(stderr, "[fqg] fused kernel: %llu tiles, %llu with a guessed line phase (%llu guessed wrong), %llu dense\n", h_ctl[8] + h_ctl[11], h_ctl[9], h_ctl[10],
+                     h_ctl[11]);
     fqg_result* res = &out->res;
     uint64_t d2h_bytes = 64 + L->eager_mask_words * 4;
 

@@ -28,6 +28,8 @@
 // Round 1's kernel shared one 19 KB tile between the four warps of a "tile group" and needed four group barriers, a
 // shared bitmap, a binary search per record and a bit-scan per line end: 80 warp-instructions per record and 8.9 barrier
 // stalls per issue (profiles/r1zz_match_fastq_ncu_full.txt); this shape does the same work in about half the instructions.
+#include <cstdlib>
+
 #include "dfa_device.cuh"
 #include "kernels.hpp"
 #include "names_device.cuh"
@@ -473,11 +475,11 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
-    // Tiles are claimed in order from an atomic counter, one claim AHEAD: while a tile is processed the warp already
-    // holds the id of its next one, so the claim's round trip is never waited for and the next tile's bytes can be
-    // pulled into L2 (126 MB) long before the bulk copy asks for them -- a warp has a single tile buffer, this is how
-    // HBM is kept busy.  (A tile claimed early publishes its newline count late; that is harmless because look-backs are
-    // resolved at the END of a tile's processing, see step 5.)
+    // Tiles are claimed in order from an atomic counter.  A tile is started the moment it is claimed: its newline count is
+    // then published a fixed time after the claim, which is what the look-backs of the tiles behind it wait for.
+    // (Claiming one tile AHEAD hides the claim's round trip, but an early-claimed tile publishes a whole tile-time later
+    // and the tiles behind it wait that much longer: measured 2.6x slower.  a.early_claim keeps that variant measurable.)
+    const uint32_t nwarps_all = gridDim.x * (blockDim.x >> 5);
     uint32_t claim = 0;
     if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
     claim = __shfl_sync(kFullMask, claim, 0);
@@ -491,7 +493,17 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
             }
-            next_claim = atomicAdd(a.tile_counter, 1u);      // consumed after the record phase
+            if (a.early_claim) next_claim = atomicAdd(a.tile_counter, 1u);      // consumed after the record phase
+            else {
+                // Tiles are handed out in order, so the tile one full wave ahead (one per resident warp) is the one some warp
+                // will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~25 MB) so that copy only pays
+                // L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
+                const uint32_t ahead = claim + nwarps_all;
+                if (ahead < a.tile_count) {
+                    const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
+                    if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
+                }
+            }
         }
         if (g.real_avail) {
             mbar_wait(bar, phase);       // try_wait suspends the warp in hardware; no issue slots are burnt
@@ -538,13 +550,15 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         const uint32_t agg = g.region == kTile ? __shfl_sync(kFullMask, incl, kTileLanes - 1u) : total;
         c.total = total;
         lookback_publish(a, g.t, agg, lane);
-        // the next tile is known by now: warm L2 with it
-        next_claim = __shfl_sync(kFullMask, next_claim, 0);
-        if (lane == 0 && next_claim < a.tile_count) {
-            const TileGeom gn = tile_geom(a, a.tile_first + next_claim, stream_len);
-            if (gn.real_avail) bulk_prefetch_l2(a.buf + gn.T0, (gn.real_avail + 15u) & ~15u);
+        if (a.early_claim) {      // the next tile is known by now: warm L2 with it
+            next_claim = __shfl_sync(kFullMask, next_claim, 0);
+            if (lane == 0 && next_claim < a.tile_count) {
+                const TileGeom gn = tile_geom(a, a.tile_first + next_claim, stream_len);
+                if (gn.real_avail) bulk_prefetch_l2(a.buf + gn.T0, (gn.real_avail + 15u) & ~15u);
+            }
         }
 
+        if (a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
         if (total > kListCap) {
             const unsigned long long Lt = lookback_resolve(a, g.t, agg, lane);
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
@@ -600,8 +614,10 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                 }
                 const uint32_t votes = __ballot_sync(kFullMask, ok);
                 const uint32_t both = votes & (votes >> 4) & 0xFu;              // candidates whose first AND second record look right
-                if (both && (both & (both - 1u)) == 0) j0 = (uint32_t)__ffs((int)both) - 1u;
-                else {
+                if (both && (both & (both - 1u)) == 0) {
+                    j0 = (uint32_t)__ffs((int)both) - 1u;
+                    if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
+                } else {
                     Lt = lookback_resolve(a, g.t, agg, lane);
                     have_Lt = true;
                     j0 = 3u - (uint32_t)(Lt & 3ull);
@@ -625,7 +641,12 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         Lt = lookback_resolve(a, g.t, agg, lane);
                         have_Lt = true;
                         const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
-                        if (exact != j0) { j0 = exact; redo = true; break; }
+                        if (exact != j0) {
+                            if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                            j0 = exact;
+                            redo = true;
+                            break;
+                        }
                         ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
                     }
                     local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
@@ -641,6 +662,10 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
         }
         __syncwarp();       // every lane is done with the list and the tile before the next bulk copy overwrites them
+        if (!a.early_claim) {
+            if (lane == 0) next_claim = atomicAdd(a.tile_counter, 1u);
+            next_claim = __shfl_sync(kFullMask, next_claim, 0);
+        }
         claim = next_claim;
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
@@ -730,6 +755,8 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only
     FastqArgs a = args;
     a.nl_xor = 0x0A0A0A0Au;
     a.nl_low7 = 0x7F7F7F7Fu;
+    static const bool early = [] { const char* e = std::getenv("FQG_FASTQ_EARLY_CLAIM"); return e && *e == '1'; }();
+    a.early_claim = early ? 1u : 0u;
     if (index_only) return launch_fastq_t<5>(dfa, a, sm_count, stream);
     if (names) return launch_fastq_t<3>(dfa, a, sm_count, stream);
     switch (dfa.tier) {

@@ -138,3 +138,52 @@ def test_cli_flags_exit_codes_names_iupac_gzip(tmp_path, kat):
     open(bad, "wb").write(b"@a\nACGT\n+\nXXX\n")
     code, _, err = run("-c", "A", bad)                           # the reference panics on malformed input -> 101
     assert code == 101 and "fqgrep panicked" in err
+
+
+@pytest.mark.gpu
+def test_cli_streams_large_inputs_through_a_small_ring(tmp_path):
+    """The command line reads its inputs a slot at a time (reader threads -> ring -> ordered write-back).  With 1 MiB slots
+    a 30 MB pair of gzip / BGZF / plain inputs takes ~30 batches per stream; counts and output bytes must be the oracle's,
+    on one device and with the batches dealt to two streams (--gpus 2 needs two devices: skipped on a one-GPU box)."""
+    import gzip
+    import random
+    from oracle import oracle as O
+    from tests.test_gpu_stream import ragged_pair
+    from tests.test_input import bgzf
+    rng = random.Random(5)
+    r1, r2 = ragged_pair(rng, 60_000)
+    p1, p2, pz1, pz2, pb1 = (str(tmp_path / n) for n in ("a_1.fq", "a_2.fq", "z_1.fq.gz", "z_2.fq.gz", "b_1.fq.bgz"))
+    open(p1, "wb").write(r1); open(p2, "wb").write(r2)
+    open(pz1, "wb").write(gzip.compress(r1, 1)); open(pz2, "wb").write(gzip.compress(r2, 1))
+    open(pb1, "wb").write(bgzf(r1, block=60000))
+    pats = ["GATTACA", "AC[GT]T{2,}"]
+    o = O.Matcher(O.REGEX_SET, pats, False, True)
+    e1 = o.grep(r1, want_output=True, threads=8)
+    ep = o.grep(r1, r2, mode=O.PAIRED, want_output=True, split=True, threads=8)
+    args = ["-e", pats[0], "-e", pats[1], "--reverse-complement", "--slot-mb", "1"]
+    for path in (p1, pz1, pb1):
+        code, out, err = run(*args, path)
+        assert code == 0 and out == e1["out"], (path, err[-300:])
+        code, out, err = run("-c", *args, path)
+        assert out == b"%d\n" % e1["count"]
+    code, out, err = run("--paired", *args, p1, p2)
+    assert code == 0 and out == O.Matcher(O.REGEX_SET, pats, False, True).grep(r1, r2, mode=O.PAIRED, want_output=True, threads=8)["out"], err[-300:]
+    code, out, err = run("--paired", *args, "--output", tmp_path / "o1.fq", tmp_path / "o2.fq", "--", pz1, pz2)
+    assert code == 0 and open(str(tmp_path / "o1.fq"), "rb").read() == ep["out"] and open(str(tmp_path / "o2.fq"), "rb").read() == ep["out2"], err[-300:]
+    code, out, err = run("-c", "--paired", "--progress", *args, p1, p2, pz1, pz2)         # counts add up over the input pairs
+    assert out == b"%d\n" % (2 * ep["count"]) and "Searched" in err
+    # mates that run out of step are the reference's panic, wherever in the stream it happens
+    open(str(tmp_path / "short_2.fq"), "wb").write(r2[: r2.rfind(b"@q")])
+    code, _, err = run("-c", "--paired", *args, p1, tmp_path / "short_2.fq")
+    assert code == 101 and "out of sync" in err
+    # a record larger than a slot cannot be batched: a clear error, not a hang
+    big = b"@big\n" + b"A" * (3 << 20) + b"\n+\n" + b"I" * (3 << 20) + b"\n"
+    open(str(tmp_path / "big.fq"), "wb").write(r1[:5000] + big)
+    code, _, err = run("-c", *args, tmp_path / "big.fq")
+    assert code == 2 and "--slot-mb" in err
+    code, out, _ = run("-c", "-e", "A{100}", "--slot-mb", "16", tmp_path / "big.fq")
+    assert out == b"1\n"
+    import torch
+    if torch.cuda.device_count() >= 2:
+        code, out, err = run("--paired", "--gpus", "2", *args, p1, p2)
+        assert code == 0 and out == O.Matcher(O.REGEX_SET, pats, False, True).grep(r1, r2, mode=O.PAIRED, want_output=True, threads=8)["out"], err[-300:]

@@ -130,3 +130,57 @@ def test_truncated_gzip_is_an_error_wherever_the_cut_falls(tmp_path):
     assert F.read_input(str(tmp_path / "ok.fq.gz")).tobytes() == a + b
     open(str(tmp_path / "ok2.fq.bgz"), "wb").write(bgzf(a + b, eof=False))
     assert F.read_input(str(tmp_path / "ok2.fq.bgz")).tobytes() == a + b
+
+
+def _read_all(path, cap, decompress=False):
+    """fqg_reader_*: the incremental reader of the streaming path, `cap` bytes per call."""
+    import ctypes as C
+    from fqgrep_b200 import _ffi
+    L = _ffi.lib()
+    h = C.c_void_p()
+    if L.fqg_reader_open(str(path).encode(), int(decompress), C.byref(h)) != 0:
+        raise F.FqgrepError(-1, _ffi.last_error())
+    out = bytearray()
+    buf = np.zeros(cap, dtype=np.uint8)
+    try:
+        for _ in range(1 << 20):
+            n, eof = C.c_size_t(0), C.c_int(0)
+            rc = L.fqg_reader_read(h, buf.ctypes.data, cap, C.byref(n), C.byref(eof))
+            if rc != 0:
+                raise F.FqgrepError(rc, _ffi.last_error())
+            assert n.value <= cap
+            out += buf[: n.value].tobytes()
+            if eof.value:
+                break
+            assert n.value > 0
+        else:
+            raise AssertionError("reader never reached eof")
+    finally:
+        L.fqg_reader_close(h)
+    return bytes(out)
+
+
+def test_incremental_reader_plain_gzip_bgzf_mixed_and_truncated(tmp_path):
+    data = fastq(["ACGT" * 40, "TTTTGGGGCCCC" * 12, "N" * 7] * 4000)      # ~1.3 MB
+    files = {"p.fq": data, "g.fq.gz": gzip.compress(data), "m.fq.gz": b"".join(gzip.compress(data[i:i + 70000]) for i in range(0, len(data), 70000)),
+             "b.fq.bgz": bgzf(data), "b_noeof.fq.gz": bgzf(data, eof=False), "mixed.fq.gz": bgzf(data[:300000], eof=False) + gzip.compress(data[300000:]),
+             "mixed2.fq.gz": gzip.compress(data[:300000]) + bgzf(data[300000:]), "e.fq": b"", "e.fq.gz": gzip.compress(b""), "z.dat": gzip.compress(data)}
+    for name, z in files.items():
+        p = tmp_path / name
+        p.write_bytes(z)
+        want = data if not name.startswith("e.") else b""
+        for cap in (1000, 65536, 100_000, 1 << 20, 8 << 20):
+            assert _read_all(p, cap, decompress=name.endswith(".dat")) == want, (name, cap)
+    (tmp_path / "raw.dat").write_bytes(data)
+    assert _read_all(tmp_path / "raw.dat", 4096) == data                   # no -Z: read as it is
+    a, b = data[:400000], data[400000:]
+    za, zb = gzip.compress(a), gzip.compress(b)
+    for name, z in {"t1.fq.gz": za[: len(za) // 2], "t2.fq.gz": za + zb[: len(zb) // 2], "t3.fq.gz": za + zb[:5], "t4.fq.bgz": bgzf(data)[:-40],
+                    "t5.fq.bgz": bgzf(data, eof=False)[: len(bgzf(data)) // 2], "t6.fq.gz": b"not gzip at all"}.items():
+        p = tmp_path / name
+        p.write_bytes(z)
+        for cap in (70000, 4 << 20):
+            with pytest.raises(F.FqgrepError):
+                _read_all(p, cap)
+    with pytest.raises(F.FqgrepError):
+        _read_all(tmp_path / "missing.fq", 100)
