@@ -41,6 +41,8 @@ struct StreamPlan {
     uint32_t tiles_done = 0, launches = 0;
 };
 
+size_t state_words(uint32_t tiles) { return (size_t)tiles + 1 + 2 * ((size_t)tiles / 32 + 2); }
+
 const char* fastq_err_name(unsigned code) {
     switch (code) {
         case 1: return "expected '@' at record start (InvalidStart)";
@@ -213,8 +215,8 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
             if ((rc = L->dev_ensure(D_BUF0 + i, n + 64, &p))) return rc;
             s.d = (const uint8_t*)p;
         } else s.d = s.src;
-        // look-back state: one word per tile, then one per segment of 32 tiles
-        if ((rc = L->dev_ensure(D_STATE0 + i, ((size_t)s.tiles + s.tiles / 32 + 2) * 8, &p))) return rc;
+        // look-back state: one word per tile, then two per segment of 32 tiles
+        if ((rc = L->dev_ensure(D_STATE0 + i, state_words(s.tiles) * 8, &p))) return rc;
         s.state = (unsigned long long*)p;
         if ((rc = L->dev_ensure(D_COUNTERS0 + i, kMaxLaunches * 4, &p))) return rc;
         s.counters = (uint32_t*)p;
@@ -255,7 +257,7 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
     CU_TRY(cudaMemcpyAsync(ctl, ctl_init, 64, cudaMemcpyHostToDevice, cs));
     if (d_stats) CU_TRY(cudaMemsetAsync(d_stats, 0, 64, cs));
     for (int i = 0; i < n_streams; i++) {
-        CU_TRY(cudaMemsetAsync(sp[i].state, 0, ((size_t)sp[i].tiles + sp[i].tiles / 32 + 2) * 8, cs));
+        CU_TRY(cudaMemsetAsync(sp[i].state, 0, state_words(sp[i].tiles) * 8, cs));
         CU_TRY(cudaMemsetAsync(sp[i].counters, 0, kMaxLaunches * 4, cs));
         CU_TRY(cudaMemsetAsync(sp[i].mask, 0, sp[i].mask_words * 4, cs));
     }
@@ -267,7 +269,7 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         FastqArgs a{};
         a.buf = s.d; a.nbytes = s.n; a.virtual_final_nl = 1;
         a.tile_first = s.tiles_done; a.tile_count = tile_end - s.tiles_done;
-        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_state = s.state + s.tiles + 1; a.lines_out = ctl + 3 + i;
+        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_acc = s.state + s.tiles + 1; a.seg_pre = a.seg_acc + s.tiles / 32 + 2; a.lines_out = ctl + 3 + i;
         a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
         a.count = mode == FQG_SINGLE ? ctl + 1 : nullptr;
         a.err = ctl + 0;

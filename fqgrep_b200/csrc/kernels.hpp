@@ -74,7 +74,8 @@ struct FastqArgs {
     uint32_t tile_first, tile_count;   // this launch handles global tiles [tile_first, tile_first + tile_count)
     uint32_t* tile_counter;        // zeroed, one per launch
     unsigned long long* tile_state;    // zeroed, one per global tile of the stream (look-back state)
-    unsigned long long* seg_state;     // zeroed, one per segment of 32 consecutive tiles (second level of the look-back)
+    unsigned long long* seg_acc;       // zeroed, one per segment of 32 consecutive tiles: tiles reported << 48 | their newlines
+    unsigned long long* seg_pre;       // zeroed, one per segment: inclusive prefix at its end once known (match_fastq.cu, Lookback)
     unsigned long long* lines_out;     // total newline count, written by the stream's last tile
     uint32_t* mask;                // zeroed record bitmask, bit = global record number
     uint64_t mask_bits;

@@ -76,6 +76,10 @@ __device__ __forceinline__ uint32_t lds_u16_volatile(uint32_t a) {
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
+// store only where `on` is non-zero -- as a PREDICATED store, not a branch around one
+__device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, uint32_t on) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n}" ::"r"(a), "h"((unsigned short)v), "r"(on) : "memory");
+}
 
 // 0x80 in every byte of w that is '\n', 0 elsewhere.  Exact (no borrow between bytes): the low 7 bits of a byte of
 // w ^ '\n' overflow into bit 7 of the sum unless they are all zero, and bit 7 of w itself must be clear.  c0a = 0x0A0A0A0A
@@ -208,23 +212,41 @@ __device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, ui
 }
 
 // ---- decoupled look-back by one warp ------------------------------------------------------------------------------------
-// Number of newlines before tile t.  Two levels.  Every resident warp works on its own tile at about the same time
-// (~2000 tiles in flight), so a flat look-back finds nothing but aggregates for a whole wave and needs wave/32 dependent L2
-// round trips per tile.  Tiles are therefore grouped in segments of 32: the tile that closes a segment publishes the
-// segment's aggregate as soon as it has seen its 31 predecessors' aggregates, and a look-back sums its own segment first
-// (one round), then hops 32 segments (1024 tiles) per round.  State words: flag << 62 | value, flag 1 = aggregate, 2 =
-// inclusive prefix.  Tiles are handed out in order, so every state a tile waits for belongs to a warp that is already
-// running and publishes it without waiting for anything later: no circular wait.
-// Split in two so that the scatter of the newline list runs between publishing the aggregate and polling the predecessors.
-__device__ __forceinline__ void lookback_publish(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
-    if (t > 0 && lane == 0) atomicExch(a.tile_state + t, (1ull << 62) | agg);
+// Number of newlines before tile t.  Every resident warp works on its own tile at about the same time (~2400 tiles in
+// flight), so a flat look-back would find nothing but per-tile counts for a whole wave.  Two levels, both fed EARLY:
+//   tile_state[t]   flag << 62 | value; flag 1 = the tile's own count, 2 = inclusive prefix (all newlines up to its end)
+//   seg_acc[s]      tiles of segment s (32 consecutive tiles) that have reported << 48 | sum of their counts: every tile ADDS
+//                   its count here the moment it knows it, so a segment's total is there when its slowest tile has scanned
+//                   its bytes -- no tile has to collect it (round 1 and the first round-2 kernel let the segment's last tile
+//                   publish the total from its own look-back: everybody behind then waited for that tile, 26 % of all stall
+//                   samples and 15 instructions per record of polling, profiles/r2d_*)
+//   seg_pre[s]      2 << 62 | inclusive prefix at the end of segment s, written by the segment's last tile when it resolves
+// publish runs right after the tile's newline masks are known, resolve at the very end of the tile (see the kernel), i.e.
+// most of a tile-time later: what it reads has long been written.  Tiles are handed out in order and started when claimed,
+// so every state a tile waits for belongs to a warp that is running and reports without waiting for anything: no cycle.
+struct Lookback {
+    unsigned long long *tile_state, *seg_acc, *seg_pre;
+};
+__device__ __forceinline__ void lookback_publish(const Lookback& lb, uint32_t t, uint32_t agg, uint32_t lane) {
+    if (lane == 0) atomicExch(lb.tile_state + t, ((t == 0 ? 2ull : 1ull) << 62) | agg);      // nothing precedes tile 0: its count is its prefix
+    if (lane == 1) atomicAdd(lb.seg_acc + (t >> 5), (1ull << 48) | agg);
 }
-__device__ __forceinline__ unsigned long long lookback_resolve(const FastqArgs& a, uint32_t t, uint32_t agg, uint32_t lane) {
-    const unsigned long long kValue = (1ull << 62) - 1;
-    auto poll = [](const unsigned long long* p) {
+__device__ __noinline__ unsigned long long lookback_resolve(Lookback lb, uint32_t t, uint32_t agg, uint32_t lane) {
+    if (t == 0) return 0;
+    const unsigned long long kValue = (1ull << 62) - 1, kSum = (1ull << 48) - 1;
+    auto poll_tile = [](const unsigned long long* p) {
         unsigned long long st;
         while (((st = *reinterpret_cast<const volatile unsigned long long*>(p)) >> 62) == 0) __nanosleep(40);      // spinning would steal issue slots
         return st;
+    };
+    auto poll_seg = [&](int32_t idx) -> unsigned long long {
+        for (;;) {
+            const unsigned long long pre = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_pre + idx);
+            if ((pre >> 62) == 2) return pre;
+            const unsigned long long acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
+            if ((acc >> 48) == 32) return (1ull << 62) | (acc & kSum);
+            __nanosleep(40);
+        }
     };
     // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix
     auto fold = [&](unsigned long long st, bool use, bool& hit_prefix) {
@@ -236,23 +258,19 @@ __device__ __forceinline__ unsigned long long lookback_resolve(const FastqArgs& 
         hit_prefix = has_prefix != 0;
         return v;
     };
-    unsigned long long excl = 0;
     const uint32_t r = t & 31u;                    // predecessors inside this tile's own segment
-    if (t > 0) {
-        bool done = false;
-        const bool mine = lane < r;
-        excl = fold(mine ? poll(a.tile_state + (t - 1u - lane)) : 0ull, mine, done);
-        if (r == 31u && !done && lane == 0) atomicExch(a.seg_state + (t >> 5), (1ull << 62) | (excl + agg));
-        int32_t seg = (int32_t)(t >> 5) - 1;       // nearest earlier segment
-        while (!done) {
-            const int32_t idx = seg - (int32_t)lane;
-            excl += fold(idx >= 0 ? poll(a.seg_state + idx) : (2ull << 62), true, done);      // before the stream: prefix 0
-            seg -= 32;
-        }
+    bool done = false;
+    const bool mine = lane < r;
+    unsigned long long excl = fold(mine ? poll_tile(lb.tile_state + (t - 1u - lane)) : 0ull, mine, done);
+    int32_t seg = (int32_t)(t >> 5) - 1;           // nearest earlier segment
+    while (!done) {
+        const int32_t idx = seg - (int32_t)lane;
+        excl += fold(idx >= 0 ? poll_seg(idx) : (2ull << 62), true, done);      // before the stream: prefix 0
+        seg -= 32;
     }
     if (lane == 0) {
-        atomicExch(a.tile_state + t, (2ull << 62) | (excl + agg));
-        if (r == 31u) atomicExch(a.seg_state + (t >> 5), (2ull << 62) | (excl + agg));
+        atomicExch(lb.tile_state + t, (2ull << 62) | (excl + agg));
+        if (r == 31u) atomicExch(lb.seg_pre + (t >> 5), (2ull << 62) | (excl + agg));
     }
     return excl;
 }
@@ -472,6 +490,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     const uint64_t stream_len = c.stream_len;
     const uint32_t c0a = a.nl_xor, c7f = a.nl_low7;     // see FastqArgs: not compile-time constants on purpose
     const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
+    const Lookback lb{a.tile_state, a.seg_acc, a.seg_pre};
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
@@ -549,7 +568,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         const uint32_t total = __shfl_sync(kFullMask, incl, 31);
         const uint32_t agg = g.region == kTile ? __shfl_sync(kFullMask, incl, kTileLanes - 1u) : total;
         c.total = total;
-        lookback_publish(a, g.t, agg, lane);
+        lookback_publish(lb, g.t, agg, lane);
         if (a.early_claim) {      // the next tile is known by now: warm L2 with it
             next_claim = __shfl_sync(kFullMask, next_claim, 0);
             if (lane == 0 && next_claim < a.tile_count) {
@@ -560,7 +579,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
 
         if (a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
         if (total > kListCap) {
-            const unsigned long long Lt = lookback_resolve(a, g.t, agg, lane);
+            const unsigned long long Lt = lookback_resolve(lb, g.t, agg, lane);
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
             LaneWords mw;
 #pragma unroll
@@ -568,7 +587,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             local_count += dense_tile<TIER>(a, ev, c, g, mw, incl - cnt, agg, Lt, lane);
         } else {
             // ---- 4. scatter: list[rank] = position in the tile.  Two branch-free steps per word (a lane rarely has more
-            //         than two newlines in 32 bytes), then a loop for whatever is left in any lane.
+            //         than two newlines in 32 bytes: the "\n+\n" of a record), then a loop for whatever is left in any lane.
             {
                 uint32_t addr = list_sa + 2u * (incl - cnt);
 #pragma unroll
@@ -577,13 +596,15 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                     const uint32_t pos0 = lane_pos + 32u * j;
 #pragma unroll
                     for (int step = 0; step < 2; step++) {
-                        const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
-                        if (w) { sts_u16(addr, pos0 + b); addr += 2u; }
+                        const uint32_t on = w ? 1u : 0u;
+                        sts_u16_if(addr, pos0 + (uint32_t)__ffs((int)w) - 1u, on);
+                        addr += 2u * on;
                         w &= w - 1u;
                     }
                     while (__any_sync(kFullMask, w != 0)) {
-                        const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
-                        if (w) { sts_u16(addr, pos0 + b); addr += 2u; }
+                        const uint32_t on = w ? 1u : 0u;
+                        sts_u16_if(addr, pos0 + (uint32_t)__ffs((int)w) - 1u, on);
+                        addr += 2u * on;
                         w &= w - 1u;
                     }
                 }
@@ -601,7 +622,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             bool have_Lt = false;
             uint32_t j0 = 3u;
             if (g.t == 0) {                // nothing precedes the first tile: no wait, but its prefix must be published for the others
-                Lt = lookback_resolve(a, g.t, agg, lane);
+                Lt = lookback_resolve(lb, g.t, agg, lane);
                 have_Lt = true;
             } else {
                 bool ok = false;
@@ -618,7 +639,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                     j0 = (uint32_t)__ffs((int)both) - 1u;
                     if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
                 } else {
-                    Lt = lookback_resolve(a, g.t, agg, lane);
+                    Lt = lookback_resolve(lb, g.t, agg, lane);
                     have_Lt = true;
                     j0 = 3u - (uint32_t)(Lt & 3ull);
                 }
@@ -638,7 +659,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         o = eval_record<TIER>(a, ev, c, s, r0, 0u);
                     }
                     if (!have_Lt) {
-                        Lt = lookback_resolve(a, g.t, agg, lane);
+                        Lt = lookback_resolve(lb, g.t, agg, lane);
                         have_Lt = true;
                         const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
                         if (exact != j0) {
@@ -652,7 +673,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                     local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
                 }
                 if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed
-                    Lt = lookback_resolve(a, g.t, agg, lane);
+                    Lt = lookback_resolve(lb, g.t, agg, lane);
                     have_Lt = true;
                     const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
                     if (exact != j0) { j0 = exact; redo = true; }
