@@ -98,7 +98,6 @@ struct FastqArgs {
     // needs two constants per LOP3 and the instruction takes one immediate: as literals (even behind an asm mov, which
     // ptxas folds) every byte-test costs five instructions per word; as constant-bank operands it costs three.
     uint32_t nl_xor, nl_low7;
-    uint32_t early_claim;           // measurement switch (FQG_FASTQ_EARLY_CLAIM): claim the next tile while the current one is processed
     unsigned long long* stats;      // optional (FQG_FASTQ_STATS): [0] tiles, [1] line phase guessed, [2] guessed wrong, [3] dense tiles
 };
 // -N over SoA headers: spans are header lines without '@'; the id ends at the first space (matcher.rs:631-638)

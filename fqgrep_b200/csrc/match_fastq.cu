@@ -231,21 +231,40 @@ __device__ __forceinline__ void lookback_publish(const Lookback& lb, uint32_t t,
     if (lane == 0) atomicExch(lb.tile_state + t, ((t == 0 ? 2ull : 1ull) << 62) | agg);      // nothing precedes tile 0: its count is its prefix
     if (lane == 1) atomicAdd(lb.seg_acc + (t >> 5), (1ull << 48) | agg);
 }
-__device__ __noinline__ unsigned long long lookback_resolve(Lookback lb, uint32_t t, uint32_t agg, uint32_t lane) {
+// What lane `lane` of tile t will look at first when it resolves: the state of tile t-1-lane (own segment) and of segment
+// (t >> 5) - 1 - lane.  Loaded BEFORE the record phase and consumed after it, so the two dependent L2 round trips of a
+// look-back (9 % of all stall samples when taken on the spot, profiles/r2e_*) overlap with the walk of the records.
+struct LookbackPre {
+    unsigned long long tile_st, seg_pre, seg_acc;
+};
+__device__ __forceinline__ LookbackPre lookback_prefetch(const Lookback& lb, uint32_t t, uint32_t lane) {
+    LookbackPre p{0ull, 0ull, 0ull};
+    if (t == 0) return p;
+    if (lane < (t & 31u)) p.tile_st = *reinterpret_cast<const volatile unsigned long long*>(lb.tile_state + (t - 1u - lane));
+    const int32_t idx = (int32_t)(t >> 5) - 1 - (int32_t)lane;
+    if (idx >= 0) {
+        p.seg_pre = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_pre + idx);
+        p.seg_acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
+    }
+    return p;
+}
+__device__ __noinline__ unsigned long long lookback_resolve(Lookback lb, uint32_t t, uint32_t agg, uint32_t lane, LookbackPre pre) {
     if (t == 0) return 0;
     const unsigned long long kValue = (1ull << 62) - 1, kSum = (1ull << 48) - 1;
-    auto poll_tile = [](const unsigned long long* p) {
-        unsigned long long st;
-        while (((st = *reinterpret_cast<const volatile unsigned long long*>(p)) >> 62) == 0) __nanosleep(40);      // spinning would steal issue slots
+    auto poll_tile = [](const unsigned long long* p, unsigned long long st) {
+        while ((st >> 62) == 0) {      // spinning would steal issue slots
+            __nanosleep(40);
+            st = *reinterpret_cast<const volatile unsigned long long*>(p);
+        }
         return st;
     };
-    auto poll_seg = [&](int32_t idx) -> unsigned long long {
+    auto poll_seg = [&](int32_t idx, unsigned long long p, unsigned long long acc) -> unsigned long long {
         for (;;) {
-            const unsigned long long pre = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_pre + idx);
-            if ((pre >> 62) == 2) return pre;
-            const unsigned long long acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
+            if ((p >> 62) == 2) return p;
             if ((acc >> 48) == 32) return (1ull << 62) | (acc & kSum);
             __nanosleep(40);
+            p = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_pre + idx);
+            acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
         }
     };
     // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix
@@ -261,12 +280,16 @@ __device__ __noinline__ unsigned long long lookback_resolve(Lookback lb, uint32_
     const uint32_t r = t & 31u;                    // predecessors inside this tile's own segment
     bool done = false;
     const bool mine = lane < r;
-    unsigned long long excl = fold(mine ? poll_tile(lb.tile_state + (t - 1u - lane)) : 0ull, mine, done);
+    unsigned long long excl = fold(mine ? poll_tile(lb.tile_state + (t - 1u - lane), pre.tile_st) : 0ull, mine, done);
     int32_t seg = (int32_t)(t >> 5) - 1;           // nearest earlier segment
+    bool first_round = true;
     while (!done) {
         const int32_t idx = seg - (int32_t)lane;
-        excl += fold(idx >= 0 ? poll_seg(idx) : (2ull << 62), true, done);      // before the stream: prefix 0
+        unsigned long long st = 2ull << 62;        // before the stream: prefix 0
+        if (idx >= 0) st = first_round ? poll_seg(idx, pre.seg_pre, pre.seg_acc) : poll_seg(idx, 0ull, 0ull);
+        excl += fold(st, true, done);
         seg -= 32;
+        first_round = false;
     }
     if (lane == 0) {
         atomicExch(lb.tile_state + t, (2ull << 62) | (excl + agg));
@@ -494,10 +517,12 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
-    // Tiles are claimed in order from an atomic counter.  A tile is started the moment it is claimed: its newline count is
-    // then published a fixed time after the claim, which is what the look-backs of the tiles behind it wait for.
-    // (Claiming one tile AHEAD hides the claim's round trip, but an early-claimed tile publishes a whole tile-time later
-    // and the tiles behind it wait that much longer: measured 2.6x slower.  a.early_claim keeps that variant measurable.)
+    // Tiles are claimed in order from an atomic counter and started the moment they are claimed: a tile's newline count is
+    // then published a fixed time after its claim, which is what the look-backs of the tiles behind it rely on.  (Claiming
+    // one tile AHEAD would hide the claim's round trip, but an early-claimed tile publishes a whole tile-time later and
+    // everything behind it waits that much longer: measured 2.6x slower, profiles/r2c_*.)  The claim for the NEXT tile is
+    // therefore issued only when the record phase of this one is over, just before the look-back is resolved and the
+    // results are committed -- enough work to cover its round trip.
     const uint32_t nwarps_all = gridDim.x * (blockDim.x >> 5);
     uint32_t claim = 0;
     if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
@@ -506,22 +531,20 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         const TileGeom g = tile_geom(a, a.tile_first + claim, stream_len);
         c.T0 = g.T0;
         uint32_t next_claim = 0;
+        bool claimed = false;
         if (lane == 0) {
             if (g.real_avail) {
                 const uint32_t bytes = (g.real_avail + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
             }
-            if (a.early_claim) next_claim = atomicAdd(a.tile_counter, 1u);      // consumed after the record phase
-            else {
-                // Tiles are handed out in order, so the tile one full wave ahead (one per resident warp) is the one some warp
-                // will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~25 MB) so that copy only pays
-                // L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
-                const uint32_t ahead = claim + nwarps_all;
-                if (ahead < a.tile_count) {
-                    const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
-                    if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
-                }
+            // Tiles are handed out in order, so the tile one full wave ahead (one per resident warp) is the one some warp
+            // will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~25 MB) so that copy only pays
+            // L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
+            const uint32_t ahead = claim + nwarps_all;
+            if (ahead < a.tile_count) {
+                const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
+                if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
             }
         }
         if (g.real_avail) {
@@ -569,17 +592,15 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         const uint32_t agg = g.region == kTile ? __shfl_sync(kFullMask, incl, kTileLanes - 1u) : total;
         c.total = total;
         lookback_publish(lb, g.t, agg, lane);
-        if (a.early_claim) {      // the next tile is known by now: warm L2 with it
-            next_claim = __shfl_sync(kFullMask, next_claim, 0);
-            if (lane == 0 && next_claim < a.tile_count) {
-                const TileGeom gn = tile_geom(a, a.tile_first + next_claim, stream_len);
-                if (gn.real_avail) bulk_prefetch_l2(a.buf + gn.T0, (gn.real_avail + 15u) & ~15u);
-            }
-        }
+        auto claim_next = [&]() {      // warp-uniform; the result is picked up at the bottom of the loop
+            if (!claimed && lane == 0) next_claim = atomicAdd(a.tile_counter, 1u);
+            claimed = true;
+        };
+        const LookbackPre no_pre{0ull, 0ull, 0ull};
 
         if (a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
         if (total > kListCap) {
-            const unsigned long long Lt = lookback_resolve(lb, g.t, agg, lane);
+            const unsigned long long Lt = lookback_resolve(lb, g.t, agg, lane, no_pre);
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
             LaneWords mw;
 #pragma unroll
@@ -621,10 +642,9 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             unsigned long long Lt = 0;
             bool have_Lt = false;
             uint32_t j0 = 3u;
-            if (g.t == 0) {                // nothing precedes the first tile: no wait, but its prefix must be published for the others
-                Lt = lookback_resolve(lb, g.t, agg, lane);
-                have_Lt = true;
-            } else {
+            LookbackPre pre = no_pre;
+            if (g.t == 0) have_Lt = true;          // nothing precedes the first tile (its prefix went out with its count)
+            else {
                 bool ok = false;
                 const uint32_t cand = lane & 3u, r = cand + 4u * (lane >> 2);      // boundary newline rank under this candidate
                 if (lane < 8u && r + 4u < total) {
@@ -638,8 +658,9 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                 if (both && (both & (both - 1u)) == 0) {
                     j0 = (uint32_t)__ffs((int)both) - 1u;
                     if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
+                    pre = lookback_prefetch(lb, g.t, lane);      // consumed after the record phase
                 } else {
-                    Lt = lookback_resolve(lb, g.t, agg, lane);
+                    Lt = lookback_resolve(lb, g.t, agg, lane, no_pre);
                     have_Lt = true;
                     j0 = 3u - (uint32_t)(Lt & 3ull);
                 }
@@ -658,8 +679,9 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
                         o = eval_record<TIER>(a, ev, c, s, r0, 0u);
                     }
+                    claim_next();
                     if (!have_Lt) {
-                        Lt = lookback_resolve(lb, g.t, agg, lane);
+                        Lt = lookback_resolve(lb, g.t, agg, lane, pre);
                         have_Lt = true;
                         const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
                         if (exact != j0) {
@@ -673,7 +695,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                     local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
                 }
                 if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed
-                    Lt = lookback_resolve(lb, g.t, agg, lane);
+                    Lt = lookback_resolve(lb, g.t, agg, lane, pre);
                     have_Lt = true;
                     const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
                     if (exact != j0) { j0 = exact; redo = true; }
@@ -683,11 +705,8 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
         }
         __syncwarp();       // every lane is done with the list and the tile before the next bulk copy overwrites them
-        if (!a.early_claim) {
-            if (lane == 0) next_claim = atomicAdd(a.tile_counter, 1u);
-            next_claim = __shfl_sync(kFullMask, next_claim, 0);
-        }
-        claim = next_claim;
+        claim_next();
+        claim = __shfl_sync(kFullMask, next_claim, 0);
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
@@ -776,8 +795,6 @@ cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only
     FastqArgs a = args;
     a.nl_xor = 0x0A0A0A0Au;
     a.nl_low7 = 0x7F7F7F7Fu;
-    static const bool early = [] { const char* e = std::getenv("FQG_FASTQ_EARLY_CLAIM"); return e && *e == '1'; }();
-    a.early_claim = early ? 1u : 0u;
     if (index_only) return launch_fastq_t<5>(dfa, a, sm_count, stream);
     if (names) return launch_fastq_t<3>(dfa, a, sm_count, stream);
     switch (dfa.tier) {
