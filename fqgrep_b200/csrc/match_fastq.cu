@@ -520,9 +520,11 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     // Tiles are claimed in order from an atomic counter and started the moment they are claimed: a tile's newline count is
     // then published a fixed time after its claim, which is what the look-backs of the tiles behind it rely on.  (Claiming
     // one tile AHEAD would hide the claim's round trip, but an early-claimed tile publishes a whole tile-time later and
-    // everything behind it waits that much longer: measured 2.6x slower, profiles/r2c_*.)  The claim for the NEXT tile is
-    // therefore issued only when the record phase of this one is over, just before the look-back is resolved and the
-    // results are committed -- enough work to cover its round trip.
+    // everything behind it waits that much longer: measured 2.6x slower, profiles/r2c_*.  Even claiming just before this
+    // tile's look-back is resolved is too early -- 3.5x slower, profiles/r2f_*: a warp that waits in its look-back while it
+    // holds an unstarted tile delays every tile behind that one, whose warps then wait holding THEIR next tiles, and the
+    // delays pile up.  The rule: between claiming a tile and publishing its count a warp never waits for another tile.)
+    // The claim for the next tile is issued right after the look-back has been resolved, before the results are committed.
     const uint32_t nwarps_all = gridDim.x * (blockDim.x >> 5);
     uint32_t claim = 0;
     if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
@@ -679,7 +681,6 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
                         o = eval_record<TIER>(a, ev, c, s, r0, 0u);
                     }
-                    claim_next();
                     if (!have_Lt) {
                         Lt = lookback_resolve(lb, g.t, agg, lane, pre);
                         have_Lt = true;
@@ -692,6 +693,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         }
                         ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
                     }
+                    claim_next();      // nothing below waits for another tile
                     local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
                 }
                 if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed
