@@ -182,6 +182,36 @@ int get_names_view(fqg_ctx* c, const fqg_matcher* cm, NamesView* out) {
     return 0;
 }
 
+// SoA reads through whichever kernel(s) the matcher's tier asks for; b.invert / b.or_mask / b.count describe the final result
+int match_soa_any(fqg_ctx* c, const fqg_matcher* m, SoaBatch b, cudaStream_t stream) {
+    DeviceDfa dd;
+    int rc = get_device_dfa(c, m, &dd);
+    if (rc) return rc;
+    if (m->kind == FQG_NAMES) {      // the spans are header lines (without '@'), not sequences
+        NamesView nv;
+        if ((rc = get_names_view(c, m, &nv))) return rc;
+        CU_TRY(launch_match_names_soa(nv, b, c->sm_count, stream));
+        count_launches(1);
+        return FQG_OK;
+    }
+    if (m->split_lit) {
+        // pass 1: literal members -> "found" bits in mask_out; pass 2: regex members, OR those bits in before invert
+        DeviceDfa d1, d2;
+        if ((rc = get_device_dfa(c, m->split_lit.get(), &d1)) || (rc = get_device_dfa(c, m->split_rest.get(), &d2))) return rc;
+        SoaBatch b1 = b;
+        b1.or_mask = nullptr; b1.count = nullptr; b1.invert = 0u; b1.pre_or_mask = nullptr;
+        CU_TRY(launch_match_soa(d1, b1, c->sm_count, stream));
+        SoaBatch b2 = b;
+        b2.pre_or_mask = b.mask_out;
+        CU_TRY(launch_match_soa(d2, b2, c->sm_count, stream));
+        count_launches(2);
+        return FQG_OK;
+    }
+    CU_TRY(launch_match_soa(dd, b, c->sm_count, stream));
+    count_launches(1);
+    return FQG_OK;
+}
+
 }  // namespace fqg
 
 extern "C" {
@@ -376,35 +406,9 @@ int fqg_match_bases_device(fqg_ctx* c, const fqg_matcher* m, const uint8_t* d_ba
     if (n_reads >= (1ull << 32)) return fail(FQG_E_TOO_LARGE, "more than 2^32-1 reads in one call; split the batch");
     if (n_reads == 0) return FQG_OK;
     CU_TRY(cudaSetDevice(c->device));
-    DeviceDfa dd;
-    int rc = get_device_dfa(c, m, &dd);
-    if (rc) return rc;
-    if (m->kind == FQG_NAMES) {      // the spans are header lines (without '@'), not sequences
-        NamesView nv;
-        if ((rc = get_names_view(c, m, &nv))) return rc;
-        SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
-                   (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr};
-        CU_TRY(launch_match_names_soa(nv, b, c->sm_count, (cudaStream_t)stream));
-        count_launches(1);
-        return FQG_OK;
-    }
-    if (m->split_lit) {
-        // pass 1: literal members -> "found" bits in d_mask_out; pass 2: regex members, OR those bits in before invert
-        DeviceDfa d1, d2;
-        if ((rc = get_device_dfa(c, m->split_lit.get(), &d1)) || (rc = get_device_dfa(c, m->split_rest.get(), &d2))) return rc;
-        SoaBatch b1{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, nullptr, nullptr, 0u, avg_read_len, nullptr};
-        CU_TRY(launch_match_soa(d1, b1, c->sm_count, (cudaStream_t)stream));
-        SoaBatch b2{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
-                    (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, d_mask_out};
-        CU_TRY(launch_match_soa(d2, b2, c->sm_count, (cudaStream_t)stream));
-        count_launches(2);
-        return FQG_OK;
-    }
     SoaBatch b{d_bases, d_start, d_end, (uint32_t)n_reads, d_mask_out, d_or_mask, reinterpret_cast<unsigned long long*>(d_count),
-               (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr};
-    CU_TRY(launch_match_soa(dd, b, c->sm_count, (cudaStream_t)stream));
-    count_launches(1);
-    return FQG_OK;
+               (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, avg_read_len, nullptr, nullptr};
+    return match_soa_any(c, m, b, (cudaStream_t)stream);
 }
 
 int fqg_match_bases_host(fqg_ctx* c, const fqg_matcher* m, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads, uint32_t* mask_out,

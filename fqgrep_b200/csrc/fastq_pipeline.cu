@@ -20,7 +20,7 @@ namespace fqg {
 
 namespace {
 enum { D_BUF0 = 0, D_BUF1, D_STATE0, D_STATE1, D_COUNTERS0, D_COUNTERS1, D_MASK0, D_MASK1, D_IDH0, D_IDH1, D_RECOFF0, D_RECOFF1, D_RECLEN0, D_RECLEN1,
-       D_CTL, D_UNITS, D_SPANS, D_SCAN, D_STATS, D_N };
+       D_CTL, D_UNITS, D_SPANS, D_SCAN, D_STATS, D_SEQSTART0, D_SEQSTART1, D_SEQLEN0, D_SEQLEN1, D_BASES0, D_BASES1, D_OFFS0, D_OFFS1, D_CSCAN0, D_CSCAN1, D_N };
 enum { H_CTL = 0, H_MASK, H_SPANS, H_N };
 constexpr size_t kCopyChunk = 32ull << 20;
 constexpr uint32_t kMaxLaunches = 1u << 12;
@@ -36,6 +36,12 @@ struct StreamPlan {
     unsigned long long* idh = nullptr;
     unsigned long long* rec_off = nullptr;
     uint32_t* rec_len = nullptr;
+    unsigned long long* seq_start = nullptr;     // record index (K0): the caller's arrays, or lane scratch when the batch is routed through the SoA kernels
+    uint32_t* seq_len = nullptr;
+    uint64_t seq_cap = 0;
+    uint8_t* soa_bases = nullptr;                // routed batches: compacted sequence lines + offsets
+    uint32_t* soa_offs = nullptr;
+    uint32_t* cscan = nullptr;
     uint64_t mask_bits = 0, idh_cap = 0, mask_words = 0;
     size_t copied = 0;
     uint32_t tiles_done = 0, launches = 0;
@@ -157,6 +163,12 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
     const int n_streams = mode == FQG_PAIRED ? 2 : 1;
     const bool check_ids = mode != FQG_SINGLE;
     const bool on_device = in.on_device;
+    // Large literal sets (tier 3: q-gram filter, tier 5: split sets) have no table the fused kernel could walk out of shared
+    // memory -- their exact automaton lives in L2 and walking it per base runs at 0.04 of the roofline (profiles/r2c_*).  Such
+    // batches are ROUTED: the fused kernel only parses, validates and indexes (K0), the sequence lines are compacted into
+    // SoA form and the SoA kernel with the filter decides (src/lib/matcher.rs:249-251 for every record, as before).
+    bool route = m && !names && (m->tier == 3 || m->split_lit);
+    for (int i = 0; i < n_streams; i++) if (in.n[i] >= 0xFFF00000ull) route = false;      // u32 offsets of the compacted bases
     if (on_device)
         for (int i = 0; i < n_streams; i++)
             if (reinterpret_cast<uintptr_t>(in.r[i]) & 15u) return fail(FQG_E_INVALID_ARG, "device FASTQ buffers must be 16-byte aligned");
@@ -226,6 +238,20 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
             if ((rc = L->dev_ensure(D_IDH0 + i, s.idh_cap * 8 + 16, &p))) return rc;
             s.idh = (unsigned long long*)p;
         }
+        if (in.idx && i == 0) { s.seq_start = in.idx->seq_start; s.seq_len = in.idx->seq_len; s.seq_cap = in.idx->cap; }
+        if (route) {
+            if ((rc = L->dev_ensure(D_SEQSTART0 + i, s.mask_bits * 8 + 16, &p))) return rc;
+            s.seq_start = (unsigned long long*)p;
+            if ((rc = L->dev_ensure(D_SEQLEN0 + i, s.mask_bits * 4 + 16, &p))) return rc;
+            s.seq_len = (uint32_t*)p;
+            s.seq_cap = s.mask_bits;
+            if ((rc = L->dev_ensure(D_BASES0 + i, n + 64, &p))) return rc;
+            s.soa_bases = (uint8_t*)p;
+            if ((rc = L->dev_ensure(D_OFFS0 + i, (s.mask_bits + 2) * 4, &p))) return rc;
+            s.soa_offs = (uint32_t*)p;
+            if ((rc = L->dev_ensure(D_CSCAN0 + i, compact_scratch_words(s.mask_bits) * 4, &p))) return rc;
+            s.cscan = (uint32_t*)p;
+        }
         if (in.want_spans) {
             if ((rc = L->dev_ensure(D_RECOFF0 + i, s.mask_bits * 8 + 16, &p))) return rc;
             s.rec_off = (unsigned long long*)p;
@@ -271,14 +297,14 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         a.tile_first = s.tiles_done; a.tile_count = tile_end - s.tiles_done;
         a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_acc = s.state + s.tiles + 1; a.seg_pre = a.seg_acc + s.tiles / 32 + 2; a.lines_out = ctl + 3 + i;
         a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
-        a.count = mode == FQG_SINGLE ? ctl + 1 : nullptr;
+        a.count = (mode == FQG_SINGLE && !route) ? ctl + 1 : nullptr;
         a.err = ctl + 0;
         a.invert = (m && (m->opts & FQG_INVERT_MATCH)) ? 1u : 0u;
         a.names = nv;
-        if (in.idx && i == 0) { a.seq_start = in.idx->seq_start; a.seq_len = in.idx->seq_len; a.span_cap = in.idx->cap; }
+        a.seq_start = s.seq_start; a.seq_len = s.seq_len; a.span_cap = s.seq_cap;
         a.rec_off = s.rec_off; a.rec_len = s.rec_len; a.rec_cap = s.rec_off ? s.mask_bits : 0;
         a.stats = d_stats;
-        CU_TRY(launch_match_fastq(dd, names, m == nullptr, a, c->sm_count, cs));
+        CU_TRY(launch_match_fastq(dd, names, m == nullptr || route, a, c->sm_count, cs));
         count_launches(1);
         s.launches++;
         s.tiles_done = tile_end;
@@ -314,6 +340,18 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         for (int i = 0; i < n_streams; i++) if ((rc = launch(i, sp[i].tiles))) return rc;   // empty streams / leftovers
     }
 
+    if (route) {
+        // every record of stream i is indexed by now: its sequence lines -> SoA, the SoA kernel(s) -> the stream's record mask
+        for (int i = 0; i < n_streams; i++) {
+            StreamPlan& s = sp[i];
+            if (s.tiles == 0) continue;
+            CU_TRY(launch_compact_bases(s.d, s.seq_start, s.seq_len, s.mask_bits, s.soa_bases, s.soa_offs, s.cscan, cs, ctl + 3 + i));
+            count_launches(4);
+            SoaBatch b{s.soa_bases, s.soa_offs, s.soa_offs + 1, (uint32_t)(s.mask_bits < 0xFFFFFFFFull ? s.mask_bits : 0xFFFFFFFFull), s.mask, nullptr,
+                       mode == FQG_SINGLE ? ctl + 1 : nullptr, (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, 0u, nullptr, ctl + 3 + i};
+            if ((rc = match_soa_any(c, m, b, cs))) return rc;
+        }
+    }
     // ---- mates -> units (src/main.rs:749-755), id agreement (:741-747)
     L->unit_mask_dev = sp[0].mask;
     uint64_t unit_words_upper = sp[0].mask_words;

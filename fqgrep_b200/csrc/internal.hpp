@@ -80,6 +80,7 @@ namespace fqg {
 int ensure_dev(fqg_ctx* c, int slot, size_t bytes, void** out);
 int get_device_dfa(fqg_ctx* c, const fqg_matcher* m, DeviceDfa* out);
 int get_names_view(fqg_ctx* c, const fqg_matcher* m, NamesView* out);
+int match_soa_any(fqg_ctx* c, const fqg_matcher* m, SoaBatch b, cudaStream_t stream);
 
 // ---- one FASTQ batch through the fused kernel (fastq_pipeline.cu) --------------------------------------------------------
 struct IndexOut {                    // K0: optional per-record index of stream 1 (device arrays owned by the caller)

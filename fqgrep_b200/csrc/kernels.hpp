@@ -55,6 +55,9 @@ struct SoaBatch {
     uint32_t invert;
     uint32_t avg_read_len;
     const uint32_t* pre_or_mask;   // optional: "pattern found" bits of another matcher, OR-ed in BEFORE invert_match is applied
+    // optional: the read count is only known on the device (the FASTQ indexer's line count, 4 lines per read); n_reads is
+    // then the capacity the launch is sized for and the kernel stops at min(n_reads, *lines_dev / 4)
+    const unsigned long long* lines_dev;
 };
 
 // K3/K2/K1: per-read DFA walk over SoA reads (bases + start/end), bitmask + count epilogue (K5 fused).
@@ -107,8 +110,10 @@ uint32_t fastq_overlap_bytes();
 // names: read-name lookup instead of an automaton; index_only: no matching at all, only parse / validate / index (K0)
 cudaError_t launch_match_fastq(const DeviceDfa& dfa, bool names, bool index_only, const FastqArgs& a, int sm_count, cudaStream_t stream);
 // K0 part 2: gather the indexed sequence lines into one contiguous SoA buffer with u32 offsets[n+1]
+// lines_dev (optional): device line count of the stream; the record count is then min(n_records, *lines_dev / 4)
 cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n_records,
-                                 uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream);
+                                 uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream,
+                                 const unsigned long long* lines_dev = nullptr);
 uint64_t compact_scratch_words(uint64_t n_records);
 cudaError_t launch_combine_pairs(const uint32_t* m1, const uint32_t* m2, uint32_t* out, uint64_t cap_words, const unsigned long long* h1, const unsigned long long* h2,
                                  uint64_t idh_cap, const unsigned long long* lines1, const unsigned long long* lines2, unsigned long long* count,

@@ -76,6 +76,14 @@ __device__ __forceinline__ uint32_t lds_u16_volatile(uint32_t a) {
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
+// atomicAdd whose result is NOT consumed on the spot: the compiler turns a one-lane atomicAdd() into its warp-aggregated
+// form and shuffles the result out immediately, i.e. waits for the round trip right there (3.6 % of all stall samples on the
+// tile claim, profiles/r2g_*); written as PTX the value is only waited for where it is used.
+__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
+}
 // store only where `on` is non-zero -- as a PREDICATED store, not a branch around one
 __device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, uint32_t on) {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n}" ::"r"(a), "h"((unsigned short)v), "r"(on) : "memory");
@@ -267,13 +275,15 @@ __device__ __noinline__ unsigned long long lookback_resolve(Lookback lb, uint32_
             acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
         }
     };
-    // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix
+    // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix: the counts in
+    // front of it fit 32 bits each and together (32 x 2^48 at most would not, but a segment holds at most 32 x 10752
+    // newlines and a tile 10752), so they go through one warp reduction; the prefix itself is one 64-bit shuffle
     auto fold = [&](unsigned long long st, bool use, bool& hit_prefix) {
         const uint32_t has_prefix = __ballot_sync(kFullMask, use && (st >> 62) == 2);
         const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
-        unsigned long long v = (use && lane <= first) ? (st & kValue) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+        const uint32_t counts = __reduce_add_sync(kFullMask, (use && lane < first) ? (uint32_t)st : 0u);
+        unsigned long long v = counts;
+        if (has_prefix) v += __shfl_sync(kFullMask, st, first) & kValue;
         hit_prefix = has_prefix != 0;
         return v;
     };
@@ -595,7 +605,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         c.total = total;
         lookback_publish(lb, g.t, agg, lane);
         auto claim_next = [&]() {      // warp-uniform; the result is picked up at the bottom of the loop
-            if (!claimed && lane == 0) next_claim = atomicAdd(a.tile_counter, 1u);
+            if (!claimed && lane == 0) next_claim = atom_add_u32(a.tile_counter, 1u);
             claimed = true;
         };
         const LookbackPre no_pre{0ull, 0ull, 0ull};
@@ -828,8 +838,14 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     *total = tot;
     return base + incl - v;
 }
-__global__ void scan_block_sums_kernel(const uint32_t* len, uint64_t n, uint32_t* block_sums) {
+__device__ __forceinline__ uint64_t records_on_device(uint64_t cap, const unsigned long long* lines_dev) {
+    if (!lines_dev) return cap;
+    const uint64_t n = *lines_dev >> 2;
+    return n < cap ? n : cap;
+}
+__global__ void scan_block_sums_kernel(const uint32_t* len, uint64_t n, uint32_t* block_sums, const unsigned long long* lines_dev) {
     __shared__ uint32_t s_w[kScanBlock / 32];
+    n = records_on_device(n, lines_dev);
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     uint32_t v = 0;
     for (uint32_t i = 0; i < kScanItems; i++) if (base + i < n) v += len[base + i];
@@ -850,8 +866,9 @@ __global__ void scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks) {     
     }
     if (threadIdx.x == 0) block_sums[n_blocks] = carry;
 }
-__global__ void scan_offsets_kernel(const uint32_t* len, uint64_t n, const uint32_t* block_sums, uint32_t* offsets) {
+__global__ void scan_offsets_kernel(const uint32_t* len, uint64_t n, const uint32_t* block_sums, uint32_t* offsets, const unsigned long long* lines_dev) {
     __shared__ uint32_t s_w[kScanBlock / 32];
+    n = records_on_device(n, lines_dev);
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     uint32_t item[kScanItems], v = 0;
     for (uint32_t i = 0; i < kScanItems; i++) { item[i] = base + i < n ? len[base + i] : 0u; v += item[i]; }
@@ -861,11 +878,12 @@ __global__ void scan_offsets_kernel(const uint32_t* len, uint64_t n, const uint3
         if (base + i < n) offsets[base + i] = run;
         run += item[i];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanBlock - 1) offsets[n] = block_sums[gridDim.x];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanBlock - 1) offsets[n] = block_sums[gridDim.x];      // blocks past a device-side n add nothing
 }
 // one warp per record: contiguous byte copy of its sequence line
 __global__ void gather_bases_kernel(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n,
-                                    const uint32_t* offsets, uint8_t* out) {
+                                    const uint32_t* offsets, uint8_t* out, const unsigned long long* lines_dev) {
+    n = records_on_device(n, lines_dev);
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n; r += warps) {
@@ -948,13 +966,13 @@ cudaError_t launch_select_spans(const uint32_t* unit_mask, uint64_t mask_words, 
 }
 
 cudaError_t launch_compact_bases(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n_records,
-                                 uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream) {
+                                 uint8_t* bases_out, uint32_t* offsets_out, uint32_t* block_sums, cudaStream_t stream, const unsigned long long* lines_dev) {
     if (n_records == 0) return cudaMemsetAsync(offsets_out, 0, 4, stream);
     const uint32_t n_blocks = (uint32_t)((n_records + kScanTile - 1) / kScanTile);
-    scan_block_sums_kernel<<<n_blocks, kScanBlock, 0, stream>>>(seq_len, n_records, block_sums);
+    scan_block_sums_kernel<<<n_blocks, kScanBlock, 0, stream>>>(seq_len, n_records, block_sums, lines_dev);
     scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(block_sums, n_blocks);
-    scan_offsets_kernel<<<n_blocks, kScanBlock, 0, stream>>>(seq_len, n_records, block_sums, offsets_out);
-    gather_bases_kernel<<<148 * 8, 256, 0, stream>>>(fastq, seq_start, seq_len, n_records, offsets_out, bases_out);
+    scan_offsets_kernel<<<n_blocks, kScanBlock, 0, stream>>>(seq_len, n_records, block_sums, offsets_out, lines_dev);
+    gather_bases_kernel<<<148 * 8, 256, 0, stream>>>(fastq, seq_start, seq_len, n_records, offsets_out, bases_out, lines_dev);
     return cudaGetLastError();
 }
 

@@ -280,6 +280,10 @@ template <int TIER>
 __global__ void __launch_bounds__(1024, 1)
 match_soa_kernel(SoaBatch b, DeviceDfa dfa, uint32_t slot_bytes, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (b.lines_dev) {      // read count known on the device only (FASTQ indexer): b.n_reads was the capacity
+        const unsigned long long n = *b.lines_dev >> 2;
+        if (n < b.n_reads) b.n_reads = (uint32_t)n;
+    }
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     // ---- smem carve-up: [table][class LUT 256][mbarriers][slots]
