@@ -88,8 +88,8 @@ class Matcher:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            _ffi.lib().fqg_matcher_free(h)
+        if h and _ffi is not None and getattr(_ffi, "_lib", None) is not None:      # (module globals are gone at interpreter shutdown)
+            _ffi._lib.fqg_matcher_free(h)
             self._h = None
 
     def opts(self):
