@@ -116,10 +116,8 @@ int get_device_dfa(fqg_ctx* c, const fqg_matcher* cm, DeviceDfa* out) {
         DeviceTables t;
         if (m->kind == FQG_NAMES) {
             CU_TRY(cudaMalloc(&t.slots, m->names.slots.size() * 8));
-            CU_TRY(cudaMalloc(&t.slot_off, m->names.slot_off.size() * 4));
             CU_TRY(cudaMalloc(&t.pool, m->names.pool.size()));
             CU_TRY(cudaMemcpy(t.slots, m->names.slots.data(), m->names.slots.size() * 8, cudaMemcpyHostToDevice));
-            CU_TRY(cudaMemcpy(t.slot_off, m->names.slot_off.data(), m->names.slot_off.size() * 4, cudaMemcpyHostToDevice));
             CU_TRY(cudaMemcpy(t.pool, m->names.pool.data(), m->names.pool.size(), cudaMemcpyHostToDevice));
         } else {
             const void* src = (m->tier == 2 || m->tier == 3) ? (const void*)m->t32.data() : (const void*)m->t16.data();
@@ -178,7 +176,7 @@ int get_names_view(fqg_ctx* c, const fqg_matcher* cm, NamesView* out) {
     fqg_matcher* m = const_cast<fqg_matcher*>(cm);
     std::lock_guard<std::mutex> lock(m->mu);
     const DeviceTables& t = m->dev[c->device];
-    out->slots = t.slots; out->slot_off = t.slot_off; out->pool = t.pool; out->mask = m->names.n_slots / 4 - 1;
+    out->slots = t.slots; out->pool = t.pool; out->mask = m->names.n_slots / 4 - 1;
     return 0;
 }
 
@@ -327,7 +325,6 @@ void fqg_matcher_free(fqg_matcher* m) {
         cudaFree(kv.second.table);
         cudaFree(kv.second.byte_class);
         cudaFree(kv.second.slots);
-        cudaFree(kv.second.slot_off);
         cudaFree(kv.second.pool);
         cudaFree(kv.second.g_bitmap); cudaFree(kv.second.g_kv); cudaFree(kv.second.g_pool);
         cudaSetDevice(prev);

@@ -75,9 +75,8 @@ std::string validate_fixed_pattern(const std::string& pattern, bool protein);
 // Read-name set -> open-addressing table (replaces AHashSet<Vec<u8>>, matcher.rs:604,632).
 struct NameTable {
     uint32_t n_slots = 0;                 // power of two
-    std::vector<uint64_t> slots;          // 0 = empty; else (hash48 << 16 | len16) packed with pool offset, see names.cc
-    std::vector<uint32_t> slot_off;       // offset of the name in pool
-    std::vector<uint8_t> pool;            // concatenated names
+    std::vector<uint64_t> slots;          // 0 = empty; else tag << 32 | offset of the name's pool entry (names_hash.h)
+    std::vector<uint8_t> pool;            // entries on 16-byte boundaries: u32 length, then the bytes, zero-padded
     uint32_t max_len = 0;
 };
 uint64_t name_hash(const uint8_t* p, size_t n);

@@ -33,7 +33,6 @@ struct DeviceTables {
     uint8_t* g_pool = nullptr;
     // names
     uint64_t* slots = nullptr;
-    uint32_t* slot_off = nullptr;
     uint8_t* pool = nullptr;
 };
 

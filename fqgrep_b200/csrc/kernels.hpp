@@ -66,7 +66,6 @@ cudaError_t launch_match_soa(const DeviceDfa& dfa, const SoaBatch& b, int sm_cou
 // ---- fused raw-FASTQ parse + match (match_fastq.cu)
 struct NamesView {
     const uint64_t* slots = nullptr;
-    const uint32_t* slot_off = nullptr;
     const uint8_t* pool = nullptr;
     uint32_t mask = 0;     // n_buckets - 1 (a bucket = four consecutive slots = 32 bytes)
 };

@@ -106,12 +106,29 @@ __device__ __forceinline__ uint32_t newline_mask8x128(uint32_t w0, uint32_t w1, 
     return __dp4a(newline_flags(w1, c0a, c7f), 0x80402010u, a);
 }
 
+// A read-name lookup in flight: the hash is known and the home bucket has been asked for.  Keeping the two halves apart
+// lets the fused kernel resolve its look-back and claim its next tile while the buckets of the 32 records travel.
+struct NamePending {
+    unsigned long long h = 0;
+    ulonglong4 bucket{0, 0, 0, 0};
+    uint32_t id_sa = 0, id_len = 0;      // the id in the staged tile (shared address)
+    bool active = false;
+};
 struct NamesProbe {
     NamesView nv;
-    // exact membership of id bytes [p, p+len) in the name set; p is a shared-window address / a global pointer
-    __device__ bool contains_shared(uint32_t p, uint32_t len) const {
-        return names_contains(nv, p, len, [](uint32_t a) { return lds_u32_volatile(a); });
+    __device__ __forceinline__ NamePending start_shared(uint32_t p, uint32_t len) const {
+        NamePending np;
+        np.h = names_hash_id(p, len, [](uint32_t a) { return lds_u32_volatile(a); });
+        np.bucket = names_load_bucket(nv, np.h);
+        np.id_sa = p;
+        np.id_len = len;
+        np.active = true;
+        return np;
     }
+    __device__ __forceinline__ bool finish_shared(const NamePending& np) const {
+        return names_probe_from(nv, np.id_sa, np.id_len, [](uint32_t a) { return lds_u32_volatile(a); }, np.h, np.bucket);
+    }
+    // exact membership of id bytes [p, p+len) in the name set (records walked in global memory)
     __device__ bool contains_global(const uint8_t* p, uint32_t len) const {
         return names_contains(nv, reinterpret_cast<uintptr_t>(p), len, [](uintptr_t a) { return __ldg(reinterpret_cast<const uint32_t*>(a)); });
     }
@@ -144,7 +161,8 @@ struct RecordEval {
     bool invert;
 
     // record fully in shared memory: s = '@' position, p0 = end of the header line (positions in the tile at shared address `tile`)
-    __device__ __forceinline__ bool eval_shared(uint32_t tile, uint32_t s, uint32_t p0, uint32_t seq_len, unsigned long long* idh, bool want_idh) const {
+    __device__ __forceinline__ bool eval_shared(uint32_t tile, uint32_t s, uint32_t p0, uint32_t seq_len, unsigned long long* idh, bool want_idh,
+                                                NamePending* pending) const {
         uint32_t head_end = p0;
         if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
         uint32_t id_len = 0;
@@ -176,7 +194,7 @@ struct RecordEval {
         }
         bool found;
         if (TIER == 5) found = false;
-        else if (TIER == 3) found = names.contains_shared(tile + s + 1, id_len);
+        else if (TIER == 3) { *pending = names.start_shared(tile + s + 1, id_len); return false; }      // decided by finish_names
         else found = walk_shared(view, tile + p0 + 1, seq_len, start) >= accept_from;
         return found != invert;
     }
@@ -342,6 +360,7 @@ __device__ __forceinline__ void stage_automaton(const DeviceDfa& dfa, uint8_t* s
 // record phase may run under a GUESSED line phase (see the kernel), so outputs -- mask bit, id hash, spans, errors -- are
 // committed only once the look-back has confirmed the guess.
 struct RecOut {
+    NamePending name;                    // TIER 3 only
     bool sel = false;
     uint32_t err = 0;                    // 0 or one of kErr*
     unsigned long long err_pos = 0;
@@ -382,7 +401,7 @@ __device__ __forceinline__ RecOut eval_record(const FastqArgs& a, const RecordEv
             o.rec_n = p3 - s + (virt ? 0u : 1u);
         }
         unsigned long long idh = 0;
-        o.sel = ev.eval_shared(tile_sa, s, p0, seq_len, &idh, c.want_idh);
+        o.sel = ev.eval_shared(tile_sa, s, p0, seq_len, &idh, c.want_idh, &o.name);
         o.idh = idh;
     } else {
         // record runs past tile+overlap (or the stream is truncated): walk it in global memory
@@ -416,6 +435,12 @@ __device__ __forceinline__ RecOut eval_record(const FastqArgs& a, const RecordEv
         }
     }
     return o;
+}
+
+// second half of a read-name lookup (see NamePending)
+template <int TIER>
+__device__ __forceinline__ void finish_names(const RecordEval<TIER>& ev, RecOut& o) {
+    if (TIER == 3 && o.name.active) o.sel = ev.names.finish_shared(o.name) != ev.invert;
 }
 
 // Writes what 32 lanes found out about records R_w .. R_w + 31 (lane i: record R_w + i, `valid` lanes only); returns the number selected.
@@ -487,6 +512,7 @@ __device__ __noinline__ uint32_t dense_tile(const FastqArgs& a, const RecordEval
             if (valid) {
                 const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(c.list_sa + 2u * (qa - win_lo)) + 1u;
                 o = eval_record<TIER>(a, ev, c, s, r0, win_lo);
+                finish_names<TIER>(ev, o);
             }
             selected += commit_records(a, c, o, valid, ph.R_base + k0, lane);
         }
@@ -704,6 +730,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
                     }
                     claim_next();      // nothing below waits for another tile
+                    finish_names<TIER>(ev, o);
                     local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
                 }
                 if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed

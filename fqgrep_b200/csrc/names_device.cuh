@@ -37,28 +37,47 @@ __device__ __forceinline__ uint64_t names_hash_id(A a, uint32_t len, Load load) 
     for (IdWords<A, Load> it(a, len, load); it.more();) h = fqg_name_hash_word(h, it.next());
     return fqg_name_hash_finish(h, len);
 }
+__device__ __forceinline__ ulonglong4 names_load_bucket(const NamesView& nv, uint64_t h) {      // (as two 16-byte reads of one sector)
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nv.slots) + 2u * (size_t)fqg_name_bucket(h, nv.mask);
+    const ulonglong2 s01 = __ldg(p), s23 = __ldg(p + 1);
+    return ulonglong4{s01.x, s01.y, s23.x, s23.y};
+}
 // The table is an array of 32-byte buckets of four slot words (one L2 sector per probe); a bucket is filled front to
-// back and overflows into the next one, so an empty slot ends the search.
+// back and overflows into the next one, so an empty slot ends the search.  `first` is the already loaded home bucket.
 template <class A, class Load>
-__device__ __forceinline__ bool names_probe(const NamesView& nv, A a, uint32_t len, Load load, uint64_t h) {
-    const uint64_t want = fqg_slot_word(h, len);
-    uint32_t bkt = (uint32_t)(h >> 32) & nv.mask;
+__device__ __forceinline__ bool names_probe_from(const NamesView& nv, A a, uint32_t len, Load load, uint64_t h, ulonglong4 first) {
+    const uint32_t tag = fqg_name_tag(h);
+    uint32_t bkt = fqg_name_bucket(h, nv.mask);
+    ulonglong4 b = first;
     for (;;) {
-        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nv.slots) + 2u * (size_t)bkt;
-        const ulonglong2 s01 = __ldg(p), s23 = __ldg(p + 1);
-        const uint64_t sl[4] = {s01.x, s01.y, s23.x, s23.y};
+        const uint64_t sl[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (uint32_t k = 0; k < 4; k++) {
             if (sl[k] == 0) return false;
-            if (sl[k] == want) {      // 40 hash bits + the length agree: confirm on the bytes (pool entries are word-aligned, zero-padded)
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(nv.pool + __ldg(nv.slot_off + 4u * (size_t)bkt + k));
-                uint32_t diff = 0;
-                for (IdWords<A, Load> it(a, len, load); it.more() && !diff;) diff = it.next() ^ __ldg(q++);
-                if (!diff) return true;
+            if ((uint32_t)(sl[k] >> 32) == tag) {      // confirm on length and bytes: one 16-byte read covers ids of up to 12 bytes
+                const uint4* q = reinterpret_cast<const uint4*>(nv.pool + (uint32_t)sl[k]);
+                const uint4 e = __ldg(q);
+                if (e.x == len) {
+                    IdWords<A, Load> it(a, len, load);
+                    uint32_t diff = 0;
+                    if (it.more()) diff |= it.next() ^ e.y;
+                    if (it.more()) diff |= it.next() ^ e.z;
+                    if (it.more()) diff |= it.next() ^ e.w;
+                    const uint32_t* rest = reinterpret_cast<const uint32_t*>(q + 1);
+                    while (it.more() && !diff) diff = it.next() ^ __ldg(rest++);
+                    if (!diff) return true;
+                }
             }
         }
         bkt = (bkt + 1u) & nv.mask;
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nv.slots) + 2u * (size_t)bkt;
+        const ulonglong2 s01 = __ldg(p), s23 = __ldg(p + 1);
+        b = ulonglong4{s01.x, s01.y, s23.x, s23.y};
     }
+}
+template <class A, class Load>
+__device__ __forceinline__ bool names_probe(const NamesView& nv, A a, uint32_t len, Load load, uint64_t h) {
+    return names_probe_from(nv, a, len, load, h, names_load_bucket(nv, h));
 }
 template <class A, class Load>
 __device__ __forceinline__ bool names_contains(const NamesView& nv, A a, uint32_t len, Load load) {

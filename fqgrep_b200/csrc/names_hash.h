@@ -29,5 +29,9 @@ FQG_HD uint64_t fqg_name_hash(const uint8_t* p, uint32_t n) {
     }
     return fqg_name_hash_finish(h, n);
 }
-// names longer than 2^24-1 bytes are rejected at construction
-FQG_HD uint64_t fqg_slot_word(uint64_t h, uint32_t len) { return ((h | (1ull << 63)) & 0xFFFFFFFFFF000000ull) | (len & 0xFFFFFFu); }
+// The table: 32-byte buckets of four 8-byte slots, slot = tag << 32 | offset of the name's pool entry, 0 = empty.
+// bucket = high half of the hash, tag = low half (never 0).  A pool entry sits on a 16-byte boundary:
+// [u32 length][bytes, zero-padded to a multiple of four and to at least 12], so ids of up to 12 bytes are confirmed
+// with ONE 16-byte read.  names longer than 2^24-1 bytes are rejected at construction.
+FQG_HD uint32_t fqg_name_bucket(uint64_t h, uint32_t mask) { return (uint32_t)(h >> 32) & mask; }
+FQG_HD uint32_t fqg_name_tag(uint64_t h) { return (uint32_t)h | 1u; }

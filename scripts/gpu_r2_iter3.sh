@@ -2,7 +2,7 @@
 # smoke + FASTQ-path tests + full bench line + ncu of the fused kernel (DFA and names)
 TAG=${1:-r2}
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1 || { echo "SMOKE FAILED"; tail -30 gpurun_out/smoke_$TAG.log; exit 1; }
-timeout 900 python -m pytest tests/test_gpu_fastq.py tests/test_gpu_stream.py -m gpu -q --timeout 600 -x > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_$TAG.log
+timeout 900 python -m pytest tests/test_gpu_fastq.py tests/test_gpu_stream.py tests/test_gpu_parity.py -m gpu -q --timeout 600 -x > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_$TAG.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; tail -n 5 gpurun_out/bench_$TAG.err
 python - <<PY
 import json

@@ -178,7 +178,7 @@ def test_cli_streams_large_inputs_through_a_small_ring(tmp_path):
     assert code == 101 and "out of sync" in err
     # a record larger than a slot cannot be batched: a clear error, not a hang
     big = b"@big\n" + b"A" * (3 << 20) + b"\n+\n" + b"I" * (3 << 20) + b"\n"
-    open(str(tmp_path / "big.fq"), "wb").write(r1[:5000] + big)
+    open(str(tmp_path / "big.fq"), "wb").write(r1[: r1.index(b"@q40/")] + big)
     code, _, err = run("-c", *args, tmp_path / "big.fq")
     assert code == 2 and "--slot-mb" in err
     code, out, _ = run("-c", "-e", "A{100}", "--slot-mb", "16", tmp_path / "big.fq")

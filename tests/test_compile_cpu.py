@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
     rust = open(os.path.join(root, "rust", "fqgrep-b200", "src", "lib.rs")).read()
     assert not [n for n in declared if n not in rust]
     hpp = open(os.path.join(root, "include", "fqgrep_b200.hpp")).read()
-    for n in ("fqg_matcher_new", "fqg_grep_fastq_host", "fqg_match_bases_host", "fqg_write_selected", "fqg_read_input", "fqg_iupac_expand"):
+    for n in ("fqg_matcher_new", "fqg_grep_fastq_host", "fqg_match_bases_host", "fqg_stream_open", "fqg_stream_next", "fqg_fastq_cut", "fqg_write_spans",
+              "fqg_reader_open", "fqg_iupac_expand"):
         assert n in hpp
 
 
