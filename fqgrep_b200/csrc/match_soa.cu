@@ -448,11 +448,9 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
 // are contiguous, so its loads share cache lines); the table probe is one random 8-byte L2 read per read.
 // Algorithmic bytes per read: header + 4 (offset) + 8 (one slot) + 1/8 (result).
 namespace {
-// A thread takes kNamesPerThread reads (of consecutive 32-read batches) at a time and runs them in lock step, stage by stage:
-// all offset loads, then all header loads, then all bucket loads are in flight together before the first one is
-// consumed.  One read per thread is a chain of three dependent global loads and ran at 0.26 of the HBM figure with
-// long-scoreboard stalls of 10 per issue (profiles/r1zz_names_soa_ncu_full.txt): latency, not bandwidth.
-constexpr int kNamesPerThread = 4;
+// (Four reads per thread run stage by stage -- all offset loads, all header loads, all bucket loads in flight together -- was
+// built and measured in round 2: 46 Greads/s against 80 for this kernel, because its 73 registers left room for three
+// blocks per SM instead of eight; the loads in flight per SM went DOWN.  Removed.)
 __global__ void __launch_bounds__(256) match_names_soa_kernel(SoaBatch b, NamesView nv) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_batches = (b.n_reads + 31u) >> 5;
@@ -460,105 +458,36 @@ __global__ void __launch_bounds__(256) match_names_soa_kernel(SoaBatch b, NamesV
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.bases);
     auto load = [](uintptr_t p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); };
     unsigned long long local_count = 0;
-    for (uint32_t batch0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kNamesPerThread; batch0 < n_batches; batch0 += warps * kNamesPerThread) {
-        uint32_t s[kNamesPerThread], n[kNamesPerThread];
-        bool valid[kNamesPerThread];
-#pragma unroll
-        for (int k = 0; k < kNamesPerThread; k++) {
-            const uint32_t r = (batch0 + k) * 32u + lane;
-            valid[k] = batch0 + k < n_batches && r < b.n_reads;
-            s[k] = valid[k] ? __ldg(b.start + r) : 0u;
-            const uint32_t e = valid[k] ? __ldg(b.end + r) : 0u;
-            n[k] = e > s[k] ? e - s[k] : 0u;
-        }
-        // the first 16 header bytes of every read: five aligned words, realigned by funnel shifts
-        uint32_t w[kNamesPerThread][4];
-#pragma unroll
-        for (int k = 0; k < kNamesPerThread; k++) {
-            const uintptr_t a = base + s[k], wp = a & ~uintptr_t(3);
-            const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-            uint32_t x[5];
-#pragma unroll
-            for (int j = 0; j < 5; j++) x[j] = (valid[k] && 4u * j < n[k] + (sh >> 3)) ? load(wp + 4u * j) : 0u;
-#pragma unroll
-            for (int j = 0; j < 4; j++) w[k][j] = __funnelshift_r(x[j], x[j + 1], sh);
-        }
-        // id = header up to the first space; ids that end within those 16 bytes are hashed from registers
-        uint64_t h[kNamesPerThread];
-        uint32_t id_len[kNamesPerThread];
-#pragma unroll
-        for (int k = 0; k < kNamesPerThread; k++) {
-            uint64_t hh = fqg_name_hash_init();
-            uint32_t len = n[k] < 16u ? n[k] : 16u;
-            bool ended = n[k] <= 16u;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t have = len > 4u * j ? len - 4u * j : 0u;                 // header bytes in this word
-                uint32_t v = w[k][j];
-                if (have < 4u) v &= have ? (1u << (8u * have)) - 1u : 0u;
-                const uint32_t x = v ^ 0x20202020u;
-                uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where a byte is ' '
-                if (have < 4u) z &= have ? (1u << (8u * have)) - 1u : 0u;
-                if (z && !ended) {
-                    const uint32_t kk = ((uint32_t)__ffs((int)z) - 1u) >> 3;
-                    len = 4u * j + kk;
-                    ended = true;
+    for (uint32_t batch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; batch < n_batches; batch += warps) {
+        const uint32_t r = batch * 32u + lane;
+        bool found = false;
+        if (r < b.n_reads) {
+            const uint32_t s = __ldg(b.start + r), e = __ldg(b.end + r);
+            const uintptr_t a = base + s;
+            const uint32_t n = e > s ? e - s : 0u;
+            // one pass: hash the header word by word until a word holds a space, which ends the id
+            uint64_t h = fqg_name_hash_init();
+            uint32_t id_len = n;
+            for (IdWords<uintptr_t, decltype(load)> it(a, n, load); it.more();) {
+                const uint32_t pos = it.pos, w = it.next(), x = w ^ 0x20202020u;
+                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);      // 0x80 where a byte is ' '
+                if (z) {                                  // (the zero padding past the end is never a space)
+                    const uint32_t k = ((uint32_t)__ffs((int)z) - 1u) >> 3;
+                    id_len = pos + k;
+                    if (k) h = fqg_name_hash_word(h, w & ((1u << (8u * k)) - 1u));
+                    break;
                 }
-                w[k][j] = v;
+                h = fqg_name_hash_word(h, w);
             }
-            // words beyond the id are zero for the hash and for the byte compare
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t have = len > 4u * j ? len - 4u * j : 0u;
-                if (have < 4u) w[k][j] &= have ? (1u << (8u * have)) - 1u : 0u;
-                if (have) hh = fqg_name_hash_word(hh, w[k][j]);
-            }
-            id_len[k] = len;
-            h[k] = fqg_name_hash_finish(hh, len);
-            if (!ended && valid[k]) {      // an id longer than 16 bytes: the general word walk (same hash, same result)
-                const uintptr_t a = base + s[k];
-                uint64_t h2 = fqg_name_hash_init();
-                uint32_t l2 = n[k];
-                for (IdWords<uintptr_t, decltype(load)> it(a, n[k], load); it.more();) {
-                    const uint32_t pos = it.pos, ww = it.next(), x = ww ^ 0x20202020u;
-                    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-                    if (z) {                                  // (the zero padding past the end is never a space)
-                        const uint32_t kk = ((uint32_t)__ffs((int)z) - 1u) >> 3;
-                        l2 = pos + kk;
-                        if (kk) h2 = fqg_name_hash_word(h2, ww & ((1u << (8u * kk)) - 1u));
-                        break;
-                    }
-                    h2 = fqg_name_hash_word(h2, ww);
-                }
-                id_len[k] = l2;
-                h[k] = fqg_name_hash_finish(h2, l2);
-            }
+            h = fqg_name_hash_finish(h, id_len);
+            found = names_probe(nv, a, id_len, load, h);
         }
-        ulonglong4 bucket[kNamesPerThread];
-#pragma unroll
-        for (int k = 0; k < kNamesPerThread; k++) bucket[k] = valid[k] ? names_load_bucket(nv, h[k]) : ulonglong4{0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < kNamesPerThread; k++) {
-            bool found = false;
-            if (valid[k]) {
-                const uint32_t tag = fqg_name_tag(h[k]);
-                const uint64_t sl[4] = {bucket[k].x, bucket[k].y, bucket[k].z, bucket[k].w};
-                bool maybe = false, open_end = false;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (sl[j] == 0) open_end = true;
-                    if (!open_end && (uint32_t)(sl[j] >> 32) == tag) maybe = true;
-                }
-                // almost always decided here: no tag of the home bucket agrees and the bucket has a free slot
-                if (maybe || !open_end) found = names_probe_from(nv, base + s[k], id_len[k], load, h[k], bucket[k]);
-            }
-            const bool sel = valid[k] && (found != (b.invert != 0));
-            uint32_t m = __ballot_sync(kFullMask, sel);
-            if (lane == 0 && batch0 + k < n_batches) {
-                if (b.or_mask) m |= __ldg(b.or_mask + batch0 + k);
-                b.mask_out[batch0 + k] = m;
-                local_count += __popc(m);
-            }
+        const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
+        uint32_t m = __ballot_sync(kFullMask, sel);
+        if (lane == 0) {
+            if (b.or_mask) m |= __ldg(b.or_mask + batch);
+            b.mask_out[batch] = m;
+            local_count += __popc(m);
         }
     }
     if (lane == 0 && b.count && local_count) atomicAdd(b.count, local_count);
@@ -568,8 +497,8 @@ __global__ void __launch_bounds__(256) match_names_soa_kernel(SoaBatch b, NamesV
 cudaError_t launch_match_names_soa(const NamesView& nv, const SoaBatch& b, int sm_count, cudaStream_t stream) {
     const uint32_t n_batches = (b.n_reads + 31u) / 32u;
     if (!n_batches) return cudaSuccess;
-    uint32_t grid = (n_batches + 8u * kNamesPerThread - 1u) / (8u * kNamesPerThread);
-    const uint32_t cap = (uint32_t)sm_count * 8u * 2u;        // 8 resident CTAs of 256 threads per SM, 2 waves' worth of slack
+    uint32_t grid = (n_batches + 7u) / 8u;
+    const uint32_t cap = (uint32_t)sm_count * 8u * 4u;        // 8 resident CTAs of 256 threads per SM, 4 waves' worth of slack
     if (grid > cap) grid = cap;
     match_names_soa_kernel<<<grid, 256, 0, stream>>>(b, nv);
     return cudaGetLastError();

@@ -51,24 +51,31 @@ __device__ __forceinline__ bool names_probe_from(const NamesView& nv, A a, uint3
     ulonglong4 b = first;
     for (;;) {
         const uint64_t sl[4] = {b.x, b.y, b.z, b.w};
+        // which slots carry the tag (almost always none or one), and does the bucket end the search (an empty slot)?
+        uint32_t cand = 0;
+        bool open_end = false;
 #pragma unroll
         for (uint32_t k = 0; k < 4; k++) {
-            if (sl[k] == 0) return false;
-            if ((uint32_t)(sl[k] >> 32) == tag) {      // confirm on length and bytes: one 16-byte read covers ids of up to 12 bytes
-                const uint4* q = reinterpret_cast<const uint4*>(nv.pool + (uint32_t)sl[k]);
-                const uint4 e = __ldg(q);
-                if (e.x == len) {
-                    IdWords<A, Load> it(a, len, load);
-                    uint32_t diff = 0;
-                    if (it.more()) diff |= it.next() ^ e.y;
-                    if (it.more()) diff |= it.next() ^ e.z;
-                    if (it.more()) diff |= it.next() ^ e.w;
-                    const uint32_t* rest = reinterpret_cast<const uint32_t*>(q + 1);
-                    while (it.more() && !diff) diff = it.next() ^ __ldg(rest++);
-                    if (!diff) return true;
-                }
-            }
+            if (sl[k] == 0) open_end = true;
+            if (!open_end && (uint32_t)(sl[k] >> 32) == tag) cand |= 1u << k;
         }
+        while (cand) {      // confirm on length and bytes: one 16-byte read covers ids of up to 12 bytes
+            const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
+            cand &= cand - 1u;
+            const uint64_t slot = k == 0 ? sl[0] : k == 1 ? sl[1] : k == 2 ? sl[2] : sl[3];
+            const uint4* q = reinterpret_cast<const uint4*>(nv.pool + (uint32_t)slot);
+            const uint4 e = __ldg(q);
+            if (e.x != len) continue;
+            IdWords<A, Load> it(a, len, load);
+            uint32_t diff = 0;
+            if (it.more()) diff |= it.next() ^ e.y;
+            if (it.more()) diff |= it.next() ^ e.z;
+            if (it.more()) diff |= it.next() ^ e.w;
+            const uint32_t* rest = reinterpret_cast<const uint32_t*>(q + 1);
+            while (it.more() && !diff) diff = it.next() ^ __ldg(rest++);
+            if (!diff) return true;
+        }
+        if (open_end) return false;
         bkt = (bkt + 1u) & nv.mask;
         const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nv.slots) + 2u * (size_t)bkt;
         const ulonglong2 s01 = __ldg(p), s23 = __ldg(p + 1);
