@@ -20,7 +20,7 @@ namespace fqg {
 
 namespace {
 enum { D_BUF0 = 0, D_BUF1, D_STATE0, D_STATE1, D_COUNTERS0, D_COUNTERS1, D_MASK0, D_MASK1, D_IDH0, D_IDH1, D_RECOFF0, D_RECOFF1, D_RECLEN0, D_RECLEN1,
-       D_CTL, D_UNITS, D_SPANS, D_SCAN, D_STATS, D_SEQSTART0, D_SEQSTART1, D_SEQLEN0, D_SEQLEN1, D_BASES0, D_BASES1, D_OFFS0, D_OFFS1, D_CSCAN0, D_CSCAN1, D_N };
+       D_CTL, D_UNITS, D_SPANS, D_SCAN, D_STATS, D_SOASTART0, D_SOASTART1, D_SOAEND0, D_SOAEND1, D_N };
 enum { H_CTL = 0, H_MASK, H_SPANS, H_N };
 constexpr size_t kCopyChunk = 32ull << 20;
 constexpr uint32_t kMaxLaunches = 1u << 12;
@@ -39,9 +39,8 @@ struct StreamPlan {
     unsigned long long* seq_start = nullptr;     // record index (K0): the caller's arrays, or lane scratch when the batch is routed through the SoA kernels
     uint32_t* seq_len = nullptr;
     uint64_t seq_cap = 0;
-    uint8_t* soa_bases = nullptr;                // routed batches: compacted sequence lines + offsets
-    uint32_t* soa_offs = nullptr;
-    uint32_t* cscan = nullptr;
+    uint32_t *soa_start = nullptr, *soa_end = nullptr;      // routed batches: every record's sequence line as offsets into the stream itself
+    uint32_t record_bytes_est = 0;               // routed batches: typical record size (sizes the SoA kernel's staging slots)
     uint64_t mask_bits = 0, idh_cap = 0, mask_words = 0;
     size_t copied = 0;
     uint32_t tiles_done = 0, launches = 0;
@@ -240,17 +239,20 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         }
         if (in.idx && i == 0) { s.seq_start = in.idx->seq_start; s.seq_len = in.idx->seq_len; s.seq_cap = in.idx->cap; }
         if (route) {
-            if ((rc = L->dev_ensure(D_SEQSTART0 + i, s.mask_bits * 8 + 16, &p))) return rc;
-            s.seq_start = (unsigned long long*)p;
-            if ((rc = L->dev_ensure(D_SEQLEN0 + i, s.mask_bits * 4 + 16, &p))) return rc;
-            s.seq_len = (uint32_t*)p;
-            s.seq_cap = s.mask_bits;
-            if ((rc = L->dev_ensure(D_BASES0 + i, n + 64, &p))) return rc;
-            s.soa_bases = (uint8_t*)p;
-            if ((rc = L->dev_ensure(D_OFFS0 + i, (s.mask_bits + 2) * 4, &p))) return rc;
-            s.soa_offs = (uint32_t*)p;
-            if ((rc = L->dev_ensure(D_CSCAN0 + i, compact_scratch_words(s.mask_bits) * 4, &p))) return rc;
-            s.cscan = (uint32_t*)p;
+            if ((rc = L->dev_ensure(D_SOASTART0 + i, s.mask_bits * 4 + 16, &p))) return rc;
+            s.soa_start = (uint32_t*)p;
+            if ((rc = L->dev_ensure(D_SOAEND0 + i, s.mask_bits * 4 + 16, &p))) return rc;
+            s.soa_end = (uint32_t*)p;
+            // typical record size from the head of the stream (4 lines per record): the SoA kernel stages the span of 32
+            // consecutive records per warp; batches that turn out larger than the slot are walked in global memory
+            uint8_t head[16384];
+            const size_t k = n < sizeof head ? n : sizeof head;
+            if (on_device) CU_TRY(cudaMemcpy(head, s.src, k, cudaMemcpyDeviceToHost));
+            else std::memcpy(head, s.src, k);
+            size_t nl = 0;
+            for (size_t j = 0; j < k; j++) nl += head[j] == '\n';
+            const size_t est = nl >= 4 ? (4 * k + nl - 1) / nl : k;
+            s.record_bytes_est = (uint32_t)(est + est / 16 + 8);
         }
         if (in.want_spans) {
             if ((rc = L->dev_ensure(D_RECOFF0 + i, s.mask_bits * 8 + 16, &p))) return rc;
@@ -302,6 +304,8 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         a.invert = (m && (m->opts & FQG_INVERT_MATCH)) ? 1u : 0u;
         a.names = nv;
         a.seq_start = s.seq_start; a.seq_len = s.seq_len; a.span_cap = s.seq_cap;
+        a.soa_start = s.soa_start; a.soa_end = s.soa_end;
+        if (s.soa_start) a.span_cap = s.mask_bits;
         a.rec_off = s.rec_off; a.rec_len = s.rec_len; a.rec_cap = s.rec_off ? s.mask_bits : 0;
         a.stats = d_stats;
         CU_TRY(launch_match_fastq(dd, names, m == nullptr || route, a, c->sm_count, cs));
@@ -341,14 +345,13 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
     }
 
     if (route) {
-        // every record of stream i is indexed by now: its sequence lines -> SoA, the SoA kernel(s) -> the stream's record mask
+        // every record of stream i is indexed by now; the SoA kernel(s) read the sequence lines where they lie in the stream
+        // (bases = the stream, start / end = the index) and leave the stream's record mask
         for (int i = 0; i < n_streams; i++) {
             StreamPlan& s = sp[i];
             if (s.tiles == 0) continue;
-            CU_TRY(launch_compact_bases(s.d, s.seq_start, s.seq_len, s.mask_bits, s.soa_bases, s.soa_offs, s.cscan, cs, ctl + 3 + i));
-            count_launches(4);
-            SoaBatch b{s.soa_bases, s.soa_offs, s.soa_offs + 1, (uint32_t)(s.mask_bits < 0xFFFFFFFFull ? s.mask_bits : 0xFFFFFFFFull), s.mask, nullptr,
-                       mode == FQG_SINGLE ? ctl + 1 : nullptr, (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, 0u, nullptr, ctl + 3 + i};
+            SoaBatch b{s.d, s.soa_start, s.soa_end, (uint32_t)(s.mask_bits < 0xFFFFFFFFull ? s.mask_bits : 0xFFFFFFFFull), s.mask, nullptr,
+                       mode == FQG_SINGLE ? ctl + 1 : nullptr, (m->opts & FQG_INVERT_MATCH) ? 1u : 0u, s.record_bytes_est, nullptr, ctl + 3 + i};
             if ((rc = match_soa_any(c, m, b, cs))) return rc;
         }
     }

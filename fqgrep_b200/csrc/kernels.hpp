@@ -90,6 +90,10 @@ struct FastqArgs {
     unsigned long long* seq_start;  // optional record index (K0): stream offset of every record's sequence line ...
     uint32_t* seq_len;              // ... and its length without line terminator
     uint64_t span_cap;
+    // optional, for batches routed through the SoA kernels: the sequence line of record R is buf[soa_start[R], soa_end[R]),
+    // so the SoA kernel reads the lines where they lie (no compaction pass); capacity span_cap like seq_start
+    uint32_t* soa_start;
+    uint32_t* soa_end;
     // optional record spans (K5, write-back without re-parsing): stream offset of every record's '@' with bit 63 set when
     // the record is not already in seq_io's write_to form (CR line ends, "+name" separator, missing final newline), and
     // its length in bytes including the final newline when there is one

@@ -76,14 +76,6 @@ __device__ __forceinline__ uint32_t lds_u16_volatile(uint32_t a) {
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
-// atomicAdd whose result is NOT consumed on the spot: the compiler turns a one-lane atomicAdd() into its warp-aggregated
-// form and shuffles the result out immediately, i.e. waits for the round trip right there (3.6 % of all stall samples on the
-// tile claim, profiles/r2g_*); written as PTX the value is only waited for where it is used.
-__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
-    uint32_t r;
-    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
-    return r;
-}
 // store only where `on` is non-zero -- as a PREDICATED store, not a branch around one
 __device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, uint32_t on) {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n}" ::"r"(a), "h"((unsigned short)v), "r"(on) : "memory");
@@ -237,93 +229,85 @@ __device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, ui
     return g;
 }
 
-// ---- decoupled look-back by one warp ------------------------------------------------------------------------------------
+// ---- global line numbers: per-tile counts + a scan warp ---------------------------------------------------------------------
 // Number of newlines before tile t.  Every resident warp works on its own tile at about the same time (~2400 tiles in
-// flight), so a flat look-back would find nothing but per-tile counts for a whole wave.  Two levels, both fed EARLY:
-//   tile_state[t]   flag << 62 | value; flag 1 = the tile's own count, 2 = inclusive prefix (all newlines up to its end)
-//   seg_acc[s]      tiles of segment s (32 consecutive tiles) that have reported << 48 | sum of their counts: every tile ADDS
-//                   its count here the moment it knows it, so a segment's total is there when its slowest tile has scanned
-//                   its bytes -- no tile has to collect it (round 1 and the first round-2 kernel let the segment's last tile
-//                   publish the total from its own look-back: everybody behind then waited for that tile, 26 % of all stall
-//                   samples and 15 instructions per record of polling, profiles/r2d_*)
-//   seg_pre[s]      2 << 62 | inclusive prefix at the end of segment s, written by the segment's last tile when it resolves
-// publish runs right after the tile's newline masks are known, resolve at the very end of the tile (see the kernel), i.e.
-// most of a tile-time later: what it reads has long been written.  Tiles are handed out in order and started when claimed,
-// so every state a tile waits for belongs to a warp that is running and reports without waiting for anything: no cycle.
+// flight), so a classic decoupled look-back would walk back through ~75 segments of per-tile counts before it met an
+// inclusive prefix (round 1 and the first round-2 kernels did: 170 instructions per tile, profiles/r2h_*).  Instead:
+//   tile_cnt[t]   0x80000000 | the tile's own newline count, stored the moment the tile has scanned its bytes
+//   seg_acc[s]    tiles of segment s (32 consecutive tiles) that have reported << 48 | sum of their counts: every tile ADDS
+//                 its count here at the same moment
+//   seg_pre[s]    2 << 62 | number of newlines up to the end of segment s -- written by ONE warp of the grid, the scan warp
+//                 (an extra warp of CTA 0 that owns no tiles): it follows the segments in order, waits until all 32 tiles of
+//                 a segment have reported, and publishes the running sum, up to 32 segments per step.
+// A tile's prefix is then seg_pre[its segment - 1] + the counts of the at most 31 tiles before it in its own segment: one
+// 64-bit word and one warp reduction.  Both are requested BEFORE the record phase and consumed after it, i.e. most of a
+// tile-time after the counts were stored, so the wait loops below hardly ever turn.  Nobody waits in a cycle: counts are
+// stored without waiting for anything, the scan warp only waits for counts, tiles only wait for counts and the scan warp.
 struct Lookback {
-    unsigned long long *tile_state, *seg_acc, *seg_pre;
+    uint32_t* tile_cnt;
+    unsigned long long *seg_acc, *seg_pre;
 };
+constexpr unsigned long long kLbValue = (1ull << 62) - 1, kLbSum = (1ull << 48) - 1;
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+
 __device__ __forceinline__ void lookback_publish(const Lookback& lb, uint32_t t, uint32_t agg, uint32_t lane) {
-    if (lane == 0) atomicExch(lb.tile_state + t, ((t == 0 ? 2ull : 1ull) << 62) | agg);      // nothing precedes tile 0: its count is its prefix
+    if (lane == 0) atomicExch(lb.tile_cnt + t, 0x80000000u | agg);
     if (lane == 1) atomicAdd(lb.seg_acc + (t >> 5), (1ull << 48) | agg);
 }
-// What lane `lane` of tile t will look at first when it resolves: the state of tile t-1-lane (own segment) and of segment
-// (t >> 5) - 1 - lane.  Loaded BEFORE the record phase and consumed after it, so the two dependent L2 round trips of a
-// look-back (9 % of all stall samples when taken on the spot, profiles/r2e_*) overlap with the walk of the records.
 struct LookbackPre {
-    unsigned long long tile_st, seg_pre, seg_acc;
+    uint32_t cnt;                 // lane < (t & 31): state of tile t - 1 - lane
+    unsigned long long seg;       // every lane: seg_pre of the segment before t's
 };
 __device__ __forceinline__ LookbackPre lookback_prefetch(const Lookback& lb, uint32_t t, uint32_t lane) {
-    LookbackPre p{0ull, 0ull, 0ull};
-    if (t == 0) return p;
-    if (lane < (t & 31u)) p.tile_st = *reinterpret_cast<const volatile unsigned long long*>(lb.tile_state + (t - 1u - lane));
-    const int32_t idx = (int32_t)(t >> 5) - 1 - (int32_t)lane;
-    if (idx >= 0) {
-        p.seg_pre = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_pre + idx);
-        p.seg_acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
-    }
+    LookbackPre p{0u, 0ull};
+    if (lane < (t & 31u)) p.cnt = ld_volatile_u32(lb.tile_cnt + (t - 1u - lane));
+    if (t >> 5) p.seg = ld_volatile_u64(lb.seg_pre + ((t >> 5) - 1u));
     return p;
 }
-__device__ __noinline__ unsigned long long lookback_resolve(Lookback lb, uint32_t t, uint32_t agg, uint32_t lane, LookbackPre pre) {
-    if (t == 0) return 0;
-    const unsigned long long kValue = (1ull << 62) - 1, kSum = (1ull << 48) - 1;
-    auto poll_tile = [](const unsigned long long* p, unsigned long long st) {
-        while ((st >> 62) == 0) {      // spinning would steal issue slots
-            __nanosleep(40);
-            st = *reinterpret_cast<const volatile unsigned long long*>(p);
+__device__ __forceinline__ unsigned long long lookback_resolve(const Lookback& lb, uint32_t t, uint32_t lane, LookbackPre pre) {
+    const bool mine = lane < (t & 31u);
+    uint32_t st = pre.cnt;
+    while (__any_sync(kFullMask, mine && !(st >> 31))) {
+        if (mine && !(st >> 31)) {
+            __nanosleep(40);      // spinning would steal issue slots
+            st = ld_volatile_u32(lb.tile_cnt + (t - 1u - lane));
         }
-        return st;
-    };
-    auto poll_seg = [&](int32_t idx, unsigned long long p, unsigned long long acc) -> unsigned long long {
-        for (;;) {
-            if ((p >> 62) == 2) return p;
-            if ((acc >> 48) == 32) return (1ull << 62) | (acc & kSum);
+    }
+    const uint32_t own = __reduce_add_sync(kFullMask, mine ? (st & 0x7FFFFFFFu) : 0u);
+    unsigned long long p = 0;
+    if (t >> 5) {
+        p = pre.seg;
+        while ((p >> 62) != 2) {      // warp-uniform: every lane reads the same word
             __nanosleep(40);
-            p = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_pre + idx);
-            acc = *reinterpret_cast<const volatile unsigned long long*>(lb.seg_acc + idx);
+            p = ld_volatile_u64(lb.seg_pre + ((t >> 5) - 1u));
         }
-    };
-    // sums the 32 states held by the lanes (lane 0 = nearest) up to and including the first inclusive prefix: the counts in
-    // front of it fit 32 bits each and together (32 x 2^48 at most would not, but a segment holds at most 32 x 10752
-    // newlines and a tile 10752), so they go through one warp reduction; the prefix itself is one 64-bit shuffle
-    auto fold = [&](unsigned long long st, bool use, bool& hit_prefix) {
-        const uint32_t has_prefix = __ballot_sync(kFullMask, use && (st >> 62) == 2);
-        const uint32_t first = has_prefix ? (uint32_t)__ffs(has_prefix) - 1u : 32u;
-        const uint32_t counts = __reduce_add_sync(kFullMask, (use && lane < first) ? (uint32_t)st : 0u);
-        unsigned long long v = counts;
-        if (has_prefix) v += __shfl_sync(kFullMask, st, first) & kValue;
-        hit_prefix = has_prefix != 0;
-        return v;
-    };
-    const uint32_t r = t & 31u;                    // predecessors inside this tile's own segment
-    bool done = false;
-    const bool mine = lane < r;
-    unsigned long long excl = fold(mine ? poll_tile(lb.tile_state + (t - 1u - lane), pre.tile_st) : 0ull, mine, done);
-    int32_t seg = (int32_t)(t >> 5) - 1;           // nearest earlier segment
-    bool first_round = true;
-    while (!done) {
-        const int32_t idx = seg - (int32_t)lane;
-        unsigned long long st = 2ull << 62;        // before the stream: prefix 0
-        if (idx >= 0) st = first_round ? poll_seg(idx, pre.seg_pre, pre.seg_acc) : poll_seg(idx, 0ull, 0ull);
-        excl += fold(st, true, done);
-        seg -= 32;
-        first_round = false;
+        p &= kLbValue;
     }
-    if (lane == 0) {
-        atomicExch(lb.tile_state + t, (2ull << 62) | (excl + agg));
-        if (r == 31u) atomicExch(lb.seg_pre + (t >> 5), (2ull << 62) | (excl + agg));
+    return p + own;
+}
+// The scan warp of a launch over tiles [first, end): segments whose last tile lies in that range get their prefix here.
+__device__ __noinline__ void scan_segments(Lookback lb, uint32_t first, uint32_t end, uint32_t lane) {
+    const uint32_t s_hi = end >> 5;
+    uint32_t base = first >> 5;
+    unsigned long long carry = base ? (ld_volatile_u64(lb.seg_pre + (base - 1u)) & kLbValue) : 0ull;      // left by an earlier launch
+    while (base < s_hi) {
+        const uint32_t sgm = base + lane;
+        unsigned long long acc = 0;
+        if (sgm < s_hi) acc = ld_volatile_u64(lb.seg_acc + sgm);
+        const uint32_t ready = __ballot_sync(kFullMask, (acc >> 48) == 32);
+        const uint32_t n = ready == kFullMask ? 32u : (uint32_t)__ffs((int)~ready) - 1u;      // leading segments that are complete
+        if (n == 0) { __nanosleep(100); continue; }
+        uint32_t incl = lane < n ? (uint32_t)(acc & kLbSum) : 0u;      // a segment holds at most 32 x 10752 newlines
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (uint32_t)d) incl += v;
+        }
+        if (lane < n) atomicExch(lb.seg_pre + sgm, (2ull << 62) | (carry + incl));
+        carry += __shfl_sync(kFullMask, incl, n - 1u);
+        base += n;
     }
-    return excl;
 }
 
 template <int TIER>
@@ -451,6 +435,7 @@ __device__ __forceinline__ uint32_t commit_records(const FastqArgs& a, const Til
         if (R >= a.mask_bits || (c.want_idh && R >= a.id_hash_cap)) { report(a, c.T0, kErrMaskOverflow); o.sel = false; }
         else if (c.want_idh) a.id_hash[R] = o.idh;
         if (a.seq_start && R < a.span_cap) { a.seq_start[R] = o.seq_pos; a.seq_len[R] = o.seq_n; }
+        if (a.soa_start && R < a.span_cap) { a.soa_start[R] = (uint32_t)o.seq_pos; a.soa_end[R] = (uint32_t)o.seq_pos + o.seq_n; }
         if (a.rec_off && R < a.rec_cap) { a.rec_off[R] = o.rec_off; a.rec_len[R] = o.rec_n; }
     }
     const uint32_t mk = __ballot_sync(kFullMask, valid && o.sel);
@@ -523,10 +508,12 @@ __device__ __noinline__ uint32_t dense_tile(const FastqArgs& a, const RecordEval
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
+// blockDim = (tile warps + 1) x 32: the last warp of CTA 0 is the scan warp (see Lookback), the last warp of every other CTA
+// leaves at once.
 template <int TIER>
-__global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+__global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, tile_warps = (blockDim.x >> 5) - 1u;
 
     // ---- smem carve-up: [automaton][class LUT 256][per-warp regions]
     uint8_t* s_tab = smem;
@@ -535,9 +522,15 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     const uint32_t bar = smem_addr(s_warp), list_sa = bar + kWarpListOff, tile_sa = bar + kWarpTileOff;
 
     stage_automaton<TIER>(dfa, s_tab, s_cls);
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0 && warp < tile_warps) mbar_init(bar, 1);
     mbar_fence_init();
     __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
+
+    const Lookback lb{reinterpret_cast<uint32_t*>(a.tile_state), a.seg_acc, a.seg_pre};
+    if (warp == tile_warps) {
+        if (blockIdx.x == 0) scan_segments(lb, a.tile_first, a.tile_first + a.tile_count, lane);
+        return;
+    }
 
     const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
     TileCtx c;
@@ -549,37 +542,26 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
     const uint64_t stream_len = c.stream_len;
     const uint32_t c0a = a.nl_xor, c7f = a.nl_low7;     // see FastqArgs: not compile-time constants on purpose
     const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
-    const Lookback lb{a.tile_state, a.seg_acc, a.seg_pre};
     uint32_t phase = 0;
     unsigned long long local_count = 0;
 
-    // Tiles are claimed in order from an atomic counter and started the moment they are claimed: a tile's newline count is
-    // then published a fixed time after its claim, which is what the look-backs of the tiles behind it rely on.  (Claiming
-    // one tile AHEAD would hide the claim's round trip, but an early-claimed tile publishes a whole tile-time later and
-    // everything behind it waits that much longer: measured 2.6x slower, profiles/r2c_*.  Even claiming just before this
-    // tile's look-back is resolved is too early -- 3.5x slower, profiles/r2f_*: a warp that waits in its look-back while it
-    // holds an unstarted tile delays every tile behind that one, whose warps then wait holding THEIR next tiles, and the
-    // delays pile up.  The rule: between claiming a tile and publishing its count a warp never waits for another tile.)
-    // The claim for the next tile is issued right after the look-back has been resolved, before the results are committed.
-    const uint32_t nwarps_all = gridDim.x * (blockDim.x >> 5);
-    uint32_t claim = 0;
-    if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
-    claim = __shfl_sync(kFullMask, claim, 0);
-    while (claim < a.tile_count) {
+    // Tiles are dealt out statically, in order: global warp w takes tiles w, w + W, w + 2W, ... of the launch (W = tile warps
+    // of the grid).  Every warp publishes the newline count of its tile without waiting for anything and only then may wait
+    // for earlier tiles, so the earliest unfinished tile can always finish.  (Rounds 1-2 claimed tiles from an atomic
+    // counter: 3.5 % of all stall samples sat on that round trip and 25 instructions per tile went into it, profiles/r2h_*.)
+    const uint32_t W = gridDim.x * tile_warps;
+    for (uint32_t claim = blockIdx.x * tile_warps + warp; claim < a.tile_count; claim += W) {
         const TileGeom g = tile_geom(a, a.tile_first + claim, stream_len);
         c.T0 = g.T0;
-        uint32_t next_claim = 0;
-        bool claimed = false;
         if (lane == 0) {
             if (g.real_avail) {
                 const uint32_t bytes = (g.real_avail + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
                 bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
             }
-            // Tiles are handed out in order, so the tile one full wave ahead (one per resident warp) is the one some warp
-            // will ask for about a tile-time from now: pull it into L2 (126 MB; a wave is ~25 MB) so that copy only pays
-            // L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
-            const uint32_t ahead = claim + nwarps_all;
+            // This warp's NEXT tile is pulled into L2 (126 MB; a wave of tiles is ~25 MB) while this one is worked on, so its
+            // copy only pays L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
+            const uint32_t ahead = claim + W;
             if (ahead < a.tile_count) {
                 const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
                 if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
@@ -617,9 +599,9 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         }
 
         // ---- 3. ranks: newlines before this lane's bytes; the tile's own count (lanes 0..28, or everything in the stream's last tile)
-        uint32_t cnt = 0;
+        uint32_t pc[kWords], cnt = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < kWords; j++) cnt += (uint32_t)__popc(m[j]);
+        for (uint32_t j = 0; j < kWords; j++) { pc[j] = (uint32_t)__popc(m[j]); cnt += pc[j]; }
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -630,58 +612,61 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
         const uint32_t agg = g.region == kTile ? __shfl_sync(kFullMask, incl, kTileLanes - 1u) : total;
         c.total = total;
         lookback_publish(lb, g.t, agg, lane);
-        auto claim_next = [&]() {      // warp-uniform; the result is picked up at the bottom of the loop
-            if (!claimed && lane == 0) next_claim = atom_add_u32(a.tile_counter, 1u);
-            claimed = true;
-        };
-        const LookbackPre no_pre{0ull, 0ull, 0ull};
+        const LookbackPre no_pre{0u, 0ull};
 
         if (a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
         if (total > kListCap) {
-            const unsigned long long Lt = lookback_resolve(lb, g.t, agg, lane, no_pre);
+            const unsigned long long Lt = lookback_resolve(lb, g.t, lane, no_pre);
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
             LaneWords mw;
 #pragma unroll
             for (uint32_t j = 0; j < kWords; j++) mw.w[j] = m[j];
             local_count += dense_tile<TIER>(a, ev, c, g, mw, incl - cnt, agg, Lt, lane);
         } else {
-            // ---- 4. scatter: list[rank] = position in the tile.  Two branch-free steps per word (a lane rarely has more
-            //         than two newlines in 32 bytes: the "\n+\n" of a record), then a loop for whatever is left in any lane.
+            // ---- 4. scatter: list[rank] = position in the tile.  The first two newlines of every 32-byte word are stored
+            //         straight away, word by word and independently of each other (a lane rarely has more than two in 32
+            //         bytes: the "\n+\n" of a record); only if some lane has a third one somewhere the generic loop runs.
             {
-                uint32_t addr = list_sa + 2u * (incl - cnt);
+                uint32_t addr = list_sa + 2u * (incl - cnt), leftover = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < kWords; j++) {
-                    uint32_t w = m[j];
-                    const uint32_t pos0 = lane_pos + 32u * j;
+                    const uint32_t rw = __brev(m[j]), pos0 = lane_pos + 32u * j;
+                    const uint32_t f1 = (uint32_t)__clz((int)rw);                         // 32 when the word is empty
+                    sts_u16_if(addr, pos0 + f1, rw);
+                    const uint32_t rw2 = rw & __funnelshift_rc(0x7FFFFFFFu, 0u, f1);      // first one cleared
+                    const uint32_t f2 = (uint32_t)__clz((int)rw2);
+                    sts_u16_if(addr + 2u, pos0 + f2, rw2);
+                    leftover |= rw2 & __funnelshift_rc(0x7FFFFFFFu, 0u, f2);
+                    addr += 2u * pc[j];
+                }
+                if (__any_sync(kFullMask, leftover != 0)) {
+                    addr = list_sa + 2u * (incl - cnt);
 #pragma unroll
-                    for (int step = 0; step < 2; step++) {
-                        const uint32_t on = w ? 1u : 0u;
-                        sts_u16_if(addr, pos0 + (uint32_t)__ffs((int)w) - 1u, on);
-                        addr += 2u * on;
-                        w &= w - 1u;
-                    }
-                    while (__any_sync(kFullMask, w != 0)) {
-                        const uint32_t on = w ? 1u : 0u;
-                        sts_u16_if(addr, pos0 + (uint32_t)__ffs((int)w) - 1u, on);
-                        addr += 2u * on;
-                        w &= w - 1u;
+                    for (uint32_t j = 0; j < kWords; j++) {
+                        uint32_t w = m[j];
+                        const uint32_t pos0 = lane_pos + 32u * j;
+                        while (w) {
+                            sts_u16(addr, pos0 + (uint32_t)__ffs((int)w) - 1u);
+                            addr += 2u;
+                            w &= w - 1u;
+                        }
                     }
                 }
             }
             __syncwarp();
 
             // ---- 5. the line phase.  Which local newline ends a record depends on the number of newlines before the tile
-            //         (mod 4), i.e. on the look-back -- which has to wait for the slowest of the ~2000 tiles in flight before
-            //         this one.  Instead of waiting, the phase is GUESSED from the tile itself: lanes 0..7 test, for the four
-            //         candidates and the first two records each, "starts with '@', '+' two lines on, equal lengths".  One
-            //         surviving candidate = the guess; the records are evaluated under it into registers, the look-back is
-            //         resolved afterwards (by then its inputs are there) and only a confirmed guess is committed.  A wrong
-            //         or impossible guess costs a second pass, never a wrong answer.
+            //         (mod 4), which is only known once every earlier tile has been scanned.  Instead of waiting, the phase
+            //         is GUESSED from the tile itself: lanes 0..7 test, for the four candidates and the first two records
+            //         each, "starts with '@', '+' two lines on, equal lengths".  One surviving candidate = the guess; the
+            //         records are evaluated under it into registers, the prefix is resolved afterwards (by then its inputs
+            //         are there) and only a confirmed guess is committed.  A wrong or impossible guess costs a second pass,
+            //         never a wrong answer.
             unsigned long long Lt = 0;
             bool have_Lt = false;
             uint32_t j0 = 3u;
             LookbackPre pre = no_pre;
-            if (g.t == 0) have_Lt = true;          // nothing precedes the first tile (its prefix went out with its count)
+            if (g.t == 0) have_Lt = true;          // nothing precedes the first tile
             else {
                 bool ok = false;
                 const uint32_t cand = lane & 3u, r = cand + 4u * (lane >> 2);      // boundary newline rank under this candidate
@@ -698,7 +683,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                     if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
                     pre = lookback_prefetch(lb, g.t, lane);      // consumed after the record phase
                 } else {
-                    Lt = lookback_resolve(lb, g.t, agg, lane, no_pre);
+                    Lt = lookback_resolve(lb, g.t, lane, no_pre);
                     have_Lt = true;
                     j0 = 3u - (uint32_t)(Lt & 3ull);
                 }
@@ -718,7 +703,7 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         o = eval_record<TIER>(a, ev, c, s, r0, 0u);
                     }
                     if (!have_Lt) {
-                        Lt = lookback_resolve(lb, g.t, agg, lane, pre);
+                        Lt = lookback_resolve(lb, g.t, lane, pre);
                         have_Lt = true;
                         const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
                         if (exact != j0) {
@@ -729,12 +714,11 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
                         }
                         ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
                     }
-                    claim_next();      // nothing below waits for another tile
                     finish_names<TIER>(ev, o);
                     local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
                 }
                 if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed
-                    Lt = lookback_resolve(lb, g.t, agg, lane, pre);
+                    Lt = lookback_resolve(lb, g.t, lane, pre);
                     have_Lt = true;
                     const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
                     if (exact != j0) { j0 = exact; redo = true; }
@@ -744,8 +728,6 @@ __global__ void __launch_bounds__(512, 1) match_fastq_kernel(FastqArgs a, Device
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
         }
         __syncwarp();       // every lane is done with the list and the tile before the next bulk copy overwrites them
-        claim_next();
-        claim = __shfl_sync(kFullMask, next_claim, 0);
     }
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
 }
@@ -808,7 +790,7 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_coun
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
     uint32_t warps = (budget - table_smem - 256u - 128u) / kWarpBytes;      // one tile buffer per warp
-    if (warps > 16u) warps = 16u;
+    if (warps > 17u) warps = 17u;
     if (warps < 1u) warps = 1u;
     if (a.tile_count < (uint32_t)sm_count * warps) {          // small inputs: spread the tiles over the SMs first
         warps = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
@@ -821,7 +803,7 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_coun
     uint32_t grid = (a.tile_count + warps - 1u) / warps;
     if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
     if (grid == 0) return cudaSuccess;
-    kern<<<grid, warps * 32u, smem, stream>>>(a, dfa, table_smem);
+    kern<<<grid, (warps + 1u) * 32u, smem, stream>>>(a, dfa, table_smem);      // + the scan warp
     return cudaGetLastError();
 }
 
