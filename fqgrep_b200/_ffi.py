@@ -48,7 +48,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.SO
+    path = os.environ.get("FQG_LIB_VARIANT") or _build.SO      # measurement hook: a variant build of the same library (build.build_variant)
     if not os.path.exists(path):
         raise ImportError("libfqgrep_b200.so is not built: run `python -m fqgrep_b200.build` (nvcc, sm_100a). "
                           "fqgrep_b200 has no CPU or pure-Python path.")

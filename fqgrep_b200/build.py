@@ -64,6 +64,25 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_variant(name, defines, sources=("match_fastq.cu",)):
+    """Measurement hook: the same library with `sources` recompiled under extra -D flags, as libfqgrep_b200_<name>.so
+    (loaded through FQG_LIB_VARIANT).  Used for A/B runs of kernel parameters inside one GPU call."""
+    build()
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objdir = os.path.join(HERE, "build")
+    objs = []
+    for src in SOURCES + HOST_SOURCES:
+        obj = os.path.join(objdir, src + ".o")
+        if src in sources:
+            obj = os.path.join(objdir, "%s.%s.o" % (src, name))
+            subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        objs.append(obj)
+    so = os.path.join(HERE, "libfqgrep_b200_%s.so" % name)
+    subprocess.check_call([nvcc, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz"])
+    return so
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print(SO)

@@ -46,7 +46,11 @@ struct StreamPlan {
     uint32_t tiles_done = 0, launches = 0;
 };
 
-size_t state_words(uint32_t tiles) { return (size_t)tiles + 1 + 2 * ((size_t)tiles / 32 + 2); }
+// look-back state of one stream: [per-tile counts (u32, in u64 slots)][seg_acc][seg_pre], the segment arrays on 32-byte
+// boundaries with slack (the scan warp reads four segments per lane with vector loads)
+size_t seg_offset(uint32_t tiles) { return ((size_t)tiles + 1 + 3) & ~(size_t)3; }
+size_t seg_words(uint32_t tiles) { return (((size_t)tiles / 32 + 2) + 7) & ~(size_t)3; }
+size_t state_words(uint32_t tiles) { return seg_offset(tiles) + 2 * seg_words(tiles); }
 
 const char* fastq_err_name(unsigned code) {
     switch (code) {
@@ -297,7 +301,7 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
         FastqArgs a{};
         a.buf = s.d; a.nbytes = s.n; a.virtual_final_nl = 1;
         a.tile_first = s.tiles_done; a.tile_count = tile_end - s.tiles_done;
-        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_acc = s.state + s.tiles + 1; a.seg_pre = a.seg_acc + s.tiles / 32 + 2; a.lines_out = ctl + 3 + i;
+        a.tile_counter = s.counters + s.launches; a.tile_state = s.state; a.seg_acc = s.state + seg_offset(s.tiles); a.seg_pre = a.seg_acc + seg_words(s.tiles); a.lines_out = ctl + 3 + i;
         a.mask = s.mask; a.mask_bits = s.mask_bits; a.id_hash = s.idh; a.id_hash_cap = s.idh_cap;
         a.count = (mode == FQG_SINGLE && !route) ? ctl + 1 : nullptr;
         a.err = ctl + 0;
@@ -410,8 +414,8 @@ int lane_wait(fqg_ctx* c, FastqLane* L, BatchOut* out) {
     const int n_streams = mode == FQG_PAIRED ? 2 : 1;
     const unsigned long long* h_ctl = (const unsigned long long*)L->h[H_CTL];
     if (L->stats)
-        std::fprintf(stderr, "[fqg] fused kernel: %llu tiles, %llu with a guessed line phase (%llu guessed wrong), %llu dense\n", h_ctl[8] + h_ctl[11], h_ctl[9], h_ctl[10],
-                     h_ctl[11]);
+        std::fprintf(stderr, "[fqg] fused kernel: %llu tiles, %llu with a guessed line phase (%llu guessed wrong), %llu dense; of %llu warp-cycles %.1f %% waited for the copy, %.1f %% for the prefix (%.1f %% on the scan warp's word)\n",
+                     h_ctl[8] + h_ctl[11], h_ctl[9], h_ctl[10], h_ctl[11], h_ctl[14], h_ctl[14] ? 100.0 * h_ctl[12] / h_ctl[14] : 0.0, h_ctl[14] ? 100.0 * h_ctl[13] / h_ctl[14] : 0.0, h_ctl[14] ? 100.0 * h_ctl[15] / h_ctl[14] : 0.0);
     fqg_result* res = &out->res;
     uint64_t d2h_bytes = 64 + L->eager_mask_words * 4;
 

@@ -37,19 +37,32 @@
 namespace fqg {
 namespace {
 
-constexpr uint32_t kUnits = 21;                        // 16-byte units per lane; ODD => lane-strided LDS.128 hits 8 distinct bank groups
+#ifndef FQG_UNITS
+#define FQG_UNITS 21
+#endif
+#ifndef FQG_EARLY_ISSUE
+#define FQG_EARLY_ISSUE 1
+#endif
+#ifndef FQG_LISTCAP
+#define FQG_LISTCAP 1024
+#endif
+constexpr uint32_t kUnits = FQG_UNITS;                        // 16-byte units per lane; ODD => lane-strided LDS.128 hits 8 distinct bank groups
 constexpr uint32_t kLaneBytes = kUnits * 16u;          // 336
 constexpr uint32_t kTileLanes = 29;                    // lanes 0..28 hold the tile proper, lanes 29..31 the overlap
 constexpr uint32_t kTile = kTileLanes * kLaneBytes;    // 9744: ~30.7 records of 317 bytes, one per lane in the record phase
 constexpr uint32_t kLoad = 32u * kLaneBytes;           // 10752 bytes staged per tile
 constexpr uint32_t kOverlap = kLoad - kTile;           // 1008
 constexpr uint32_t kWords = (kUnits + 1u) / 2u;        // 11 bitmap words per lane (the last one holds 16 bits)
-constexpr uint32_t kListCap = 1024;                    // newline positions per window; denser tiles take several windows
+constexpr uint32_t kListCap = FQG_LISTCAP;                    // newline positions per window; denser tiles take several windows
 constexpr uint32_t kWindowStep = kListCap - 8u;        // ranks a window is responsible for (a record needs 5 consecutive ranks)
 // per-warp shared memory: [mbarrier, 128][newline list, 2 * kListCap + 128][tile, kLoad + 128]
 constexpr uint32_t kWarpListOff = 128u, kWarpTileOff = kWarpListOff + 2u * kListCap + 128u;
 constexpr uint32_t kWarpBytes = kWarpTileOff + kLoad + 128u;
 static_assert(kWarpBytes % 128u == 0 && kWarpTileOff % 128u == 0, "TMA destination alignment");
+// tile warps that fit 227 KB of shared memory next to the smallest automaton; the register budget follows from it (launch bounds)
+constexpr uint32_t kSmemWarps = (227u * 1024u - 256u - 1024u) / kWarpBytes;
+// (17 would fit next to a tiny table, but a CTA of more than 512 threads leaves every thread 96 registers instead of 128)
+constexpr uint32_t kMaxTileWarps = kSmemWarps > 16u && kSmemWarps < 20u ? 16u : kSmemWarps;
 static_assert(kTile % 16u == 0, "tiles start on 16-byte boundaries (bulk copy source alignment)");
 
 enum : uint32_t { kErrInvalidStart = 1, kErrInvalidSep = 2, kErrUnequal = 3, kErrUnexpectedEnd = 4, kErrMaskOverflow = 6 };
@@ -75,6 +88,14 @@ __device__ __forceinline__ uint32_t lds_u16_volatile(uint32_t a) {
 }
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+// atomicAdd whose result is NOT consumed on the spot: the compiler turns a one-lane atomicAdd() into its warp-aggregated
+// form and shuffles the result out immediately, i.e. waits for the round trip right there; written as PTX the value is only
+// waited for where it is used.
+__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
 }
 // store only where `on` is non-zero -- as a PREDICATED store, not a branch around one
 __device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, uint32_t on) {
@@ -229,6 +250,13 @@ __device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, ui
     return g;
 }
 
+// real bytes of tile t that a copy has to bring in (0: the tile holds nothing but the virtual final newline)
+__device__ __forceinline__ uint32_t tile_real_avail(const FastqArgs& a, uint32_t t) {
+    const uint64_t T0 = (uint64_t)t * kTile;
+    const uint64_t left = a.nbytes > T0 ? a.nbytes - T0 : 0;
+    return left < kLoad ? (uint32_t)left : kLoad;
+}
+
 // ---- global line numbers: per-tile counts + a scan warp ---------------------------------------------------------------------
 // Number of newlines before tile t.  Every resident warp works on its own tile at about the same time (~2400 tiles in
 // flight), so a classic decoupled look-back would walk back through ~75 segments of per-tile counts before it met an
@@ -255,6 +283,10 @@ __device__ __forceinline__ void lookback_publish(const Lookback& lb, uint32_t t,
     if (lane == 0) atomicExch(lb.tile_cnt + t, 0x80000000u | agg);
     if (lane == 1) atomicAdd(lb.seg_acc + (t >> 5), (1ull << 48) | agg);
 }
+// (Letting a tile fall back to the nearest published prefix among the last 32 segments plus the complete seg_acc sums in
+// front of it -- tolerant of a lagging scan warp -- was built and measured: 0.54 -> 0.40 of the roofline.  Every tile then
+// reads the 32 seg_acc words that the tiles of the current wave are busy adding to; those few L2 sectors cannot serve 4 M
+// reads next to the atomics.  seg_acc is read by the scan warp only.)
 struct LookbackPre {
     uint32_t cnt;                 // lane < (t & 31): state of tile t - 1 - lane
     unsigned long long seg;       // every lane: seg_pre of the segment before t's
@@ -265,7 +297,7 @@ __device__ __forceinline__ LookbackPre lookback_prefetch(const Lookback& lb, uin
     if (t >> 5) p.seg = ld_volatile_u64(lb.seg_pre + ((t >> 5) - 1u));
     return p;
 }
-__device__ __forceinline__ unsigned long long lookback_resolve(const Lookback& lb, uint32_t t, uint32_t lane, LookbackPre pre) {
+__device__ __forceinline__ unsigned long long lookback_resolve(const Lookback& lb, uint32_t t, uint32_t lane, LookbackPre pre, long long* t_seg = nullptr) {
     const bool mine = lane < (t & 31u);
     uint32_t st = pre.cnt;
     while (__any_sync(kFullMask, mine && !(st >> 31))) {
@@ -277,36 +309,71 @@ __device__ __forceinline__ unsigned long long lookback_resolve(const Lookback& l
     const uint32_t own = __reduce_add_sync(kFullMask, mine ? (st & 0x7FFFFFFFu) : 0u);
     unsigned long long p = 0;
     if (t >> 5) {
+        const long long t0 = t_seg ? clock64() : 0;
         p = pre.seg;
+        // (Falling back, on a miss, to the nearest published prefix among the last four segments plus the complete seg_acc
+        // sums in front of it was measured twice: the code costs the match kernel 8 registers it does not have -- spills in
+        // the walk, 0.56 -> 0.46 -- and buys the index-only kernel nothing.)
         while ((p >> 62) != 2) {      // warp-uniform: every lane reads the same word
             __nanosleep(40);
             p = ld_volatile_u64(lb.seg_pre + ((t >> 5) - 1u));
         }
         p &= kLbValue;
+        if (t_seg) *t_seg += clock64() - t0;
     }
     return p + own;
 }
 // The scan warp of a launch over tiles [first, end): segments whose last tile lies in that range get their prefix here.
+// Four segments per lane and step (one 32-byte sector of seg_acc each, two vector loads): a step costs an L2 round trip, and
+// at 32 segments per step the warp could only just follow the tile warps (12 segments per microsecond) -- they then waited
+// for IT, 15 % of their time in the match kernel and 34 % in the index-only kernel (FQG_FASTQ_STATS).
 __device__ __noinline__ void scan_segments(Lookback lb, uint32_t first, uint32_t end, uint32_t lane) {
     const uint32_t s_hi = end >> 5;
     uint32_t base = first >> 5;
     unsigned long long carry = base ? (ld_volatile_u64(lb.seg_pre + (base - 1u)) & kLbValue) : 0ull;      // left by an earlier launch
     while (base < s_hi) {
-        const uint32_t sgm = base + lane;
-        unsigned long long acc = 0;
-        if (sgm < s_hi) acc = ld_volatile_u64(lb.seg_acc + sgm);
-        const uint32_t ready = __ballot_sync(kFullMask, (acc >> 48) == 32);
-        const uint32_t n = ready == kFullMask ? 32u : (uint32_t)__ffs((int)~ready) - 1u;      // leading segments that are complete
-        if (n == 0) { __nanosleep(100); continue; }
-        uint32_t incl = lane < n ? (uint32_t)(acc & kLbSum) : 0u;      // a segment holds at most 32 x 10752 newlines
+        const uint32_t s0 = (base & ~3u) + 4u * lane;
+        unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        if (s0 < s_hi) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(acc[0]), "=l"(acc[1]) : "l"(lb.seg_acc + s0));
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(acc[2]), "=l"(acc[3]) : "l"(lb.seg_acc + s0 + 2u));
+        }
+        // segments in front of `base` are done (they count as complete and add nothing), segments from s_hi on are not ours
+        uint32_t lead = 0;
+        bool all = true;
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            const uint32_t sgm = s0 + j;
+            const bool ok = sgm < base || (sgm < s_hi && (acc[j] >> 48) == 32);
+            all = all && ok;
+            lead += all ? 1u : 0u;
+        }
+        const uint32_t full = __ballot_sync(kFullMask, lead == 4u);
+        const uint32_t fp = full == kFullMask ? 32u : (uint32_t)__ffs((int)~full) - 1u;      // first lane that is not complete
+        const uint32_t new_end = (base & ~3u) + 4u * fp + (fp < 32u ? __shfl_sync(kFullMask, lead, fp & 31u) : 0u);
+        if (new_end <= base) { __nanosleep(60); continue; }
+        uint32_t v[4], lane_tot = 0;      // a segment holds at most 32 x 10752 newlines
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            const uint32_t sgm = s0 + j;
+            v[j] = (sgm >= base && sgm < new_end) ? (uint32_t)(acc[j] & kLbSum) : 0u;
+            lane_tot += v[j];
+        }
+        uint32_t incl = lane_tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
+            const uint32_t u = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (uint32_t)d) incl += u;
         }
-        if (lane < n) atomicExch(lb.seg_pre + sgm, (2ull << 62) | (carry + incl));
-        carry += __shfl_sync(kFullMask, incl, n - 1u);
-        base += n;
+        unsigned long long running = carry + (incl - lane_tot);
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            const uint32_t sgm = s0 + j;
+            running += v[j];
+            if (sgm >= base && sgm < new_end) atomicExch(lb.seg_pre + sgm, (2ull << 62) | running);
+        }
+        carry += __shfl_sync(kFullMask, incl, 31);
+        base = new_end;
     }
 }
 
@@ -359,6 +426,41 @@ struct TileCtx {
     bool want_idh;
 };
 
+// Record that starts at stream position gs, read straight from global memory: records that do not end inside tile + overlap
+// (reads longer than ~400 bases) and the slow second look at a tile whose guessed line phase turned out wrong.
+template <int TIER>
+__device__ __noinline__ RecOut eval_record_global(const FastqArgs& a, const RecordEval<TIER>& ev, const TileCtx& c, uint64_t gs) {
+    RecOut o;
+    const uint8_t* base = a.buf;
+    uint64_t q[4];
+    uint64_t p = gs;
+    int found = 0;
+    for (; found < 4 && p < c.stream_len; p++)
+        if (p == a.nbytes || base[p] == '\n') q[found++] = p;
+    if (found < 4) { o.err = kErrUnexpectedEnd; o.err_pos = gs; }
+    else {
+        const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
+        const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
+        const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
+        const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
+        if (base[gs] != '@') { o.err = kErrInvalidStart; o.err_pos = gs; }
+        else if (base[q[1] + 1] != '+') { o.err = kErrInvalidSep; o.err_pos = q[1] + 1; }
+        else if (seq_len != qual_len) { o.err = kErrUnequal; o.err_pos = gs; }
+        o.seq_pos = q[0] + 1;
+        o.seq_n = (uint32_t)seq_len;
+        if (a.rec_off) {
+            const bool virt = q[3] == a.nbytes;
+            const bool norm = (cr0 | cr1 | cr3) != 0 || q[2] - q[1] != 2u || virt;
+            o.rec_off = gs | (norm ? 1ull << 63 : 0ull);
+            o.rec_n = (uint32_t)(q[3] - gs + (virt ? 0u : 1u));
+        }
+        unsigned long long idh = 0;      // (its address goes to an out-of-line function: keep that away from `o`, which lives in registers)
+        o.sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, c.want_idh);
+        o.idh = idh;
+    }
+    return o;
+}
+
 // Record whose line ends have ranks r0 .. r0+3 in the newline list (list entry of rank r = list[r - win_lo]) and that starts
 // at tile position s.
 template <int TIER>
@@ -388,35 +490,7 @@ __device__ __forceinline__ RecOut eval_record(const FastqArgs& a, const RecordEv
         o.sel = ev.eval_shared(tile_sa, s, p0, seq_len, &idh, c.want_idh, &o.name);
         o.idh = idh;
     } else {
-        // record runs past tile+overlap (or the stream is truncated): walk it in global memory
-        const uint8_t* base = a.buf;
-        const uint64_t gs = T0 + s;
-        uint64_t q[4];
-        uint64_t p = gs;
-        int found = 0;
-        for (; found < 4 && p < c.stream_len; p++)
-            if (p == a.nbytes || base[p] == '\n') q[found++] = p;
-        if (found < 4) { o.err = kErrUnexpectedEnd; o.err_pos = gs; }
-        else {
-            const uint32_t cr0 = (q[0] > gs + 1 && base[q[0] - 1] == '\r') ? 1u : 0u;
-            const uint32_t cr1 = (q[1] > q[0] + 1 && base[q[1] - 1] == '\r') ? 1u : 0u;
-            const uint32_t cr3 = (q[3] > q[2] + 1 && base[q[3] - 1] == '\r') ? 1u : 0u;
-            const uint64_t seq_len = q[1] - q[0] - 1 - cr1, qual_len = q[3] - q[2] - 1 - cr3;
-            if (base[gs] != '@') { o.err = kErrInvalidStart; o.err_pos = gs; }
-            else if (base[q[1] + 1] != '+') { o.err = kErrInvalidSep; o.err_pos = q[1] + 1; }
-            else if (seq_len != qual_len) { o.err = kErrUnequal; o.err_pos = gs; }
-            o.seq_pos = q[0] + 1;
-            o.seq_n = (uint32_t)seq_len;
-            if (a.rec_off) {
-                const bool virt = q[3] == a.nbytes;
-                const bool norm = (cr0 | cr1 | cr3) != 0 || q[2] - q[1] != 2u || virt;
-                o.rec_off = gs | (norm ? 1ull << 63 : 0ull);
-                o.rec_n = (uint32_t)(q[3] - gs + (virt ? 0u : 1u));
-            }
-            unsigned long long idh = 0;      // (its address goes to an out-of-line function: keep that away from `o`, which lives in registers)
-            o.sel = ev.eval_global(base + gs + 1, q[0] > gs ? (uint32_t)(q[0] - gs - 1 - cr0) : 0u, base + q[0] + 1, (uint32_t)seq_len, &idh, c.want_idh);
-            o.idh = idh;
-        }
+        o = eval_record_global<TIER>(a, ev, c, T0 + s);      // record runs past tile+overlap (or the stream is truncated)
     }
     return o;
 }
@@ -428,12 +502,13 @@ __device__ __forceinline__ void finish_names(const RecordEval<TIER>& ev, RecOut&
 }
 
 // Writes what 32 lanes found out about records R_w .. R_w + 31 (lane i: record R_w + i, `valid` lanes only); returns the number selected.
-__device__ __forceinline__ uint32_t commit_records(const FastqArgs& a, const TileCtx& c, RecOut o, bool valid, unsigned long long R_w, uint32_t lane) {
+__device__ __forceinline__ uint32_t commit_records(const FastqArgs& a, uint64_t T0, bool want_idh, const RecOut& o_in, bool valid, unsigned long long R_w, uint32_t lane) {
+    RecOut o = o_in;
     if (valid) {
         const unsigned long long R = R_w + lane;
         if (o.err) report(a, o.err_pos, o.err);
-        if (R >= a.mask_bits || (c.want_idh && R >= a.id_hash_cap)) { report(a, c.T0, kErrMaskOverflow); o.sel = false; }
-        else if (c.want_idh) a.id_hash[R] = o.idh;
+        if (R >= a.mask_bits || (want_idh && R >= a.id_hash_cap)) { report(a, T0, kErrMaskOverflow); o.sel = false; }
+        else if (want_idh) a.id_hash[R] = o.idh;
         if (a.seq_start && R < a.span_cap) { a.seq_start[R] = o.seq_pos; a.seq_len[R] = o.seq_n; }
         if (a.soa_start && R < a.span_cap) { a.soa_start[R] = (uint32_t)o.seq_pos; a.soa_end[R] = (uint32_t)o.seq_pos + o.seq_n; }
         if (a.rec_off && R < a.rec_cap) { a.rec_off[R] = o.rec_off; a.rec_len[R] = o.rec_n; }
@@ -462,6 +537,40 @@ __device__ __forceinline__ TilePhase tile_phase(const TileGeom& g, uint32_t j0, 
     p.n_list = p.extra + (agg > j0 ? (agg - j0 + 3u) / 4u : 0u);
     if (g.T0 + g.region == stream_len && agg > j0 && ((agg - j0 - 1u) & 3u) == 0) p.n_list--;   // the stream's final newline starts nothing
     return p;
+}
+
+// A tile whose records have to be found again under the exact line phase because the guessed one was wrong -- which means
+// that the first records of the tile are malformed (a well-formed tile always confirms its guess), so this only ever runs
+// on damaged input and may be slow: ONE lane walks the tile's bytes in global memory, record by record.  It does not touch
+// the warp's shared-memory tile (which may already hold the next tile).
+template <int TIER>
+__device__ __noinline__ uint32_t redo_tile_global(const FastqArgs& a, const RecordEval<TIER>& ev, TileCtx c, uint32_t t, unsigned long long Lt, uint32_t lane) {
+    c.T0 = (uint64_t)t * kTile;
+    const uint64_t end = c.T0 + kTile < c.stream_len ? c.T0 + kTile : c.stream_len;
+    uint64_t pos = c.T0;
+    unsigned long long lines = Lt;      // newlines before pos
+    bool stream_start = t == 0;
+    uint32_t selected = 0;
+    for (;;) {
+        unsigned long long gs = ~0ull, R = 0;      // next record that starts in the tile: right after the 4th newline of its predecessor
+        if (lane == 0) {
+            if (stream_start) gs = 0;
+            else
+                while (pos < end) {
+                    const bool nl = pos == a.nbytes || a.buf[pos] == '\n';
+                    pos++;
+                    if (nl && ((++lines) & 3ull) == 0 && pos < c.stream_len) { gs = pos; R = lines >> 2; break; }
+                }
+        }
+        stream_start = false;
+        gs = __shfl_sync(kFullMask, gs, 0);
+        R = __shfl_sync(kFullMask, R, 0);
+        if (gs == ~0ull) break;
+        RecOut o;
+        if (lane == 0) o = eval_record_global<TIER>(a, ev, c, gs);
+        selected += commit_records(a, c.T0, c.want_idh, o, lane == 0, R, lane);
+    }
+    return selected;
 }
 
 // Tiles with more newlines than the list holds (records of a few bytes: the reference's own test fixtures): several windows
@@ -499,7 +608,7 @@ __device__ __noinline__ uint32_t dense_tile(const FastqArgs& a, const RecordEval
                 o = eval_record<TIER>(a, ev, c, s, r0, win_lo);
                 finish_names<TIER>(ev, o);
             }
-            selected += commit_records(a, c, o, valid, ph.R_base + k0, lane);
+            selected += commit_records(a, c.T0, c.want_idh, o, valid, ph.R_base + k0, lane);
         }
         __syncwarp();       // every lane is done with the list before the next window overwrites it
         if (win_lo + kWindowStep >= agg) break;
@@ -508,12 +617,12 @@ __device__ __noinline__ uint32_t dense_tile(const FastqArgs& a, const RecordEval
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
-// blockDim = (tile warps + 1) x 32: the last warp of CTA 0 is the scan warp (see Lookback), the last warp of every other CTA
-// leaves at once.
+// Every warp of the grid is a tile warp, except the last warp of CTA 0: that one is the scan warp (see Lookback) and owns
+// no tiles.  (An extra warp per CTA for it would push the CTA past 512 threads and cost every thread 32 registers.)
 template <int TIER>
-__global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+__global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, tile_warps = (blockDim.x >> 5) - 1u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, cta_warps = blockDim.x >> 5;
 
     // ---- smem carve-up: [automaton][class LUT 256][per-warp regions]
     uint8_t* s_tab = smem;
@@ -522,13 +631,14 @@ __global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, Device
     const uint32_t bar = smem_addr(s_warp), list_sa = bar + kWarpListOff, tile_sa = bar + kWarpTileOff;
 
     stage_automaton<TIER>(dfa, s_tab, s_cls);
-    if (lane == 0 && warp < tile_warps) mbar_init(bar, 1);
+    if (lane == 0) mbar_init(bar, 1);
     mbar_fence_init();
     __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
 
     const Lookback lb{reinterpret_cast<uint32_t*>(a.tile_state), a.seg_acc, a.seg_pre};
-    if (warp == tile_warps) {
-        if (blockIdx.x == 0) scan_segments(lb, a.tile_first, a.tile_first + a.tile_count, lane);
+    const uint32_t scan_warp = cta_warps - 1u;      // of CTA 0
+    if (blockIdx.x == 0 && warp == scan_warp && a.scan_warp) {
+        scan_segments(lb, a.tile_first, a.tile_first + a.tile_count, lane);
         return;
     }
 
@@ -544,32 +654,82 @@ __global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, Device
     const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
     uint32_t phase = 0;
     unsigned long long local_count = 0;
+    long long t_copy = 0, t_prefix = 0, t_seg = 0, t_all = a.stats ? clock64() : 0;      // measurement hook (FQG_FASTQ_STATS): cycles spent waiting
 
-    // Tiles are dealt out statically, in order: global warp w takes tiles w, w + W, w + 2W, ... of the launch (W = tile warps
-    // of the grid).  Every warp publishes the newline count of its tile without waiting for anything and only then may wait
-    // for earlier tiles, so the earliest unfinished tile can always finish.  (Rounds 1-2 claimed tiles from an atomic
-    // counter: 3.5 % of all stall samples sat on that round trip and 25 instructions per tile went into it, profiles/r2h_*.)
-    const uint32_t W = gridDim.x * tile_warps;
-    for (uint32_t claim = blockIdx.x * tile_warps + warp; claim < a.tile_count; claim += W) {
-        const TileGeom g = tile_geom(a, a.tile_first + claim, stream_len);
-        c.T0 = g.T0;
-        if (lane == 0) {
-            if (g.real_avail) {
-                const uint32_t bytes = (g.real_avail + 15u) & ~15u;
+    // Tiles are claimed in order from an atomic counter.  (Dealing them out statically -- warp w takes tiles w, w + W, ... --
+    // saves the atomic but was measured slower: warps do not run at the same speed (the issue arbiter prefers high warp ids,
+    // one SM also hosts the scan warp), a tile needs the counts of ALL earlier tiles, and with a fixed deal everybody ends up
+    // waiting for the slowest warp's tiles: 15 % of all warp cycles in the match kernel, 34 % in the index-only kernel,
+    // FQG_FASTQ_STATS.  With claims, slow warps simply take fewer tiles.)  The claim for the next tile is issued just before
+    // this tile's records are walked -- after the only place where the warp may wait for other tiles (step 7) -- and picked up
+    // after the walk, so its round trip is hidden and the warp never waits while it holds a tile it has not started.
+    const uint32_t W = gridDim.x * cta_warps - a.scan_warp;      // tile warps of the grid
+    // Starts the copy of tile `cl` of this launch into the warp's buffer (the buffer must be free) and pulls the tile after it
+    // into L2 (126 MB; a wave of tiles is ~25 MB), so that one's copy will only pay L2 latency: a warp has a single tile
+    // buffer, hence no other way to keep HBM busy.
+    auto issue_tile = [&](uint32_t cl) {
+        if (lane == 0 && cl < a.tile_count) {
+            const uint32_t tn = a.tile_first + cl, avail_n = tile_real_avail(a, tn);
+            if (avail_n) {
+                const uint32_t bytes = (avail_n + 15u) & ~15u;
                 mbar_arrive_expect_tx(bar, bytes);
-                bulk_copy_g2s(tile_sa, a.buf + g.T0, bytes, bar);
+                bulk_copy_g2s(tile_sa, a.buf + (uint64_t)tn * kTile, bytes, bar);
             }
-            // This warp's NEXT tile is pulled into L2 (126 MB; a wave of tiles is ~25 MB) while this one is worked on, so its
-            // copy only pays L2 latency.  A warp has a single tile buffer, hence no other way to keep HBM busy.
-            const uint32_t ahead = claim + W;
-            if (ahead < a.tile_count) {
-                const TileGeom ga = tile_geom(a, a.tile_first + ahead, stream_len);
-                if (ga.real_avail) bulk_prefetch_l2(a.buf + ga.T0, (ga.real_avail + 15u) & ~15u);
+            if (cl + W < a.tile_count) {
+                const uint32_t ta = tn + W, avail_a = tile_real_avail(a, ta);
+                if (avail_a) bulk_prefetch_l2(a.buf + (uint64_t)ta * kTile, (avail_a + 15u) & ~15u);
             }
         }
+    };
+    // Results of the previous tile that still wait for their global record numbers (see step 7 in the loop).
+    bool pend = false, p_valid = false, p_last = false;
+    RecOut po;
+    uint32_t p_t = 0, p_agg = 0, p_j0 = 0;
+    LookbackPre p_pre{0u, 0ull};
+    auto complete_pending = [&]() {
+        if (!pend) return;
+        pend = false;
+        const long long t0 = a.stats ? clock64() : 0;
+        const unsigned long long Lp = lookback_resolve(lb, p_t, lane, p_pre, a.stats ? &t_seg : nullptr);
+        if (a.stats) t_prefix += clock64() - t0;
+        if (3u - (uint32_t)(Lp & 3ull) != p_j0) {      // damaged input only
+            if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+            local_count += redo_tile_global<TIER>(a, ev, c, p_t, Lp, lane);
+        } else {
+            local_count += commit_records(a, (uint64_t)p_t * kTile, c.want_idh, po, p_valid, (Lp + p_j0 + 1ull) >> 2, lane);
+        }
+        if (lane == 0 && p_last) *a.lines_out = Lp + p_agg;
+    };
+    uint32_t claim = 0, next_claim = 0;
+    if (lane == 0) claim = atomicAdd(a.tile_counter, 1u);
+    claim = __shfl_sync(kFullMask, claim, 0);
+    issue_tile(claim);
+    bool claimed = false;
+    auto claim_next = [&]() {      // warp-uniform; issued once per tile, the value is picked up by take_next
+        if (!claimed && lane == 0) next_claim = atom_add_u32(a.tile_counter, 1u);
+        claimed = true;
+    };
+    auto take_next = [&]() {
+        claim_next();
+        claimed = false;
+        return __shfl_sync(kFullMask, next_claim, 0);
+    };
+    while (claim < a.tile_count) {
+        const TileGeom g = tile_geom(a, a.tile_first + claim, stream_len);
+        c.T0 = g.T0;
+        // The copy of the NEXT tile is started as soon as the last record of this one has been walked (the prefix is resolved
+        // and the results are committed from registers while it travels): 7.6 % of all stall samples used to sit on this wait
+        // (profiles/r2j_*).
+        bool next_issued = false;
+        // The prefix words of the pending tile are requested here -- its count went out most of a tile-time ago, so they have
+        // been published by now (asked for right after its own count they never were: every resolve then paid a second L2
+        // round trip) -- and consumed in step 7, after this tile's bytes have been scanned.
+        if (pend) p_pre = lookback_prefetch(lb, p_t, lane);
         if (g.real_avail) {
+            const long long t0 = a.stats ? clock64() : 0;
             mbar_wait(bar, phase);       // try_wait suspends the warp in hardware; no issue slots are burnt
             phase ^= 1u;
+            if (a.stats) t_copy += clock64() - t0;
         }
 
         // ---- 2. newline masks of this lane's 336 bytes, in registers
@@ -616,7 +776,9 @@ __global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, Device
 
         if (a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
         if (total > kListCap) {
+            complete_pending();
             const unsigned long long Lt = lookback_resolve(lb, g.t, lane, no_pre);
+            claim_next();
             if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
             LaneWords mw;
 #pragma unroll
@@ -659,15 +821,13 @@ __global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, Device
             //         (mod 4), which is only known once every earlier tile has been scanned.  Instead of waiting, the phase
             //         is GUESSED from the tile itself: lanes 0..7 test, for the four candidates and the first two records
             //         each, "starts with '@', '+' two lines on, equal lengths".  One surviving candidate = the guess; the
-            //         records are evaluated under it into registers, the prefix is resolved afterwards (by then its inputs
-            //         are there) and only a confirmed guess is committed.  A wrong or impossible guess costs a second pass,
-            //         never a wrong answer.
+            //         records are evaluated under it into registers and only a confirmed guess is committed (step 7).  A
+            //         wrong or impossible guess costs a second look, never a wrong answer.
             unsigned long long Lt = 0;
-            bool have_Lt = false;
+            bool have_Lt = g.t == 0, guessed = false;          // nothing precedes the first tile
             uint32_t j0 = 3u;
             LookbackPre pre = no_pre;
-            if (g.t == 0) have_Lt = true;          // nothing precedes the first tile
-            else {
+            if (!have_Lt) {
                 bool ok = false;
                 const uint32_t cand = lane & 3u, r = cand + 4u * (lane >> 2);      // boundary newline rank under this candidate
                 if (lane < 8u && r + 4u < total) {
@@ -679,57 +839,90 @@ __global__ void __launch_bounds__(576, 1) match_fastq_kernel(FastqArgs a, Device
                 const uint32_t votes = __ballot_sync(kFullMask, ok);
                 const uint32_t both = votes & (votes >> 4) & 0xFu;              // candidates whose first AND second record look right
                 if (both && (both & (both - 1u)) == 0) {
+                    guessed = true;
                     j0 = (uint32_t)__ffs((int)both) - 1u;
                     if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
-                    pre = lookback_prefetch(lb, g.t, lane);      // consumed after the record phase
-                } else {
-                    Lt = lookback_resolve(lb, g.t, lane, no_pre);
-                    have_Lt = true;
-                    j0 = 3u - (uint32_t)(Lt & 3ull);
                 }
             }
+            // ---- 7 (of the PREVIOUS tile).  Its records were evaluated under a guess and wait in registers.  By now this
+            //         tile's count has been published and its bytes scanned -- a good third of a tile-time after the previous
+            //         tile was walked -- so the prefix of the previous tile is there without waiting: confirm its guess, commit.
+            //         (Resolving right after the walk made the warps wait 8 % of their time in the match kernel and 25 % in
+            //         the index-only kernel, FQG_FASTQ_STATS.)
+            if (TIER != 5 || have_Lt || !guessed) complete_pending();      // (index-only: later still, see below)
+            if (!have_Lt && !guessed) {      // no usable guess (no two whole records in the tile, or ambiguous): wait for the prefix
+                Lt = lookback_resolve(lb, g.t, lane, no_pre);
+                have_Lt = true;
+                j0 = 3u - (uint32_t)(Lt & 3ull);
+            }
+            claim_next();      // nothing below waits for another tile (except a guess that covers more than 32 records)
             // ---- 6. one lane per record that starts in the tile
-            for (;;) {
-                TilePhase ph = tile_phase(g, j0, Lt, agg, stream_len);
-                bool redo = false;
-                for (uint32_t k0 = 0; k0 < ph.n_list; k0 += 32u) {
+            const bool last_tile = g.T0 + g.region == stream_len;
+            TilePhase ph = tile_phase(g, j0, Lt, agg, stream_len);
+            if (!have_Lt && ph.n_list <= 32u) {
+                // the usual case: a guessed phase and at most one record per lane.  Evaluate, hand the buffer to the next
+                // tile's copy, keep the results for step 7.
+                const bool valid = lane < ph.n_list;
+                const uint32_t qa = lane < ph.extra ? 0u : ph.j0 + 4u * (lane - ph.extra);
+                RecOut o;
+                if (valid) {
+                    const uint32_t s = lane < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
+                    o = eval_record<TIER>(a, ev, c, s, lane < ph.extra ? 0u : qa + 1u, 0u);
+                }
+                finish_names<TIER>(ev, o);      // compares id bytes in the tile
+                if (FQG_EARLY_ISSUE) {
+                    __syncwarp();
+                    claim = take_next();
+                    issue_tile(claim);
+                    next_issued = true;
+                }
+                // The index-only kernel has no walk to spend between a tile's count and its prefix, so there the previous tile is
+                // settled only now, a whole tile-time after its count went out.
+                if (TIER == 5) complete_pending();
+                pend = true;
+                po = o; po.name = NamePending();      // (settled by finish_names; nothing of it is needed any more)
+                p_valid = valid; p_t = g.t; p_agg = agg; p_j0 = j0; p_last = last_tile;
+                p_pre = LookbackPre{0u, 0ull};      // requested at the top of the next iteration (or polled, after the last tile)
+            } else {
+                bool redone = false;
+                if (!have_Lt) {      // a guess, but more than 32 records start in the tile: confirm it now
+                    Lt = lookback_resolve(lb, g.t, lane, pre);
+                    have_Lt = true;
+                    if (3u - (uint32_t)(Lt & 3ull) != j0) {
+                        if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                        local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
+                        redone = true;
+                    } else ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
+                }
+                for (uint32_t k0 = 0; !redone && k0 < ph.n_list; k0 += 32u) {
                     const uint32_t k = k0 + lane;
                     const uint32_t qa = k < ph.extra ? 0u : ph.j0 + 4u * (k - ph.extra);
-                    const uint32_t r0 = k < ph.extra ? 0u : qa + 1u;
                     const bool valid = k < ph.n_list;
                     RecOut o;
                     if (valid) {
                         const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
-                        o = eval_record<TIER>(a, ev, c, s, r0, 0u);
-                    }
-                    if (!have_Lt) {
-                        Lt = lookback_resolve(lb, g.t, lane, pre);
-                        have_Lt = true;
-                        const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
-                        if (exact != j0) {
-                            if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
-                            j0 = exact;
-                            redo = true;
-                            break;
-                        }
-                        ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
+                        o = eval_record<TIER>(a, ev, c, s, k < ph.extra ? 0u : qa + 1u, 0u);
                     }
                     finish_names<TIER>(ev, o);
-                    local_count += commit_records(a, c, o, valid, ph.R_base + k0, lane);
+                    local_count += commit_records(a, c.T0, c.want_idh, o, valid, ph.R_base + k0, lane);
                 }
-                if (!redo && !have_Lt) {      // no record starts in the tile under the guess: the guess still has to be confirmed
-                    Lt = lookback_resolve(lb, g.t, lane, pre);
-                    have_Lt = true;
-                    const uint32_t exact = 3u - (uint32_t)(Lt & 3ull);
-                    if (exact != j0) { j0 = exact; redo = true; }
-                }
-                if (!redo) break;
+                if (lane == 0 && last_tile) *a.lines_out = Lt + agg;
             }
-            if (lane == 0 && g.T0 + g.region == stream_len) *a.lines_out = Lt + agg;
         }
-        __syncwarp();       // every lane is done with the list and the tile before the next bulk copy overwrites them
+        if (!next_issued) {
+            __syncwarp();       // every lane is done with the list and the tile before the next bulk copy overwrites them
+            claim = take_next();
+            issue_tile(claim);
+        }
     }
+    complete_pending();
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
+    if (a.stats && lane == 0) {
+        atomicAdd(a.stats + 4, (unsigned long long)t_copy);
+        atomicAdd(a.stats + 5, (unsigned long long)t_prefix);
+        atomicAdd(a.stats + 7, (unsigned long long)t_seg);
+        atomicAdd(a.stats + 6, (unsigned long long)(clock64() - t_all));
+    }
 }
 
 // pair rule (src/main.rs:749-755) for mates in two streams: unit mask = m1 | m2; ids must agree (:741-747).
@@ -786,24 +979,29 @@ __global__ void combine_interleaved_kernel(const uint32_t* m, uint32_t* out, uin
 }
 
 template <int TIER>
-cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& a, int sm_count, cudaStream_t stream) {
+cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& args, int sm_count, cudaStream_t stream) {
+    FastqArgs a = args;
+    if (a.tile_count == 0) return cudaSuccess;
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
     uint32_t warps = (budget - table_smem - 256u - 128u) / kWarpBytes;      // one tile buffer per warp
-    if (warps > 17u) warps = 17u;
+    if (warps > kMaxTileWarps) warps = kMaxTileWarps;
     if (warps < 1u) warps = 1u;
-    if (a.tile_count < (uint32_t)sm_count * warps) {          // small inputs: spread the tiles over the SMs first
-        warps = (a.tile_count + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
+    // the scan warp is only there when this launch completes a segment of 32 tiles (see Lookback)
+    a.scan_warp = ((a.tile_first + a.tile_count) >> 5) > (a.tile_first >> 5) ? 1u : 0u;
+    const uint32_t need = a.tile_count + a.scan_warp;         // warps that find work
+    if (need < (uint32_t)sm_count * warps) {                  // small inputs: spread the tiles over the SMs first
+        warps = (need + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
         if (warps < 1u) warps = 1u;
     }
+    if (a.scan_warp && warps < 2u && kMaxTileWarps >= 2u && need < 2u * (uint32_t)sm_count) warps = need < 2u ? 2u : warps;
     const uint32_t smem = table_smem + 256u + warps * kWarpBytes;
     auto kern = match_fastq_kernel<TIER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    uint32_t grid = (a.tile_count + warps - 1u) / warps;
+    uint32_t grid = (need + warps - 1u) / warps;
     if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-    if (grid == 0) return cudaSuccess;
-    kern<<<grid, (warps + 1u) * 32u, smem, stream>>>(a, dfa, table_smem);      // + the scan warp
+    kern<<<grid, warps * 32u, smem, stream>>>(a, dfa, table_smem);
     return cudaGetLastError();
 }
 

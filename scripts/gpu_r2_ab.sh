@@ -1,15 +1,12 @@
 #!/bin/bash
-# A/B of fused-kernel switches on the raw-FASTQ-resident leg (device-event timed), no ncu.
+# A/B of kernel-parameter variants of the library inside one GPU call (variants built beforehand with build.build_variant)
 TAG=${1:-ab}
-CMD="python bench.py --pairs 1000000 --steps 6 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --raw-pairs 20000000"
-timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1 || { echo "SMOKE FAILED"; tail -30 gpurun_out/smoke_$TAG.log; exit 1; }
-for V in 0 1; do
-  FQG_FASTQ_EARLY_CLAIM=$V FQG_FASTQ_STATS=1 timeout 300 $CMD > gpurun_out/ab_${TAG}_early$V.json 2> gpurun_out/ab_${TAG}_early$V.err
-  echo "early_claim=$V"; python - <<PY
-import json
-d=json.load(open("gpurun_out/ab_${TAG}_early$V.json"))
-r=d["raw_fastq_resident"]; print(r.get("value"), r.get("ms_per_step"), r.get("roofline",{}).get("frac"), r.get("error"))
-print(d["sharded"])
-PY
-  grep "fused kernel" gpurun_out/ab_${TAG}_early$V.err | sort | uniq -c | sort -rn | head -4
+CMD="python bench.py --pairs 1000000 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --raw-pairs 8000000"
+for so in "" $(ls fqgrep_b200/libfqgrep_b200_*.so); do
+  for rep in 1 2; do
+    FQG_LIB_VARIANT=${so:+$PWD/$so} timeout 300 $CMD 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['raw_fastq_resident']
+print('${so:-default}', 'raw', round(r.get('value',0),1), round(r.get('roofline',{}).get('frac',0),4), 'selected', r.get('selected'), r.get('error'))"
+  done
 done
