@@ -10,24 +10,30 @@
 //
 // Shape: WARP-AUTONOMOUS TILES.  The byte stream is cut into tiles of 29 x 336 = 9744 bytes.  Every warp of the
 // persistent grid runs the whole tile loop on its own, with no CTA-wide barrier after start-up:
-//   1. claim the next tile id from an atomic counter (in order), pull tile + 1008 bytes of overlap into the warp's own
-//      shared-memory buffer with ONE bulk async copy (TMA, completion on the warp's mbarrier);
+//   1. the tile (claimed in order from an atomic counter one step earlier, see 6) + 1008 bytes of overlap arrive in the
+//      warp's own shared-memory buffer by ONE bulk async copy (TMA, completion on the warp's mbarrier); the tile one wave
+//      ahead is pulled into L2 at the same time (a warp has a single buffer);
 //   2. newline masks: lane l owns the 336 bytes [336 l, 336 l + 336) of the buffer -- 21 LDS.128 at a lane stride of 21
 //      16-byte units, which is bank-conflict free because 21 is odd -- and turns them into 11 bitmap words held in
 //      REGISTERS (exact per-byte test in 3 integer ops per word, bits gathered by IDP.4A);
-//   3. popcounts -> warp scan -> the tile's newline count is published for the decoupled look-back;
+//   3. popcounts -> warp scan -> the tile's newline count is published (per-tile word + an atomic add into its segment of 32
+//      tiles; ONE warp of the grid, the scan warp, turns complete segments into running prefixes, see Lookback);
 //   4. every newline's position is scattered into a small shared list at its rank (so line k of the tile is list[k]);
 //   5. the line phase (line number mod 4 of the tile's first byte) is guessed from the tile's own first records;
-//   6. lane k takes record k of the tile: five list entries give the record start and its four line ends, the
-//      record is validated by seq_io's rules and its sequence line is walked through the DFA straight out of shared
-//      memory (or its id probed in the name table), results held in registers;
-//   7. the look-back (two levels, see lookback_resolve) yields the global line number of the tile's first byte -- by now
-//      its inputs have long been published, so it does not wait; it confirms the guess (else step 6 runs again) and
-//      gives the global record number of the tile's first record; ballot -> atomicOr into the global record bitmask.
-// Records that do not end inside tile + overlap (reads longer than ~400 bases) are walked in global memory.
-// Round 1's kernel shared one 19 KB tile between the four warps of a "tile group" and needed four group barriers, a
-// shared bitmap, a binary search per record and a bit-scan per line end: 80 warp-instructions per record and 8.9 barrier
-// stalls per issue (profiles/r1zz_match_fastq_ncu_full.txt); this shape does the same work in about half the instructions.
+//   6. the next tile is claimed (the atomic's round trip hides behind the walk); lane k takes record k of the tile: five list
+//      entries give the record start and its four line ends, the record is validated by seq_io's rules and its sequence line
+//      is walked through the DFA straight out of shared memory, results held in registers; the moment the last record is
+//      walked the buffer is handed to the next tile's copy;
+//   7. ONE TILE LATER -- after steps 1-5 of the next tile, i.e. when every earlier tile has long reported -- the number of
+//      newlines before the tile is read (one 64-bit word + the counts of at most 31 tiles of its own segment, both requested
+//      at the top of that iteration), the guess is confirmed and the results are committed: ballot -> atomicOr into the
+//      global record bitmask, id hashes, spans.  A wrong guess (damaged input only) is re-done from global memory.
+// Records that do not end inside tile + overlap (reads longer than ~400 bases) are walked in global memory.  Read-name
+// lookups (-N) settle their tile at once instead (their id bytes live in the tile), the index-only kernel defers by a whole
+// tile.  Round 1's kernel shared one 19 KB tile between the four warps of a "tile group" and needed four group barriers, a
+// shared bitmap, a binary search per record and a bit-scan per line end: 80 warp-instructions per record, 8.9 barrier stalls
+// per issue, 0.35 of the raw-FASTQ roofline (profiles/r1zz_match_fastq_ncu_full.txt); this one runs at 0.59-0.62 (match) and
+// 0.75 (index only) with 62 warp-instructions per record (profiles/r3*).
 #include <cstdlib>
 
 #include "dfa_device.cuh"
@@ -842,6 +848,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                     guessed = true;
                     j0 = (uint32_t)__ffs((int)both) - 1u;
                     if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
+                    if (TIER == 3) pre = lookback_prefetch(lb, g.t, lane);      // read names settle their tile at once, see step 6
                 }
             }
             // ---- 7 (of the PREVIOUS tile).  Its records were evaluated under a guess and wait in registers.  By now this
@@ -869,7 +876,21 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                     const uint32_t s = lane < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
                     o = eval_record<TIER>(a, ev, c, s, lane < ph.extra ? 0u : qa + 1u, 0u);
                 }
-                finish_names<TIER>(ev, o);      // compares id bytes in the tile
+                if (TIER == 3) {
+                    // Read names: a lookup is two dependent L2 / HBM round trips (bucket, then the stored id), and the id bytes it
+                    // is compared with sit in the tile, so nothing is deferred here: the prefix is resolved while the buckets
+                    // travel, then the lookups are finished and committed, then the buffer goes to the next copy.
+                    Lt = lookback_resolve(lb, g.t, lane, pre);
+                    have_Lt = true;
+                    if (3u - (uint32_t)(Lt & 3ull) != j0) {
+                        if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                        local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
+                    } else {
+                        finish_names<TIER>(ev, o);
+                        local_count += commit_records(a, c.T0, c.want_idh, o, valid, (Lt + j0 + 1ull) >> 2, lane);
+                    }
+                    if (lane == 0 && last_tile) *a.lines_out = Lt + agg;
+                } else {
                 if (FQG_EARLY_ISSUE) {
                     __syncwarp();
                     claim = take_next();
@@ -883,6 +904,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 po = o; po.name = NamePending();      // (settled by finish_names; nothing of it is needed any more)
                 p_valid = valid; p_t = g.t; p_agg = agg; p_j0 = j0; p_last = last_tile;
                 p_pre = LookbackPre{0u, 0ull};      // requested at the top of the next iteration (or polled, after the last tile)
+                }
             } else {
                 bool redone = false;
                 if (!have_Lt) {      // a guess, but more than 32 records start in the tile: confirm it now
