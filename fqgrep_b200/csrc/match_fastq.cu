@@ -862,7 +862,9 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 have_Lt = true;
                 j0 = 3u - (uint32_t)(Lt & 3ull);
             }
-            claim_next();      // nothing below waits for another tile (except a guess that covers more than 32 records)
+            // (the claim must not be outstanding while the warp waits for other tiles: read names and guesses that cover more
+            // than 32 records resolve their prefix below and claim after that)
+            if (have_Lt || TIER != 3) claim_next();
             // ---- 6. one lane per record that starts in the tile
             const bool last_tile = g.T0 + g.region == stream_len;
             TilePhase ph = tile_phase(g, j0, Lt, agg, stream_len);
@@ -882,6 +884,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                     // travel, then the lookups are finished and committed, then the buffer goes to the next copy.
                     Lt = lookback_resolve(lb, g.t, lane, pre);
                     have_Lt = true;
+                    claim_next();
                     if (3u - (uint32_t)(Lt & 3ull) != j0) {
                         if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
                         local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);

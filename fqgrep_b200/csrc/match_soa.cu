@@ -448,6 +448,10 @@ cudaError_t launch_t(const DeviceDfa& dfa, const SoaBatch& b, int sm_count, cuda
 // are contiguous, so its loads share cache lines); the table probe is one random 8-byte L2 read per read.
 // Algorithmic bytes per read: header + 4 (offset) + 8 (one slot) + 1/8 (result).
 namespace {
+// (A software pipeline over the chain offsets -> header -> bucket -> stored id -- every iteration consumes what the previous
+// one asked for and asks for the next link of four different batches, header bytes re-read from L1 -- was built and measured
+// in round 2 as well: 61 Greads/s against 82 for this kernel.  The lookup is bound by instruction issue as much as by
+// latency (8.4 warp-instructions per read, issue slots 62 % busy), and the pipeline's bookkeeping costs more than it hides.)
 // (Four reads per thread run stage by stage -- all offset loads, all header loads, all bucket loads in flight together -- was
 // built and measured in round 2: 46 Greads/s against 80 for this kernel, because its 73 registers left room for three
 // blocks per SM instead of eight; the loads in flight per SM went DOWN.  Removed.)
