@@ -11,6 +11,11 @@ __device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {      // (tables: constant for the lifetime of the kernel)
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     uint32_t v;   // zero-extended straight into a 32-bit register: no 16-bit register shuffling in the hot loop
     asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
@@ -52,6 +57,9 @@ struct DfaView {
     // tiers 1, 2, 4: when the automaton has a dead state (^-anchored sets), a read is decided once its state is the dead
     // or the all-accepting one, usually after a few bases; settle != 0 makes the walk stop there (kernels.hpp)
     uint32_t settled_a = 0xFFFFFFFFu, settled_b = 0xFFFFFFFFu, settle = 0;
+    // packed tiers, fused FASTQ kernel only: shared address of a 256-entry table "the four letters these four codes stand
+    // for" (see step4_acgt<true>)
+    uint32_t etab = 0;
 
     __device__ __forceinline__ uint32_t step1(uint32_t st, uint32_t byte) const {
         if (TIER == 0) return lds_u16(st + 512u + lds_u8(cls + byte));
@@ -72,11 +80,21 @@ struct DfaView {
     //   code  x = (byte >> 1) & 3           A=0 C=1 T=2 G=3
     //   byte & ~6 is 0x41 for A,C,G and 0x50 for T  =>  ((byte & ~6) ^ 0x41) must equal 0x11 * [code == 2]
     //   index = c3 | c2<<2 | c1<<4 | c0<<6 (times two, byte offset) = (x * 0x40100401) >> 23; bit 0 is provably clear
+    // ETAB: the exact "is this word pure ACGT" test as ONE more table lookup instead of arithmetic: the 8-bit code index
+    // that selects the transition also selects the word the four letters must spell (etab), so bad |= w ^ etab[index] --
+    // 2 ALU + 1 LDS instead of 4 ALU + 1 IMAD per word.  Right for the fused FASTQ kernel, which is bound by integer issue
+    // with shared memory at 47 % of its wavefront peak; wrong for the SoA kernel, which sits at 86 % of it.
+    template <bool ETAB = false>
     __device__ __forceinline__ uint32_t step4_acgt(uint32_t st, uint32_t w, uint32_t& bad) const {
         const uint32_t x = (w >> 1) & 0x03030303u;
-        const uint32_t t = (x >> 1) & ~x & 0x01010101u;
-        bad |= ((w & 0xF9F9F9F9u) ^ 0x41414141u) ^ (t * 0x11u);
-        const uint32_t idx2 = (x * 0x40100401u) >> 23;                       // packed codes of the word, times two
+        const uint32_t prod = x * 0x40100401u;                               // packed codes of the word in bits 24..31 (22, 23 clear)
+        if (ETAB) {
+            bad |= w ^ lds_u32(etab + (prod >> 22));
+        } else {
+            const uint32_t t = (x >> 1) & ~x & 0x01010101u;
+            bad |= ((w & 0xF9F9F9F9u) ^ 0x41414141u) ^ (t * 0x11u);
+        }
+        const uint32_t idx2 = prod >> 23;                                    // packed codes, times two
         if (TIER == 4) {                                                     // tier 4: rows of 16 two-base entries
             st = lds_u16(st + ((idx2 >> 4) & 0x1Eu));                        // first two bases
             return lds_u16(st + (idx2 & 0x1Eu));                             // last two bases
@@ -84,6 +102,20 @@ struct DfaView {
         return lds_u16(st + idx2);
     }
 };
+
+// etab[e] for e = c0 << 6 | c1 << 4 | c2 << 2 | c3 (c0 = the first of the four bases = the low byte of the word):
+// the little-endian word of the letters the codes stand for (A=0 C=1 T=2 G=3)
+__device__ __forceinline__ void stage_etab(uint32_t* s_etab, uint32_t tid, uint32_t nthreads) {
+    for (uint32_t e = tid; e < 256u; e += nthreads) {
+        uint32_t word = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; k++) {
+            const uint32_t c = (e >> (6u - 2u * k)) & 3u;
+            word |= (c == 0u ? 0x41u : c == 1u ? 0x43u : c == 2u ? 0x54u : 0x47u) << (8u * k);
+        }
+        s_etab[e] = word;
+    }
+}
 
 // Copies a tier-0/1 table into shared memory, turning row offsets into absolute shared addresses.
 // The table sits at the start of dynamic shared memory and is < 62 KB, so addresses fit 16 bits.
@@ -114,7 +146,7 @@ __device__ __noinline__ uint32_t walk_shared_bytes(const DfaView<TIER>& d, uint3
 // walk `len` bytes starting at shared address p (any alignment)
 // SETTLE: leave the walk once the state is the dead or the all-accepting one (only instantiated where the automaton
 // has a dead state: the check costs a crossbar-bound loop like tier 4's 20 % when it sits there unused)
-template <int TIER, bool SETTLE>
+template <int TIER, bool SETTLE, bool ETAB = false>
 __device__ __forceinline__ uint32_t walk_shared_impl(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st0) {
     const uint32_t sh = (p & 3u) * 8u;
     uint32_t wp = p & ~3u;
@@ -127,7 +159,7 @@ __device__ __forceinline__ uint32_t walk_shared_impl(const DfaView<TIER>& d, uin
         const uint32_t w1 = lds_u32_volatile(wp);
         const uint32_t w = __funnelshift_r(w0, w1, sh);
         w0 = w1;
-        if (kPackedCodes<TIER>) st = d.step4_acgt(st, w, bad);
+        if (kPackedCodes<TIER>) st = d.template step4_acgt<ETAB>(st, w, bad);
         else {
             st = d.step1(st, w & 0xFFu);
             st = d.step1(st, (w >> 8) & 0xFFu);
@@ -148,10 +180,10 @@ __device__ __forceinline__ uint32_t walk_shared_impl(const DfaView<TIER>& d, uin
     return st;
 }
 
-template <int TIER>
+template <int TIER, bool ETAB = false>
 __device__ __forceinline__ uint32_t walk_shared(const DfaView<TIER>& d, uint32_t p, uint32_t len, uint32_t st0) {
-    if (TIER != 0 && d.settle) return walk_shared_impl<TIER, true>(d, p, len, st0);      // warp-uniform choice
-    return walk_shared_impl<TIER, false>(d, p, len, st0);
+    if (TIER != 0 && d.settle) return walk_shared_impl<TIER, true, ETAB>(d, p, len, st0);      // warp-uniform choice
+    return walk_shared_impl<TIER, false, ETAB>(d, p, len, st0);
 }
 
 // fallback for reads that do not fit the shared-memory staging (very long reads): straight from global memory

@@ -46,6 +46,12 @@ namespace {
 #ifndef FQG_UNITS
 #define FQG_UNITS 21
 #endif
+// FQG_ETAB=1: the walk's exact ACGT check as a table lookup (dfa_device.cuh, step4_acgt<true>) instead of arithmetic.  Measured
+// on B200 (A/B of two builds in one call): 0.553 with it against 0.557 without -- two integer instructions saved per word, one
+// more conflict-prone LDS and 58 bytes of spills paid.  Off.
+#ifndef FQG_ETAB
+#define FQG_ETAB 0
+#endif
 #ifndef FQG_EARLY_ISSUE
 #define FQG_EARLY_ISSUE 1
 #endif
@@ -66,6 +72,8 @@ constexpr uint32_t kWarpListOff = 128u, kWarpTileOff = kWarpListOff + 2u * kList
 constexpr uint32_t kWarpBytes = kWarpTileOff + kLoad + 128u;
 static_assert(kWarpBytes % 128u == 0 && kWarpTileOff % 128u == 0, "TMA destination alignment");
 // tile warps that fit 227 KB of shared memory next to the smallest automaton; the register budget follows from it (launch bounds)
+template <int TIER>
+constexpr uint32_t kEtabBytes = (kPackedCodes<TIER> && FQG_ETAB) ? 1024u : 0u;
 constexpr uint32_t kSmemWarps = (227u * 1024u - 256u - 1024u) / kWarpBytes;
 // (17 would fit next to a tiny table, but a CTA of more than 512 threads leaves every thread 96 registers instead of 128)
 constexpr uint32_t kMaxTileWarps = kSmemWarps > 16u && kSmemWarps < 20u ? 16u : kSmemWarps;
@@ -214,7 +222,7 @@ struct RecordEval {
         bool found;
         if (TIER == 5) found = false;
         else if (TIER == 3) { *pending = names.start_shared(tile + s + 1, id_len); return false; }      // decided by finish_names
-        else found = walk_shared(view, tile + p0 + 1, seq_len, start) >= accept_from;
+        else found = walk_shared<((TIER != 3 && TIER != 5) ? TIER : 0), kPackedCodes<TIER> && FQG_ETAB>(view, tile + p0 + 1, seq_len, start) >= accept_from;
         return found != invert;
     }
     __device__ __noinline__ bool eval_global(const uint8_t* head, uint32_t head_len, const uint8_t* seq, uint32_t seq_len, unsigned long long* idh, bool want_idh) const {
@@ -630,13 +638,15 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, cta_warps = blockDim.x >> 5;
 
-    // ---- smem carve-up: [automaton][class LUT 256][per-warp regions]
+    // ---- smem carve-up: [automaton][class LUT 256][letters-of-codes table 1024, packed tiers][per-warp regions]
     uint8_t* s_tab = smem;
     uint8_t* s_cls = smem + table_smem_bytes;
-    uint8_t* s_warp = s_cls + 256 + (size_t)warp * kWarpBytes;
+    uint32_t* s_etab = reinterpret_cast<uint32_t*>(s_cls + 256);
+    uint8_t* s_warp = s_cls + 256 + kEtabBytes<TIER> + (size_t)warp * kWarpBytes;
     const uint32_t bar = smem_addr(s_warp), list_sa = bar + kWarpListOff, tile_sa = bar + kWarpTileOff;
 
     stage_automaton<TIER>(dfa, s_tab, s_cls);
+    if (kPackedCodes<TIER> && FQG_ETAB) stage_etab(s_etab, threadIdx.x, blockDim.x);
     if (lane == 0) mbar_init(bar, 1);
     mbar_fence_init();
     __syncthreads();       // the only CTA-wide barrier: table staged, mbarriers initialised
@@ -648,7 +658,8 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         return;
     }
 
-    const RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
+    RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
+    ev.view.etab = smem_addr(s_etab);
     TileCtx c;
     c.tile_sa = tile_sa;
     c.list_sa = list_sa;
@@ -881,7 +892,10 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 if (TIER == 3) {
                     // Read names: a lookup is two dependent L2 / HBM round trips (bucket, then the stored id), and the id bytes it
                     // is compared with sit in the tile, so nothing is deferred here: the prefix is resolved while the buckets
-                    // travel, then the lookups are finished and committed, then the buffer goes to the next copy.
+                    // travel, then the lookups are finished, the buffer goes to the next copy and the results are committed.
+                    // (Carrying the lookup across the deferral -- bucket checked when the next tile's copy has landed, stored id
+                    // compared against the id's bytes re-read from global memory in step 7 -- was built and measured: the pending
+                    // lookup state does not fit next to the newline masks, 400-550 bytes of spills, 0.40 -> 0.23.)
                     Lt = lookback_resolve(lb, g.t, lane, pre);
                     have_Lt = true;
                     claim_next();
@@ -890,6 +904,12 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                         local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
                     } else {
                         finish_names<TIER>(ev, o);
+                        if (FQG_EARLY_ISSUE) {      // the tile's bytes are not needed any more
+                            __syncwarp();
+                            claim = take_next();
+                            issue_tile(claim);
+                            next_issued = true;
+                        }
                         local_count += commit_records(a, c.T0, c.want_idh, o, valid, (Lt + j0 + 1ull) >> 2, lane);
                     }
                     if (lane == 0 && last_tile) *a.lines_out = Lt + agg;
@@ -1009,7 +1029,7 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& args, int sm_c
     if (a.tile_count == 0) return cudaSuccess;
     const uint32_t table_smem = kSmemTable<TIER> ? ((dfa.table_bytes + 127u) & ~127u) : TIER == 2 ? ((dfa.hot_entries * 4u + 127u) & ~127u) : 0u;
     const uint32_t budget = 227u * 1024u;
-    uint32_t warps = (budget - table_smem - 256u - 128u) / kWarpBytes;      // one tile buffer per warp
+    uint32_t warps = (budget - table_smem - 256u - kEtabBytes<TIER> - 128u) / kWarpBytes;      // one tile buffer per warp
     if (warps > kMaxTileWarps) warps = kMaxTileWarps;
     if (warps < 1u) warps = 1u;
     // the scan warp is only there when this launch completes a segment of 32 tiles (see Lookback)
@@ -1020,7 +1040,7 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& args, int sm_c
         if (warps < 1u) warps = 1u;
     }
     if (a.scan_warp && warps < 2u && kMaxTileWarps >= 2u && need < 2u * (uint32_t)sm_count) warps = need < 2u ? 2u : warps;
-    const uint32_t smem = table_smem + 256u + warps * kWarpBytes;
+    const uint32_t smem = table_smem + 256u + kEtabBytes<TIER> + warps * kWarpBytes;
     auto kern = match_fastq_kernel<TIER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -212,6 +212,36 @@ def test_tiny_records_like_reference_fixtures():
     both(F.REGEX_SET, ["^A", "GG"], False, False, data, data, mode=F.PAIRED)
 
 
+def test_line_phase_guess_wrong_and_ambiguous_in_multi_tile_files():
+    """The fused kernel guesses a tile's line phase from its first two records and confirms the guess a tile later.
+    (a) One line dropped in the middle of a file of many tiles: every tile behind it guesses a phase that the line count
+        contradicts -- those tiles are walked again from global memory; the file is an error, like in the oracle, and the
+        part in front of the damage alone still gives the oracle's answer.
+    (b) Records whose lines 2 and 4 could be lines 1 and 3 ("@..", "@..", "+..", "+.."): two phases look right, no guess is
+        made; results must not depend on it.  Once with ~24 records per tile, once with ~40 (more than one per lane)."""
+    rng = random.Random(5)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(150)) for _ in range(6000)]      # ~1.9 MB, ~190 tiles
+    seqs[4000] = seqs[4000][:50] + "GACGAGATTA" + seqs[4000][60:]
+    good = fastq(seqs)
+    lines = good.split(b"\n")
+    m = F.Matcher(F.FIXED, ["GACGAGATTA"], opts(False, True))
+    for drop in (4 * 3000 + 1, 4 * 3000 + 3, 4 * 17):      # a sequence line, a quality line, a header
+        bad = b"\n".join(lines[:drop] + lines[drop + 1:])
+        with pytest.raises(O.OracleError):
+            O.Matcher(O.FIXED, ["GACGAGATTA"], False, True).grep(bad)
+        with pytest.raises(F.FqgrepError) as e:
+            m.grep_fastq(bad)
+        assert e.value.exit_code == 101
+    both(F.FIXED, ["GACGAGATTA"], False, True, good)
+    for width in (100, 60):
+        recs = []
+        for i in range(5000):
+            recs.append(b"@" + (b"%d" % i).ljust(width, b"x") + b"\n@" + b"AC"[i % 2:i % 2 + 1] * width + b"\n+" + b"z" * width + b"\n+" + b"I" * width + b"\n")
+        amb = b"".join(recs)
+        both(F.REGEX_SET, ["^@A", "C{5}$"], False, False, amb)
+        both(F.NAMES, ["%d" % i + "x" * (width - len("%d" % i)) for i in (0, 7, 4999)], False, False, amb)
+
+
 def test_malformed_fastq_is_an_error_like_the_reference_panic():
     m = F.Matcher(F.FIXED, ["AC"])
     good = fastq(["ACGT"] * 100)
