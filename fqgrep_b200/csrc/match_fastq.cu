@@ -658,8 +658,9 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         return;
     }
 
-    RecordEval<TIER> ev = make_eval<TIER>(a, dfa, s_tab, s_cls);
-    ev.view.etab = smem_addr(s_etab);
+    RecordEval<TIER> ev_init = make_eval<TIER>(a, dfa, s_tab, s_cls);
+    if (kPackedCodes<TIER> && FQG_ETAB) ev_init.view.etab = smem_addr(s_etab);
+    const RecordEval<TIER> ev = ev_init;
     TileCtx c;
     c.tile_sa = tile_sa;
     c.list_sa = list_sa;
