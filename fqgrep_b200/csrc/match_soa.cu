@@ -455,7 +455,11 @@ namespace {
 // (Four reads per thread run stage by stage -- all offset loads, all header loads, all bucket loads in flight together -- was
 // built and measured in round 2: 46 Greads/s against 80 for this kernel, because its 73 registers left room for three
 // blocks per SM instead of eight; the loads in flight per SM went DOWN.  Removed.)
-__global__ void __launch_bounds__(256) match_names_soa_kernel(SoaBatch b, NamesView nv) {
+// eight resident CTAs of 256 threads (32 registers each): measured 77 / 85 / 95 Greads/s with 4 / 6 / 8 of them
+#ifndef FQG_NAMES_MIN_BLOCKS
+#define FQG_NAMES_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(256, FQG_NAMES_MIN_BLOCKS) match_names_soa_kernel(SoaBatch b, NamesView nv) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_batches = (b.n_reads + 31u) >> 5;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -469,22 +473,58 @@ __global__ void __launch_bounds__(256) match_names_soa_kernel(SoaBatch b, NamesV
             const uint32_t s = __ldg(b.start + r), e = __ldg(b.end + r);
             const uintptr_t a = base + s;
             const uint32_t n = e > s ? e - s : 0u;
-            // one pass: hash the header word by word until a word holds a space, which ends the id
-            uint64_t h = fqg_name_hash_init();
-            uint32_t id_len = n;
-            for (IdWords<uintptr_t, decltype(load)> it(a, n, load); it.more();) {
-                const uint32_t pos = it.pos, w = it.next(), x = w ^ 0x20202020u;
-                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);      // 0x80 where a byte is ' '
-                if (z) {                                  // (the zero padding past the end is never a space)
-                    const uint32_t k = ((uint32_t)__ffs((int)z) - 1u) >> 3;
-                    id_len = pos + k;
-                    if (k) h = fqg_name_hash_word(h, w & ((1u << (8u * k)) - 1u));
-                    break;
+            // Fast path, ids that end within the first 16 header bytes: the five aligned words that hold those bytes are
+            // requested together, the id is cut at the first space, hashed and later compared out of registers -- no loop,
+            // no second pass over the header.  (The generic word-by-word path below cost 8.4 warp-instructions per read,
+            // a third of them iterator bookkeeping, profiles/r2h_names_soa_ncu.txt.)
+            const uint32_t n16 = n < 16u ? n : 16u, sh = (uint32_t)(a & 3u) * 8u, span = (uint32_t)(a & 3u) + n16;
+            const uintptr_t wp = a & ~uintptr_t(3);
+            uint32_t raw[5];
+#pragma unroll
+            for (uint32_t k = 0; k < 5u; k++) raw[k] = 4u * k < span ? load(wp + 4u * k) : 0u;
+            uint32_t w[4], id_len = n16;
+            bool ended = n <= 16u;      // the header itself ends within the 16 bytes
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; k++) {
+                w[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+                const uint32_t have = n16 > 4u * k ? n16 - 4u * k : 0u;      // header bytes in this word
+                const uint32_t keep = have >= 4u ? 0xFFFFFFFFu : (1u << (8u * have)) - 1u;
+                w[k] &= keep;
+                const uint32_t x = w[k] ^ 0x20202020u;
+                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu) & keep & 0x80808080u;      // 0x80 where a byte is ' '
+                if (z && id_len == n16 && 4u * k < id_len) {
+                    const uint32_t kk = 4u * k + (((uint32_t)__ffs((int)z) - 1u) >> 3);
+                    if (kk < id_len) { id_len = kk; ended = true; }
                 }
-                h = fqg_name_hash_word(h, w);
             }
-            h = fqg_name_hash_finish(h, id_len);
-            found = names_probe(nv, a, id_len, load, h);
+            if (ended) {
+                uint64_t h = fqg_name_hash_init();
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; k++) {
+                    const uint32_t have = id_len > 4u * k ? id_len - 4u * k : 0u;
+                    w[k] &= have >= 4u ? 0xFFFFFFFFu : (1u << (8u * have)) - 1u;
+                    if (have) h = fqg_name_hash_word(h, w[k]);
+                }
+                h = fqg_name_hash_finish(h, id_len);
+                found = names_probe_words(nv, w, id_len, h, names_load_bucket(nv, h));
+            } else {
+                // longer ids: hash the header word by word until a word holds a space, which ends the id
+                uint64_t h = fqg_name_hash_init();
+                id_len = n;
+                for (IdWords<uintptr_t, decltype(load)> it(a, n, load); it.more();) {
+                    const uint32_t pos = it.pos, ww = it.next(), x = ww ^ 0x20202020u;
+                    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);      // 0x80 where a byte is ' '
+                    if (z) {                                  // (the zero padding past the end is never a space)
+                        const uint32_t k = ((uint32_t)__ffs((int)z) - 1u) >> 3;
+                        id_len = pos + k;
+                        if (k) h = fqg_name_hash_word(h, ww & ((1u << (8u * k)) - 1u));
+                        break;
+                    }
+                    h = fqg_name_hash_word(h, ww);
+                }
+                h = fqg_name_hash_finish(h, id_len);
+                found = names_probe(nv, a, id_len, load, h);
+            }
         }
         const bool sel = (r < b.n_reads) && (found != (b.invert != 0));
         uint32_t m = __ballot_sync(kFullMask, sel);

@@ -82,6 +82,31 @@ __device__ __forceinline__ bool names_probe_from(const NamesView& nv, A a, uint3
         b = ulonglong4{s01.x, s01.y, s23.x, s23.y};
     }
 }
+// The same search for an id of at most 16 bytes that is already at hand as four zero-padded little-endian words: nothing
+// is read again, a stored id is compared with registers (one 16-byte read for ids of up to 12 bytes, one more word beyond).
+__device__ __forceinline__ bool names_probe_words(const NamesView& nv, const uint32_t (&w)[4], uint32_t len, uint64_t h, ulonglong4 first) {
+    const uint32_t tag = fqg_name_tag(h);
+    uint32_t bkt = fqg_name_bucket(h, nv.mask);
+    ulonglong4 b = first;
+    for (;;) {
+        const uint64_t sl[4] = {b.x, b.y, b.z, b.w};
+        bool open_end = false;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            if (sl[k] == 0) open_end = true;
+            if (!open_end && (uint32_t)(sl[k] >> 32) == tag) {
+                const uint4* q = reinterpret_cast<const uint4*>(nv.pool + (uint32_t)sl[k]);
+                const uint4 e = __ldg(q);
+                if (e.x == len && e.y == w[0] && e.z == w[1] && e.w == w[2] && (len <= 12u || __ldg(reinterpret_cast<const uint32_t*>(q + 1)) == w[3])) return true;
+            }
+        }
+        if (open_end) return false;
+        bkt = (bkt + 1u) & nv.mask;
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nv.slots) + 2u * (size_t)bkt;
+        const ulonglong2 s01 = __ldg(p), s23 = __ldg(p + 1);
+        b = ulonglong4{s01.x, s01.y, s23.x, s23.y};
+    }
+}
 template <class A, class Load>
 __device__ __forceinline__ bool names_probe(const NamesView& nv, A a, uint32_t len, Load load, uint64_t h) {
     return names_probe_from(nv, a, len, load, h, names_load_bucket(nv, h));

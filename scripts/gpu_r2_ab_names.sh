@@ -1,0 +1,5 @@
+#!/bin/bash
+for so in "" $(ls fqgrep_b200/libfqgrep_b200_*.so 2>/dev/null); do
+  echo "${so:-default}: $(FQG_LIB_VARIANT=${so:+$PWD/$so} timeout 300 python scripts/prof_names_soa.py 2>&1 | tail -1 | cut -c1-220)"
+  echo "${so:-default}: $(FQG_LIB_VARIANT=${so:+$PWD/$so} timeout 300 python scripts/prof_names.py 2>&1 | tail -1 | cut -c1-220)"
+done

@@ -131,3 +131,48 @@ def test_paired_files_with_different_read_lengths_stream_in_step():
     g = m.grep_fastq(f1, f2, mode=F.PAIRED)
     e = O.Matcher(O.REGEX_SET, PATS, True, True).grep(f1, f2, mode=O.PAIRED, threads=16)
     assert g["count"] == e["count"] and (g["mask"] == (e["flags"] != 0)).all()
+
+
+def test_one_million_read_names_full_scale():
+    """configs[4]b at its stated size: a read-names file of 1,000,000 ids (matcher.rs:601-639) over 2 M device-generated
+    records -- fused FASTQ kernel, SoA name kernel and oracle agree on every bit; ids of three lengths (11, 23 and 36
+    bytes: the last two go past the 12 bytes a pool entry's first read covers)."""
+    import torch
+    L = _ffi.lib()
+    ctx = F.context(0)
+    dev = torch.device("cuda:0")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n = 2_000_000
+    rng = np.random.default_rng(11)
+    chosen = np.sort(rng.choice(n, 600_000, replace=False))
+    names = ["r%010d" % i for i in chosen] + ["r%010d" % (n + i) for i in range(400_000)]
+    assert len(names) == 1_000_000
+    m = F.Matcher(F.NAMES, names)
+    fq = _gen(torch, n, 1, 99, 1)
+    nbytes = n * (2 * RL + 17)
+    words = n // 32 + 2
+    dm = torch.zeros(words, dtype=torch.int32, device=dev)
+    res = _ffi.Result()
+    rc = L.fqg_grep_fastq_device(ctx, m._h, F.SINGLE, fq.data_ptr(), nbytes, None, 0, dm.data_ptr(), words, C.byref(res), sp)
+    assert rc == 0, _ffi.last_error()
+    want = np.zeros(n, dtype=bool)
+    want[chosen] = True
+    got = np.unpackbits(dm.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert res.n_units == n and res.n_selected == chosen.size and (got == want).all()
+    host = fq[:nbytes].cpu().numpy()
+    e = O.Matcher(O.NAMES, names, False, False).grep(host, threads=16)
+    assert e["count"] == chosen.size and ((e["flags"] != 0) == want).all()
+    # SoA name kernel over the header lines (ids back to back + u32 offsets)
+    ids = np.frombuffer(("".join("r%010d" % i for i in range(200_000))).encode(), dtype=np.uint8)
+    offs = np.arange(200_001, dtype=np.uint64) * 11
+    bits, count = m.match_bases(ids, offs)
+    assert count == int(want[:200_000].sum()) and (bits == want[:200_000]).all()
+    # longer ids, with and without a comment after the id
+    long_names = ["A00123:45:HXXXXDSXX:1:1101:%07d" % i for i in range(0, 300_000, 3)] + ["read_with_a_23_byte_%03d" % i for i in range(0, 1000, 2)]
+    ml = F.Matcher(F.NAMES, long_names)
+    heads = ["A00123:45:HXXXXDSXX:1:1101:%07d 1:N:0:ACGT" % i for i in range(40_000)] + ["read_with_a_23_byte_%03d" % i for i in range(1000)]
+    from tests.fq_util import fastq
+    data = fastq(["ACGT"] * len(heads), heads=heads)
+    g = ml.grep_fastq(data)
+    el = O.Matcher(O.NAMES, long_names, False, False).grep(data, threads=8)
+    assert g["count"] == el["count"] == (40_000 + 2) // 3 + 500 and (g["mask"] == (el["flags"] != 0)).all()
