@@ -103,12 +103,15 @@ __device__ __forceinline__ uint32_t lds_u16_volatile(uint32_t a) {
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
-// atomicAdd whose result is NOT consumed on the spot: the compiler turns a one-lane atomicAdd() into its warp-aggregated
-// form and shuffles the result out immediately, i.e. waits for the round trip right there; written as PTX the value is only
-// waited for where it is used.
+// Tile claim whose result is NOT consumed on the spot.  A one-lane atomicAdd() on a warp-uniform address -- also as inline
+// `atom.global.add` or `atom.global.inc` -- is turned by ptxas into its warp-aggregated form (leader election, ATOMG, then
+// a SHFL of the result to all lanes right behind it), i.e. the warp waits for the round trip at the claim: 4.6 % of all
+// stall samples sat on that SHFL (profiles/r3o_*).  The address below is the counter plus threadIdx.y (always 0: the blocks
+// are one-dimensional), which ptxas has to treat as per-thread: no aggregation, and the value is only waited for where
+// take_next() reads it, a walk later (+0.5 %).
 __device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
     uint32_t r;
-    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p + threadIdx.y), "r"(v) : "memory");
     return r;
 }
 // store only where `on` is non-zero -- as a PREDICATED store, not a branch around one
@@ -194,6 +197,8 @@ struct RecordEval {
         if (head_end > s + 1 && lds_u8_volatile(tile + head_end - 1) == '\r') head_end--;
         uint32_t id_len = 0;
         if (TIER == 3 || want_idh) {      // id = header up to the first space; scanned and hashed four bytes at a time
+            // (a loop-free variant for ids that end within 16 bytes -- five words read together, cut, masked, hashed -- costs ten
+            // more live registers than the kernel has: measured 0.592 -> 0.564 paired, 0.385 -> 0.305 for read names)
             // (a malformed record may "start" on an empty line: p0 == s, no header bytes at all)
             const uint32_t a0 = tile + s + 1u, n = head_end > s + 1u ? head_end - (s + 1u) : 0u, sh = (a0 & 3u) * 8u;
             uint32_t wp = a0 & ~3u, w0 = lds_u32_volatile(wp);
