@@ -638,8 +638,15 @@ __device__ __noinline__ uint32_t dense_tile(const FastqArgs& a, const RecordEval
 // ---- the kernel ---------------------------------------------------------------------------------------------------------
 // Every warp of the grid is a tile warp, except the last warp of CTA 0: that one is the scan warp (see Lookback) and owns
 // no tiles.  (An extra warp per CTA for it would push the CTA past 512 threads and cost every thread 32 registers.)
-template <int TIER>
-__global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(FastqArgs a, DeviceDfa dfa, uint32_t table_smem_bytes) {
+// FEAT: which per-record outputs beside the mask the launch asks for -- bit 0 the 64-bit id hashes (paired / interleaved
+// input), bit 1 any of the record index / spans (seq_start, soa_start, rec_off).  They are compiled out where they are not
+// wanted: the kernel runs at 118-124 of its 128 registers, and results that wait a tile for their commit (step 7) keep every
+// output field alive across the next tile's scan.
+template <int TIER, int FEAT>
+__global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(FastqArgs a_in, DeviceDfa dfa, uint32_t table_smem_bytes) {
+    FastqArgs a = a_in;
+    if (!(FEAT & 1)) { a.id_hash = nullptr; a.id_hash_cap = 0; }
+    if (!(FEAT & 2)) { a.seq_start = nullptr; a.seq_len = nullptr; a.soa_start = nullptr; a.soa_end = nullptr; a.rec_off = nullptr; a.rec_len = nullptr; }
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, cta_warps = blockDim.x >> 5;
 
@@ -1047,7 +1054,8 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& args, int sm_c
     }
     if (a.scan_warp && warps < 2u && kMaxTileWarps >= 2u && need < 2u * (uint32_t)sm_count) warps = need < 2u ? 2u : warps;
     const uint32_t smem = table_smem + 256u + kEtabBytes<TIER> + warps * kWarpBytes;
-    auto kern = match_fastq_kernel<TIER>;
+    const int feat = (a.id_hash ? 1 : 0) | ((a.seq_start || a.soa_start || a.rec_off) ? 2 : 0);
+    auto kern = feat == 0 ? match_fastq_kernel<TIER, 0> : feat == 1 ? match_fastq_kernel<TIER, 1> : feat == 2 ? match_fastq_kernel<TIER, 2> : match_fastq_kernel<TIER, 3>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     uint32_t grid = (need + warps - 1u) / warps;
