@@ -413,9 +413,13 @@ int lane_wait(fqg_ctx* c, FastqLane* L, BatchOut* out) {
     const int mode = in.mode;
     const int n_streams = mode == FQG_PAIRED ? 2 : 1;
     const unsigned long long* h_ctl = (const unsigned long long*)L->h[H_CTL];
-    if (L->stats)
-        std::fprintf(stderr, "[fqg] fused kernel: %llu tiles, %llu with a guessed line phase (%llu guessed wrong), %llu dense; of %llu warp-cycles %.1f %% waited for the copy, %.1f %% for the prefix (%.1f %% on the scan warp's word)\n",
-                     h_ctl[8] + h_ctl[11], h_ctl[9], h_ctl[10], h_ctl[11], h_ctl[14], h_ctl[14] ? 100.0 * h_ctl[12] / h_ctl[14] : 0.0, h_ctl[14] ? 100.0 * h_ctl[13] / h_ctl[14] : 0.0, h_ctl[14] ? 100.0 * h_ctl[15] / h_ctl[14] : 0.0);
+    if (L->stats) {
+        std::fprintf(stderr, "[fqg] fused kernel: %llu tiles, %llu with a guessed line phase (%llu guessed wrong), %llu dense", h_ctl[8] + h_ctl[11], h_ctl[9], h_ctl[10], h_ctl[11]);
+        if (h_ctl[14])      // only a FQG_FASTQ_TIMING build counts cycles
+            std::fprintf(stderr, "; of %llu warp-cycles %.1f %% waited for the copy, %.1f %% for the prefix (%.1f %% on the scan warp's word)", h_ctl[14],
+                         100.0 * h_ctl[12] / h_ctl[14], 100.0 * h_ctl[13] / h_ctl[14], 100.0 * h_ctl[15] / h_ctl[14]);
+        std::fprintf(stderr, "\n");
+    }
     fqg_result* res = &out->res;
     uint64_t d2h_bytes = 64 + L->eager_mask_words * 4;
 

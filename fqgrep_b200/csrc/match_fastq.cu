@@ -52,6 +52,12 @@ namespace {
 #ifndef FQG_ETAB
 #define FQG_ETAB 0
 #endif
+// FQG_FASTQ_TIMING=1 (a variant build, build.build_variant): per-warp cycle counters around the two places a warp can wait --
+// the tile's copy and the prefix -- reported through FQG_FASTQ_STATS.  Off in the product build: the four 64-bit accumulators
+// would stay live across the whole tile loop of a kernel that has no register to spare.
+#ifndef FQG_FASTQ_TIMING
+#define FQG_FASTQ_TIMING 0
+#endif
 #ifndef FQG_EARLY_ISSUE
 #define FQG_EARLY_ISSUE 1
 #endif
@@ -328,7 +334,7 @@ __device__ __forceinline__ unsigned long long lookback_resolve(const Lookback& l
     const uint32_t own = __reduce_add_sync(kFullMask, mine ? (st & 0x7FFFFFFFu) : 0u);
     unsigned long long p = 0;
     if (t >> 5) {
-        const long long t0 = t_seg ? clock64() : 0;
+        const long long t0 = (FQG_FASTQ_TIMING && t_seg) ? clock64() : 0;
         p = pre.seg;
         // (Falling back, on a miss, to the nearest published prefix among the last four segments plus the complete seg_acc
         // sums in front of it was measured twice: the code costs the match kernel 8 registers it does not have -- spills in
@@ -338,7 +344,7 @@ __device__ __forceinline__ unsigned long long lookback_resolve(const Lookback& l
             p = ld_volatile_u64(lb.seg_pre + ((t >> 5) - 1u));
         }
         p &= kLbValue;
-        if (t_seg) *t_seg += clock64() - t0;
+        if (FQG_FASTQ_TIMING && t_seg) *t_seg += clock64() - t0;
     }
     return p + own;
 }
@@ -684,7 +690,8 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
     const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
     uint32_t phase = 0;
     unsigned long long local_count = 0;
-    long long t_copy = 0, t_prefix = 0, t_seg = 0, t_all = a.stats ? clock64() : 0;      // measurement hook (FQG_FASTQ_STATS): cycles spent waiting
+    const bool timing = FQG_FASTQ_TIMING && a.stats;      // measurement hook: cycles spent waiting (see FQG_FASTQ_TIMING)
+    long long t_copy = 0, t_prefix = 0, t_seg = 0, t_all = timing ? clock64() : 0;
 
     // Tiles are claimed in order from an atomic counter.  (Dealing them out statically -- warp w takes tiles w, w + W, ... --
     // saves the atomic but was measured slower: warps do not run at the same speed (the issue arbiter prefers high warp ids,
@@ -719,9 +726,9 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
     auto complete_pending = [&]() {
         if (!pend) return;
         pend = false;
-        const long long t0 = a.stats ? clock64() : 0;
-        const unsigned long long Lp = lookback_resolve(lb, p_t, lane, p_pre, a.stats ? &t_seg : nullptr);
-        if (a.stats) t_prefix += clock64() - t0;
+        const long long t0 = timing ? clock64() : 0;
+        const unsigned long long Lp = lookback_resolve(lb, p_t, lane, p_pre, timing ? &t_seg : nullptr);
+        if (timing) t_prefix += clock64() - t0;
         if (3u - (uint32_t)(Lp & 3ull) != p_j0) {      // damaged input only
             if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
             local_count += redo_tile_global<TIER>(a, ev, c, p_t, Lp, lane);
@@ -756,10 +763,10 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         // round trip) -- and consumed in step 7, after this tile's bytes have been scanned.
         if (pend) p_pre = lookback_prefetch(lb, p_t, lane);
         if (g.real_avail) {
-            const long long t0 = a.stats ? clock64() : 0;
+            const long long t0 = timing ? clock64() : 0;
             mbar_wait(bar, phase);       // try_wait suspends the warp in hardware; no issue slots are burnt
             phase ^= 1u;
-            if (a.stats) t_copy += clock64() - t0;
+            if (timing) t_copy += clock64() - t0;
         }
 
         // ---- 2. newline masks of this lane's 336 bytes, in registers
@@ -975,7 +982,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
     }
     complete_pending();
     if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
-    if (a.stats && lane == 0) {
+    if (timing && lane == 0) {
         atomicAdd(a.stats + 4, (unsigned long long)t_copy);
         atomicAdd(a.stats + 5, (unsigned long long)t_prefix);
         atomicAdd(a.stats + 7, (unsigned long long)t_seg);
