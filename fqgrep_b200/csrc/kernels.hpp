@@ -104,6 +104,7 @@ struct FastqArgs {
     // needs two constants per LOP3 and the instruction takes one immediate: as literals (even behind an asm mov, which
     // ptxas folds) every byte-test costs five instructions per word; as constant-bank operands it costs three.
     uint32_t nl_xor, nl_low7;
+    uint32_t full_tiles;            // filled in by the launcher: tiles [0, full_tiles) are whole (tile + overlap inside the real bytes)
     uint32_t scan_warp;             // filled in by the launcher: 1 when the last warp of CTA 0 is the scan warp of this launch (match_fastq.cu, Lookback)
     unsigned long long* stats;      // optional (FQG_FASTQ_STATS): [0] tiles, [1] line phase guessed, [2] guessed wrong, [3] dense tiles
 };

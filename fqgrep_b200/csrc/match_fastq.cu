@@ -267,6 +267,10 @@ __device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, ui
     TileGeom g;
     g.t = t;
     g.T0 = (uint64_t)t * kTile;
+    if (t < a.full_tiles) {      // all but the last one or two tiles of a stream: no 64-bit arithmetic
+        g.avail = kLoad; g.region = kTile; g.real_avail = kLoad;
+        return g;
+    }
     const uint64_t remaining = stream_len - g.T0;
     g.avail = remaining < kLoad ? (uint32_t)remaining : kLoad;
     g.region = remaining < kTile ? (uint32_t)remaining : kTile;
@@ -274,9 +278,9 @@ __device__ __forceinline__ TileGeom tile_geom(const FastqArgs& a, uint32_t t, ui
     g.real_avail = real_left < kLoad ? (uint32_t)real_left : kLoad;
     return g;
 }
-
 // real bytes of tile t that a copy has to bring in (0: the tile holds nothing but the virtual final newline)
 __device__ __forceinline__ uint32_t tile_real_avail(const FastqArgs& a, uint32_t t) {
+    if (t < a.full_tiles) return kLoad;
     const uint64_t T0 = (uint64_t)t * kTile;
     const uint64_t left = a.nbytes > T0 ? a.nbytes - T0 : 0;
     return left < kLoad ? (uint32_t)left : kLoad;
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
     const uint32_t c0a = a.nl_xor, c7f = a.nl_low7;     // see FastqArgs: not compile-time constants on purpose
     const uint32_t lane_pos = lane * kLaneBytes;       // this lane's first byte in the staged tile
     uint32_t phase = 0;
-    unsigned long long local_count = 0;
+    uint32_t local_count = 0;      // (a stream holds fewer than 2^32 records: <= 4 GiB of at least 8 bytes each)
     const bool timing = FQG_FASTQ_TIMING && a.stats;      // measurement hook: cycles spent waiting (see FQG_FASTQ_TIMING)
     long long t_copy = 0, t_prefix = 0, t_seg = 0, t_all = timing ? clock64() : 0;
 
@@ -981,7 +985,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         }
     }
     complete_pending();
-    if (lane == 0 && local_count && a.count) atomicAdd(a.count, local_count);
+    if (lane == 0 && local_count && a.count) atomicAdd(a.count, (unsigned long long)local_count);
     if (timing && lane == 0) {
         atomicAdd(a.stats + 4, (unsigned long long)t_copy);
         atomicAdd(a.stats + 5, (unsigned long long)t_prefix);
@@ -1054,6 +1058,7 @@ cudaError_t launch_fastq_t(const DeviceDfa& dfa, const FastqArgs& args, int sm_c
     if (warps < 1u) warps = 1u;
     // the scan warp is only there when this launch completes a segment of 32 tiles (see Lookback)
     a.scan_warp = ((a.tile_first + a.tile_count) >> 5) > (a.tile_first >> 5) ? 1u : 0u;
+    a.full_tiles = a.nbytes >= kLoad ? (uint32_t)((a.nbytes - kLoad) / kTile + 1u) : 0u;      // tiles whose tile + overlap lie inside the real bytes
     const uint32_t need = a.tile_count + a.scan_warp;         // warps that find work
     if (need < (uint32_t)sm_count * warps) {                  // small inputs: spread the tiles over the SMs first
         warps = (need + (uint32_t)sm_count - 1u) / (uint32_t)sm_count;
