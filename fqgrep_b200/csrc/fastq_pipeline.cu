@@ -168,10 +168,11 @@ int lane_submit(fqg_ctx* c, FastqLane* L, const fqg_matcher* m, const BatchIn& i
     const bool on_device = in.on_device;
     // Large literal sets (tier 3: q-gram filter, tier 5: split sets) have no table the fused kernel could walk out of shared
     // memory -- their exact automaton lives in L2 and walking it per base runs at 0.04 of the roofline (profiles/r2c_*).  Such
-    // batches are ROUTED: the fused kernel only parses, validates and indexes (K0), the sequence lines are compacted into
-    // SoA form and the SoA kernel with the filter decides (src/lib/matcher.rs:249-251 for every record, as before).
+    // batches are ROUTED: the fused kernel only parses, validates and indexes (K0: u32 start / end of every sequence line), and
+    // the SoA kernel with the filter then reads those lines where they lie in the stream and decides
+    // (src/lib/matcher.rs:249-251 for every record, as before).
     bool route = m && !names && (m->tier == 3 || m->split_lit);
-    for (int i = 0; i < n_streams; i++) if (in.n[i] >= 0xFFF00000ull) route = false;      // u32 offsets of the compacted bases
+    for (int i = 0; i < n_streams; i++) if (in.n[i] >= 0xFFF00000ull) route = false;      // the index holds u32 offsets into the stream
     if (on_device)
         for (int i = 0; i < n_streams; i++)
             if (reinterpret_cast<uintptr_t>(in.r[i]) & 15u) return fail(FQG_E_INVALID_ARG, "device FASTQ buffers must be 16-byte aligned");

@@ -75,9 +75,9 @@ struct FastqArgs {
     uint32_t virtual_final_nl;     // 1: treat offset nbytes as a newline
     uint32_t tile_first, tile_count;   // this launch handles global tiles [tile_first, tile_first + tile_count)
     uint32_t* tile_counter;        // zeroed, one per launch
-    unsigned long long* tile_state;    // zeroed, one per global tile of the stream (look-back state)
+    unsigned long long* tile_state;    // zeroed, one slot per global tile of the stream (used as u32: 0x80000000 | the tile's newline count)
     unsigned long long* seg_acc;       // zeroed, one per segment of 32 consecutive tiles: tiles reported << 48 | their newlines
-    unsigned long long* seg_pre;       // zeroed, one per segment: inclusive prefix at its end once known (match_fastq.cu, Lookback)
+    unsigned long long* seg_pre;       // zeroed, one per segment: 2 << 62 | newlines up to its end, written by the scan warp (match_fastq.cu, Lookback)
     unsigned long long* lines_out;     // total newline count, written by the stream's last tile
     uint32_t* mask;                // zeroed record bitmask, bit = global record number
     uint64_t mask_bits;
