@@ -17,7 +17,7 @@ L = _ffi.lib()
 dev = torch.device("cuda:0")
 ctx = F.context(0)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-n = 4_000_000
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 rng = np.random.default_rng(7)
 pats = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(10_000)]
 blob = "".join(pats[:200]).encode()
