@@ -143,6 +143,11 @@ __device__ __noinline__ uint32_t walk_shared_bytes(const DfaView<TIER>& d, uint3
     return st;
 }
 
+#ifndef FQG_WALK_UNROLL
+#define FQG_WALK_UNROLL 4
+#endif
+constexpr int kWalkUnroll = FQG_WALK_UNROLL;      // words of the read per trip of the walk loop
+
 // walk `len` bytes starting at shared address p (any alignment)
 // SETTLE: leave the walk once the state is the dead or the all-accepting one (only instantiated where the automaton
 // has a dead state: the check costs a crossbar-bound loop like tier 4's 20 % when it sits there unused)
@@ -153,7 +158,7 @@ __device__ __forceinline__ uint32_t walk_shared_impl(const DfaView<TIER>& d, uin
     uint32_t w0 = lds_u32_volatile(wp);
     const uint32_t nw = len >> 2;
     uint32_t st = st0, bad = 0;
-#pragma unroll 4
+#pragma unroll kWalkUnroll
     for (uint32_t k = 0; k < nw; k++) {
         wp += 4;
         const uint32_t w1 = lds_u32_volatile(wp);

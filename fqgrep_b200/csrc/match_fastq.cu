@@ -58,6 +58,10 @@ namespace {
 #ifndef FQG_FASTQ_TIMING
 #define FQG_FASTQ_TIMING 0
 #endif
+// FQG_FASTQ_COUNTERS=0 compiles the tile statistics of FQG_FASTQ_STATS (tiles, guessed / wrongly guessed phases, dense tiles) out
+#ifndef FQG_FASTQ_COUNTERS
+#define FQG_FASTQ_COUNTERS 1
+#endif
 #ifndef FQG_EARLY_ISSUE
 #define FQG_EARLY_ISSUE 1
 #endif
@@ -734,7 +738,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         const unsigned long long Lp = lookback_resolve(lb, p_t, lane, p_pre, timing ? &t_seg : nullptr);
         if (timing) t_prefix += clock64() - t0;
         if (3u - (uint32_t)(Lp & 3ull) != p_j0) {      // damaged input only
-            if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+            if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
             local_count += redo_tile_global<TIER>(a, ev, c, p_t, Lp, lane);
         } else {
             local_count += commit_records(a, (uint64_t)p_t * kTile, c.want_idh, po, p_valid, (Lp + p_j0 + 1ull) >> 2, lane);
@@ -815,7 +819,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         lookback_publish(lb, g.t, agg, lane);
         const LookbackPre no_pre{0u, 0ull};
 
-        if (a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
+        if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + (total > kListCap ? 3 : 0), 1ull);
         if (total > kListCap) {
             complete_pending();
             const unsigned long long Lt = lookback_resolve(lb, g.t, lane, no_pre);
@@ -882,7 +886,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 if (both && (both & (both - 1u)) == 0) {
                     guessed = true;
                     j0 = (uint32_t)__ffs((int)both) - 1u;
-                    if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
+                    if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
                     if (TIER == 3) pre = lookback_prefetch(lb, g.t, lane);      // read names settle their tile at once, see step 6
                 }
             }
@@ -924,7 +928,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                     have_Lt = true;
                     claim_next();
                     if (3u - (uint32_t)(Lt & 3ull) != j0) {
-                        if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                        if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
                         local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
                     } else {
                         finish_names<TIER>(ev, o);
@@ -958,7 +962,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                     Lt = lookback_resolve(lb, g.t, lane, pre);
                     have_Lt = true;
                     if (3u - (uint32_t)(Lt & 3ull) != j0) {
-                        if (a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                        if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
                         local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
                         redone = true;
                     } else ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
