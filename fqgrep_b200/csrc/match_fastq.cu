@@ -727,6 +727,10 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
         }
     };
     // Results of the previous tile that still wait for their global record numbers (see step 7 in the loop).
+    // (Short reads put more than 32 records into a tile.  Letting every lane take a second record and deferring tiles of up to
+    // 64 records was built and measured: the second set of pending results spills -- 150-base reads 0.63 -> 0.40, 100-base
+    // reads 0.39 -> 0.32.  Such tiles are settled at once, after their prefix is resolved and before the next claim.)
+    constexpr uint32_t kDeferMax = 32u;
     bool pend = false, p_valid = false, p_last = false;
     RecOut po;
     uint32_t p_t = 0, p_agg = 0, p_j0 = 0;
@@ -901,13 +905,13 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 have_Lt = true;
                 j0 = 3u - (uint32_t)(Lt & 3ull);
             }
-            // (the claim must not be outstanding while the warp waits for other tiles: read names and guesses that cover more
-            // than 32 records resolve their prefix below and claim after that)
-            if (have_Lt || TIER != 3) claim_next();
             // ---- 6. one lane per record that starts in the tile
             const bool last_tile = g.T0 + g.region == stream_len;
             TilePhase ph = tile_phase(g, j0, Lt, agg, stream_len);
-            if (!have_Lt && ph.n_list <= 32u) {
+            // The claim must not be outstanding while the warp waits for other tiles: read names, and guesses that cover more
+            // than 32 records (short reads), resolve their prefix below and claim right after that.
+            if (have_Lt || (TIER != 3 && ph.n_list <= kDeferMax)) claim_next();
+            if (!have_Lt && ph.n_list <= kDeferMax) {
                 // the usual case: a guessed phase and at most one record per lane.  Evaluate, hand the buffer to the next
                 // tile's copy, keep the results for step 7.
                 const bool valid = lane < ph.n_list;
@@ -957,16 +961,11 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 p_pre = LookbackPre{0u, 0ull};      // requested at the top of the next iteration (or polled, after the last tile)
                 }
             } else {
+                // Known prefix (first tile, no usable guess), or a guess that covers more than 32 records (short reads).  In the
+                // second case the prefix is only asked for here and resolved inside the loop, after the first 32 records have
+                // been evaluated -- their walk is what the request hides behind; nothing is committed before the guess holds.
                 bool redone = false;
-                if (!have_Lt) {      // a guess, but more than 32 records start in the tile: confirm it now
-                    Lt = lookback_resolve(lb, g.t, lane, pre);
-                    have_Lt = true;
-                    if (3u - (uint32_t)(Lt & 3ull) != j0) {
-                        if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
-                        local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
-                        redone = true;
-                    } else ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
-                }
+                if (!have_Lt) pre = lookback_prefetch(lb, g.t, lane);
                 for (uint32_t k0 = 0; !redone && k0 < ph.n_list; k0 += 32u) {
                     const uint32_t k = k0 + lane;
                     const uint32_t qa = k < ph.extra ? 0u : ph.j0 + 4u * (k - ph.extra);
@@ -976,8 +975,24 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                         const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
                         o = eval_record<TIER>(a, ev, c, s, k < ph.extra ? 0u : qa + 1u, 0u);
                     }
+                    if (!have_Lt) {
+                        Lt = lookback_resolve(lb, g.t, lane, pre);
+                        have_Lt = true;
+                        claim_next();      // (only now: the warp must not wait while it holds a tile it has not started)
+                        if (3u - (uint32_t)(Lt & 3ull) != j0) {
+                            if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                            local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
+                            redone = true;
+                            break;
+                        }
+                        ph = tile_phase(g, j0, Lt, agg, stream_len);      // same records, now with their global numbers
+                    }
                     finish_names<TIER>(ev, o);
                     local_count += commit_records(a, c.T0, c.want_idh, o, valid, ph.R_base + k0, lane);
+                }
+                if (!have_Lt) {      // (a guess always covers two records, so the loop ran; kept for symmetry)
+                    Lt = lookback_resolve(lb, g.t, lane, pre);
+                    have_Lt = true;
                 }
                 if (lane == 0 && last_tile) *a.lines_out = Lt + agg;
             }
