@@ -8,6 +8,8 @@ A "step" is one pass of the hot path over all pairs a rank owns.
   value        Gbases/s, reads resident in HBM as SoA bases + u32 offsets (device-event timed, max over ranks)
   roofline     match_soa kernel: algorithmic bytes (154.125 B/read) / measured launch time vs MEASURED_PEAKS.json hbm_gbs
   raw_fastq_resident   the same pairs as raw FASTQ bytes in HBM through the fused parse+match kernel (325.125 B/record)
+  raw_fastq_read_lengths   the fused kernel on single-end reads of 250 / 100 / 75 / 50 bases (4 M records each), every mask
+               compared bit for bit with the SoA kernel's on the same reads
   configs      every other BASELINE.json config on one GPU (cfg1, cfg3, cfg4, cfg5a, cfg5b + the headline's own parity):
                SoA-resident rate and roofline fraction, raw-FASTQ-resident rate, tier, and parity -- the whole device mask
                of the first 2 M reads against the oracle, and the SoA kernel against the fused FASTQ kernel bit for bit
@@ -156,15 +158,15 @@ class Env:
         self.sp = C.c_void_p(self.stream.cuda_stream)
         self.peak, self.peak_src = peaks()
 
-    def synth(self, n, first, seed, plant, rate, pseed, fastq):
+    def synth(self, n, first, seed, plant, rate, pseed, fastq, read_len=READ_LEN):
         """n synthetic reads starting at read index `first`, generated in HBM (SoA bases or 317-byte FASTQ records)."""
         blob = "".join(plant).encode()
         offs = np.zeros(len(plant) + 1, dtype=np.uint32)
         if plant:
             offs[1:] = np.cumsum([len(p) for p in plant])
-        rec = FASTQ_BYTES_PER_READ if fastq else READ_LEN
+        rec = (2 * read_len + 17) if fastq else read_len
         t = self.torch.empty(n * rec + 64, dtype=self.torch.uint8, device=self.dev)
-        rc = self.L.fqg_synth_reads_device(self.ctx, t.data_ptr(), n, first, READ_LEN, int(fastq), seed, blob, offs.ctypes.data_as(C.c_void_p), len(plant),
+        rc = self.L.fqg_synth_reads_device(self.ctx, t.data_ptr(), n, first, read_len, int(fastq), seed, blob, offs.ctypes.data_as(C.c_void_p), len(plant),
                                            rate, pseed, self.sp)
         assert rc == 0, self.ffi.last_error()
         return t
@@ -316,6 +318,7 @@ def main():
 
     # ---- second resident layout: raw FASTQ bytes in HBM through the fused parse+match kernel (SURVEY 8(d), 2nd roofline column)
     raw = None if args.no_raw else guarded(lambda: run_raw_fastq(env, matcher))
+    read_lengths = guarded(lambda: run_read_lengths(env, matcher)) if (world == 1 and not args.no_raw and not args.no_configs) else None
     torch.cuda.empty_cache()
 
     # ---- every other BASELINE config, one GPU
@@ -348,7 +351,7 @@ def main():
             "config": {"workload": "configs[1]: --paired -e GACGAGATTA -e GACGTGATTA --reverse-complement, %d pairs x 150bp per GPU" % n_pairs,
                        "layout": "SoA bases + u32 offsets resident in HBM (%.1f GB per GPU, >> 126 MB L2, no L2 flush needed)" % (bases_per_step_rank / 1e9),
                        "pairs_per_gpu": n_pairs, "selected_pairs_rank0": selected, "parallelism": "shard%d" % world},
-            "roofline": roofline, "raw_fastq_resident": raw, "configs": configs, "h2d_probe": probe, "e2e": e2e, "e2e_write": e2e_write,
+            "roofline": roofline, "raw_fastq_resident": raw, "raw_fastq_read_lengths": read_lengths, "configs": configs, "h2d_probe": probe, "e2e": e2e, "e2e_write": e2e_write,
             "sharded": sharded, "sharded_parity_ok": bool(isinstance(sharded, dict) and sharded.get("parity_ok")),
             "one_process_multi_gpu": multi, "cpu_baseline": cpu, "gpu_launches": int(launches_timed), "clocks": clocks,
         }
@@ -580,6 +583,39 @@ def run_raw_fastq(env, matcher):
             "roofline": {"bound": "hbm", "kernel": "match_fastq_kernel<tier0> (warp-autonomous tiles)", "algorithmic_bytes_per_record": FASTQ_ALGO_BYTES,
                          "achieved": gbs, "peak": env.peak, "unit": "GB/s", "frac": gbs / env.peak,
                          "note": "whole call (memsets + 2 fused kernels + combine) over device events; kernel share in profiles/"}}
+
+
+def run_read_lengths(env, matcher, lengths=(250, 100, 75, 50), n=4_000_000):
+    """The fused kernel away from the benchmark's 150 bases: single-end, HBM-resident, each length with the SoA kernel's mask
+    of the same reads as the check (bit for bit).  Below ~130 bases a tile holds more than one record per lane."""
+    torch, L, ffi = env.torch, env.L, env.ffi
+    out = {}
+    for rl in lengths:
+        rec = 2 * rl + 17
+        fq = env.synth(n, 0, 1, PATTERNS, 0.01, 99, fastq=True, read_len=rl)
+        words = n // 32 + 2
+        fmask = torch.zeros(words, dtype=torch.int32, device=env.dev)
+        res = ffi.Result()
+        kms = []
+        for _ in range(4):
+            rc = L.fqg_grep_fastq_device(env.ctx, matcher._h, 0, fq.data_ptr(), n * rec, None, 0, fmask.data_ptr(), words, C.byref(res), env.sp)
+            if rc != 0:
+                raise RuntimeError(ffi.last_error())
+            kms.append(res.kernel_ms)
+        del fq
+        tb = env.synth(n, 0, 1, PATTERNS, 0.01, 99, fastq=False, read_len=rl)
+        offs = (torch.arange(n + 1, dtype=torch.int64, device=env.dev) * rl).to(torch.int32)
+        smask = torch.zeros(words, dtype=torch.int32, device=env.dev)
+        rc = L.fqg_match_bases_device(env.ctx, matcher._h, tb.data_ptr(), offs.data_ptr(), offs.data_ptr() + 4, n, smask.data_ptr(), None, None, rl, env.sp)
+        if rc != 0:
+            raise RuntimeError(ffi.last_error())
+        torch.cuda.synchronize()
+        fms = float(np.mean(kms[1:]))
+        out["%d" % rl] = {"records": n, "record_bytes": rec, "ms_per_pass": fms, "gbases_s": n * rl / (fms / 1e3) / 1e9,
+                          "roofline_frac": (rec + 8.125) * n / (fms / 1e3) / 1e9 / env.peak, "selected": int(res.n_selected),
+                          "fastq_eq_soa_ok": bool(torch.equal(fmask[: n // 32], smask[: n // 32]))}
+        del tb, offs
+    return out
 
 
 # ---- host-memory legs ---------------------------------------------------------------------------------------------------
