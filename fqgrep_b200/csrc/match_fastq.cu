@@ -965,7 +965,18 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                 // second case the prefix is only asked for here and resolved inside the loop, after the first 32 records have
                 // been evaluated -- their walk is what the request hides behind; nothing is committed before the guess holds.
                 bool redone = false;
-                if (!have_Lt) pre = lookback_prefetch(lb, g.t, lane);
+                if (!have_Lt) {
+                    if (TIER == 3) {      // read names: resolved up front (their lookups are finished inside the loop)
+                        Lt = lookback_resolve(lb, g.t, lane, pre);
+                        have_Lt = true;
+                        claim_next();
+                        if (3u - (uint32_t)(Lt & 3ull) != j0) {
+                            if (FQG_FASTQ_COUNTERS && a.stats && lane == 0) atomicAdd(a.stats + 2, 1ull);
+                            local_count += redo_tile_global<TIER>(a, ev, c, g.t, Lt, lane);
+                            redone = true;
+                        } else ph = tile_phase(g, j0, Lt, agg, stream_len);
+                    } else pre = lookback_prefetch(lb, g.t, lane);
+                }
                 for (uint32_t k0 = 0; !redone && k0 < ph.n_list; k0 += 32u) {
                     const uint32_t k = k0 + lane;
                     const uint32_t qa = k < ph.extra ? 0u : ph.j0 + 4u * (k - ph.extra);
@@ -975,7 +986,7 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
                         const uint32_t s = k < ph.extra ? 0u : lds_u16_volatile(list_sa + 2u * qa) + 1u;
                         o = eval_record<TIER>(a, ev, c, s, k < ph.extra ? 0u : qa + 1u, 0u);
                     }
-                    if (!have_Lt) {
+                    if (TIER != 3 && !have_Lt) {
                         Lt = lookback_resolve(lb, g.t, lane, pre);
                         have_Lt = true;
                         claim_next();      // (only now: the warp must not wait while it holds a tile it has not started)
