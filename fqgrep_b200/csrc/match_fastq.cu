@@ -729,7 +729,9 @@ __global__ void __launch_bounds__(kMaxTileWarps * 32u, 1) match_fastq_kernel(Fas
     // Results of the previous tile that still wait for their global record numbers (see step 7 in the loop).
     // (Short reads put more than 32 records into a tile.  Letting every lane take a second record and deferring tiles of up to
     // 64 records was built and measured: the second set of pending results spills -- 150-base reads 0.63 -> 0.40, 100-base
-    // reads 0.39 -> 0.32.  Such tiles are settled at once, after their prefix is resolved and before the next claim.)
+    // reads 0.39 -> 0.32; a compact form that keeps only the second record's selected bit and id hash, evaluated in a
+    // two-trip loop, loses as well: 0.61 -> 0.50 and 0.44 -> 0.41.  Such tiles are settled at once, after their prefix is
+    // resolved and before the next claim.)
     constexpr uint32_t kDeferMax = 32u;
     bool pend = false, p_valid = false, p_last = false;
     RecOut po;
