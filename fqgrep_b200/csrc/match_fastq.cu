@@ -1190,7 +1190,9 @@ __global__ void scan_offsets_kernel(const uint32_t* len, uint64_t n, const uint3
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanBlock - 1) offsets[n] = block_sums[gridDim.x];      // blocks past a device-side n add nothing
 }
-// one warp per record: contiguous byte copy of its sequence line
+// one warp per record: its sequence line moves as ALIGNED 32-bit words of the destination -- every lane assembles its word from
+// two aligned words of the source (the two are not aligned alike in general) -- with single bytes only in front of the first
+// aligned word and behind the last one.  (A byte per lane and trip moved 32 bytes per warp instruction: 1.3 TB/s.)
 __global__ void gather_bases_kernel(const uint8_t* fastq, const unsigned long long* seq_start, const uint32_t* seq_len, uint64_t n,
                                     const uint32_t* offsets, uint8_t* out, const unsigned long long* lines_dev) {
     n = records_on_device(n, lines_dev);
@@ -1200,7 +1202,20 @@ __global__ void gather_bases_kernel(const uint8_t* fastq, const unsigned long lo
         const uint8_t* src = fastq + seq_start[r];
         uint8_t* dst = out + offsets[r];
         const uint32_t L = seq_len[r];
-        for (uint32_t i = lane; i < L; i += 32u) dst[i] = src[i];
+        uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;      // bytes in front of the first aligned word
+        if (head > L) head = L;
+        if (lane < head) dst[lane] = src[lane];
+        const uint32_t n_words = (L - head) >> 2;
+        const uintptr_t s2 = reinterpret_cast<uintptr_t>(src + head);
+        const uint32_t sh = (uint32_t)(s2 & 3u) * 8u;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 & ~uintptr_t(3));
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+        for (uint32_t i = lane; i < n_words; i += 32u) {
+            const uint32_t lo = sw[i], hi = sh ? sw[i + 1u] : 0u;      // (the stream is readable 16 bytes past its end)
+            dw[i] = __funnelshift_r(lo, hi, sh);
+        }
+        const uint32_t done = head + 4u * n_words;
+        if (lane < L - done) dst[done + lane] = src[done + lane];
     }
 }
 
